@@ -1,0 +1,194 @@
+/*
+ * planedepth_b200 — C ABI of the B200-native photometric-reconstruction path.
+ *
+ * The reference (svip-lab/PlaneDepth) is pure Python on PyTorch and has NO plugin / FFI surface; its
+ * seam for this path is two Python methods plus a dict contract:
+ *     Trainer.pred_novel_images(inputs, outputs)   /root/reference/trainer.py:523-603
+ *     Trainer.compute_losses(inputs, outputs)      /root/reference/trainer.py:701-773
+ * This header is the boundary a binding for that seam talks to (INTEGRATION.md shows the ctypes stub
+ * and the two-line patch to the reference's trainer.py).  Plain pointers and sizes only: no torch /
+ * ATen / pybind types cross this line.  Each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to fp32 unless stated otherwise; tensors are NCHW-contiguous
+ *    unless a pd_strides4 says otherwise (element strides, 0 = broadcast along that dimension);
+ *  - the caller owns every buffer (incl. workspace); the library allocates nothing persistent and
+ *    keeps no global state apart from a thread-local error string;
+ *  - all work is enqueued on the given stream; no entry point synchronises the host;
+ *  - return value: PD_OK (0) or a pd_status error code; never aborts, never throws;
+ *    pd_last_error() returns the message of the last failing call on this thread;
+ *  - outputs are fully overwritten by the call (the library zero-fills scatter targets itself).
+ */
+#ifndef PLANEDEPTH_B200_H
+#define PLANEDEPTH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PD_ABI_VERSION 1
+
+typedef void* pd_stream_t; /* a cudaStream_t */
+
+typedef enum pd_status {
+    PD_OK = 0,
+    PD_ERR_ARG = 1,       /* NULL / inconsistent argument */
+    PD_ERR_SHAPE = 2,     /* unsupported shape (B,N,H,W must be >=1; N <= PD_MAX_PLANES) */
+    PD_ERR_ALIGN = 3,     /* pointer / stride alignment */
+    PD_ERR_ARCH = 4,      /* device is not sm_100 */
+    PD_ERR_CUDA = 5,      /* a CUDA runtime call failed (message in pd_last_error) */
+    PD_ERR_WORKSPACE = 6  /* workspace NULL while pd_*_workspace_bytes() > 0 */
+} pd_status;
+
+#define PD_MAX_PLANES 256
+
+/* trainer.py:533 / 540 / 556 — options.py --warp_type */
+typedef enum pd_warp_type { PD_WARP_DISP = 0, PD_WARP_HOMOGRAPHY = 1, PD_WARP_DEPTH = 2 } pd_warp_type;
+
+/* photometric term: trainer.py:738-742 (L1), 729-736 (Laplacian mixture NLL, layers.py:454-466),
+ * 687-699 + layers.py:276-306 (0.85 SSIM + 0.15 L1 — BASELINE.json north_star) */
+typedef enum pd_loss_mode { PD_LOSS_L1 = 0, PD_LOSS_MIXTURE = 1, PD_LOSS_SSIM_L1 = 2 } pd_loss_mode;
+
+typedef enum pd_mask_dtype { PD_MASK_NONE = 0, PD_MASK_F32 = 1, PD_MASK_U8 = 2 } pd_mask_dtype;
+
+typedef struct pd_strides4 {
+    int64_t b, n, y, x;
+} pd_strides4;
+
+/* ------------------------------------------------------------------------------------------------
+ * Warp + composite: replaces trainer.py:533-603 for ONE target side (grid build, N-plane bilinear
+ * warp of [rgb | logit | sigma], validity mask, softmax / Laplacian-mixture weights, compositing)
+ * without materialising the N warped tensors.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pd_warp_desc {
+    int32_t B, N, H, W;
+    int32_t warp_type;      /* pd_warp_type */
+    int32_t mixture;        /* opt.use_mixture_loss: sigma channel, w = (pi/sigma)/sum, NLL map */
+    int32_t automask;       /* mixture only: also write nll_auto (trainer.py:731-734) */
+    int32_t mask_dtype;     /* pd_mask_dtype of pd_warp_in.mask */
+    float disp_sign;        /* PD_WARP_DISP: +1 target 'r', -1 target 'l', 0 otherwise (trainer.py:545-548) */
+    int32_t reserved0;
+    pd_strides4 disp_stride; /* PD_WARP_DISP / PD_WARP_DEPTH: strides of disp_layered (0 allowed:
+                                depth_decoder.py:156 hands out a stride-0 expand) */
+    pd_strides4 mask_stride; /* strides of padding_mask */
+} pd_warp_desc;
+
+typedef struct pd_warp_in {
+    const float* src;    /* [B,3,H,W] source colour  inputs[(color,"l")]           trainer.py:567 */
+    const float* tgt;    /* [B,3,H,W] target colour; required iff mixture (NLL)    trainer.py:729 */
+    const float* logits; /* [B,N,H,W] outputs["logits"]                           trainer.py:568 */
+    const float* sigma;  /* [B,N,H,W] outputs["sigma"]; required iff mixture      trainer.py:571 */
+    const float* disp;   /* outputs["disp_layered"], strided (DISP / DEPTH)        trainer.py:534,541 */
+    const void* mask;    /* outputs["padding_mask"], strided, mask_dtype; may be NULL (all valid).
+                            Ignored for HOMOGRAPHY (mask computed in-kernel, layers.py:223-226) */
+    const float* hmat;   /* HOMOGRAPHY: [B*N,12] = H_t2s row-major (9, layers.py:220) then R·n (3,
+                            layers.py:223) */
+    const float* cam;    /* HOMOGRAPHY: [B,9] inv_K 3x3 row-major.  DEPTH: [B,21] = inv_K 3x3 (9) then
+                            (K·T)[:3,:] row-major (12)  (layers.py:152,172) */
+} pd_warp_in;
+
+/* Number of per-pixel fp32 statistics saved for the backward pass: [B,PD_STATS(mixture),H,W].
+ * non-mixture: {max logit, sum exp}.  mixture: {max logit, sum exp, sum exp/sigma, mixture density} */
+#define PD_STATS_PLAIN 2
+#define PD_STATS_MIXTURE 4
+
+typedef struct pd_warp_out {
+    float* rgb_rec;  /* [B,3,H,W]   outputs[("rgb_rec", s)]                       trainer.py:603 */
+    float* stats;    /* [B,PD_STATS,H,W] saved for pd_warp_composite_bwd */
+    float* nll;      /* [B,1,H,W] mixture: -log(sum pi*lap + 1e-7)                trainer.py:730 */
+    float* nll_auto; /* [B,1,H,W] mixture+automask: same with err = |src - tgt|   trainer.py:732-733 */
+    /* optional (NULL = not materialised; tests and tensorboard-style consumers only) */
+    float* rgb_rec_layered; /* [B,N,3,H,W]                                        trainer.py:582 */
+    float* logit_rec;       /* [B,N,H,W]                                          trainer.py:583 */
+    float* probability_rec; /* [B,N,H,W]                                          trainer.py:593,602 */
+    float* sigma_rec;       /* [B,N,H,W]                                          trainer.py:598 */
+    float* pi_rec;          /* [B,N,H,W]                                          trainer.py:599 */
+} pd_warp_out;
+
+typedef struct pd_warp_grad_out { /* upstream gradients */
+    const float* g_rgb_rec; /* [B,3,H,W] d loss / d rgb_rec (photometric + perceptual) */
+    const float* g_nll;     /* [B,1,H,W] d loss / d nll map; mixture only, may be NULL (= 0) */
+} pd_warp_grad_out;
+
+typedef struct pd_warp_grad_in { /* produced gradients; any pointer may be NULL (= not needed) */
+    float* g_logits; /* [B,N,H,W] */
+    float* g_sigma;  /* [B,N,H,W] mixture only */
+    float* g_disp;   /* DISP / DEPTH: gradient w.r.t. disp_layered, laid out with g_disp_stride; a 0
+                        stride means "reduce over that dimension" (the transpose of the expand) */
+    pd_strides4 g_disp_stride;
+    float* g_hmat;   /* HOMOGRAPHY: [B*N,9] gradient w.r.t. H_t2s (autograd carries it through
+                        inverse / pose algebra on the host side, layers.py:217-220) */
+} pd_warp_grad_in;
+
+int pd_version(void);
+const char* pd_last_error(void);
+
+size_t pd_warp_composite_workspace_bytes(const pd_warp_desc* desc);
+
+int pd_warp_composite_fwd(const pd_warp_desc* desc, const pd_warp_in* in, pd_warp_out* out,
+                          void* workspace, pd_stream_t stream);
+
+/* Transpose of the above (what autograd replays through trainer.py:573-603: softmax / mixture
+ * weights, mask, ATen grid_sampler_2d_backward incl. the grid gradient, the grid arithmetic). */
+int pd_warp_composite_bwd(const pd_warp_desc* desc, const pd_warp_in* in, const pd_warp_out* saved,
+                          const pd_warp_grad_out* gout, pd_warp_grad_in* gin, void* workspace,
+                          pd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Photometric term of compute_losses for ONE target side: trainer.py:720-742 (+ 687-699 for SSIM).
+ *   pred = rgb_rec*m + tgt*(1-m)            if mask_novel                 trainer.py:724-726
+ *   L1:       ph = mean_c|pred-tgt|  [min with mean_c|src-tgt| if automask]          :738-741
+ *   MIXTURE:  ph = nll [min with nll_auto if automask] [* m]                          :730-736
+ *   SSIM_L1:  ph = 0.85*mean_c SSIM(pred,tgt) + 0.15*mean_c|pred-tgt| [min with the same on src]
+ *   ph_sum = sum_{b,y,x} ph   (the caller divides by B*H*W:  ph_loss.mean(), :742)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pd_loss_desc {
+    int32_t B, H, W;
+    int32_t loss_mode; /* pd_loss_mode */
+    int32_t automask;
+    int32_t has_mask_novel;
+} pd_loss_desc;
+
+typedef struct pd_loss_in {
+    const float* rgb_rec;    /* [B,3,H,W] */
+    const float* tgt;        /* [B,3,H,W] */
+    const float* src;        /* [B,3,H,W] iff automask and loss_mode != MIXTURE */
+    const float* mask_novel; /* [B,1,H,W] iff has_mask_novel */
+    const float* nll;        /* [B,1,H,W] iff MIXTURE */
+    const float* nll_auto;   /* [B,1,H,W] iff MIXTURE && automask */
+} pd_loss_in;
+
+typedef struct pd_loss_out {
+    float* pred;   /* [B,3,H,W] blended prediction; required iff has_mask_novel (else pred == rgb_rec) */
+    float* ph_map; /* [B,1,H,W] optional per-pixel photometric term (NULL = skip) */
+    float* ph_sum; /* [1] */
+} pd_loss_out;
+
+typedef struct pd_loss_grad_out {
+    const float* g_ph_sum; /* [1] device scalar: d loss / d ph_sum */
+    const float* g_pred;   /* [B,3,H,W] d loss / d pred from outside (perceptual term); may be NULL */
+} pd_loss_grad_out;
+
+typedef struct pd_loss_grad_in {
+    float* g_rgb_rec; /* [B,3,H,W] */
+    float* g_nll;     /* [B,1,H,W] MIXTURE only */
+} pd_loss_grad_in;
+
+size_t pd_photometric_workspace_bytes(const pd_loss_desc* desc);
+int pd_photometric_fwd(const pd_loss_desc* desc, const pd_loss_in* in, pd_loss_out* out, void* workspace,
+                       pd_stream_t stream);
+int pd_photometric_bwd(const pd_loss_desc* desc, const pd_loss_in* in, const pd_loss_grad_out* gout,
+                       pd_loss_grad_in* gin, void* workspace, pd_stream_t stream);
+
+/* Introspection for tests / bench: number of kernels the library has launched on this thread since
+ * the last pd_reset_launch_count() (bench.py reports it as gpu_launches). */
+int64_t pd_launch_count(void);
+void pd_reset_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLANEDEPTH_B200_H */

@@ -1,0 +1,159 @@
+"""ctypes binding of the C ABI in include/planedepth_b200.h (the only way Python reaches the CUDA path).
+
+There is deliberately no CPU / PyTorch fallback: if the shared library is missing or a call fails the
+error is raised, so a silent eager path can never stand in for the kernels."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libplanedepth_b200.so")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+]
+
+PD_WARP_DISP, PD_WARP_HOMOGRAPHY, PD_WARP_DEPTH = 0, 1, 2
+PD_LOSS_L1, PD_LOSS_MIXTURE, PD_LOSS_SSIM_L1 = 0, 1, 2
+PD_MASK_NONE, PD_MASK_F32, PD_MASK_U8 = 0, 1, 2
+PD_STATS_PLAIN, PD_STATS_MIXTURE = 2, 4
+
+EXPORTS = [
+    "pd_version", "pd_last_error", "pd_launch_count", "pd_reset_launch_count",
+    "pd_warp_composite_workspace_bytes", "pd_warp_composite_fwd", "pd_warp_composite_bwd",
+    "pd_photometric_workspace_bytes", "pd_photometric_fwd", "pd_photometric_bwd",
+]
+
+
+class Strides4(C.Structure):
+    _fields_ = [("b", C.c_int64), ("n", C.c_int64), ("y", C.c_int64), ("x", C.c_int64)]
+
+
+class WarpDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("warp_type", C.c_int32), ("mixture", C.c_int32), ("automask", C.c_int32), ("mask_dtype", C.c_int32),
+        ("disp_sign", C.c_float), ("reserved0", C.c_int32),
+        ("disp_stride", Strides4), ("mask_stride", Strides4),
+    ]
+
+
+class WarpIn(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("src", "tgt", "logits", "sigma", "disp", "mask", "hmat", "cam")]
+
+
+class WarpOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in (
+        "rgb_rec", "stats", "nll", "nll_auto", "rgb_rec_layered", "logit_rec", "probability_rec", "sigma_rec", "pi_rec")]
+
+
+class WarpGradOut(C.Structure):
+    _fields_ = [("g_rgb_rec", C.c_void_p), ("g_nll", C.c_void_p)]
+
+
+class WarpGradIn(C.Structure):
+    _fields_ = [("g_logits", C.c_void_p), ("g_sigma", C.c_void_p), ("g_disp", C.c_void_p),
+                ("g_disp_stride", Strides4), ("g_hmat", C.c_void_p)]
+
+
+class LossDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("loss_mode", C.c_int32),
+                ("automask", C.c_int32), ("has_mask_novel", C.c_int32)]
+
+
+class LossIn(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("rgb_rec", "tgt", "src", "mask_novel", "nll", "nll_auto")]
+
+
+class LossOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("pred", "ph_map", "ph_sum")]
+
+
+class LossGradOut(C.Structure):
+    _fields_ = [("g_ph_sum", C.c_void_p), ("g_pred", C.c_void_p)]
+
+
+class LossGradIn(C.Structure):
+    _fields_ = [("g_rgb_rec", C.c_void_p), ("g_nll", C.c_void_p)]
+
+
+class PlaneDepthLibraryError(RuntimeError):
+    pass
+
+
+def build_library(verbose: bool = False) -> str:
+    """Compile csrc/pd_abi.cu (which includes every kernel) into libplanedepth_b200.so for sm_100a.
+    nvcc cross-compiles without a GPU."""
+    src = os.path.join(CSRC, "pd_abi.cu")
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-o", LIB_PATH, src]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise PlaneDepthLibraryError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
+    if verbose:
+        sys.stderr.write(res.stderr)
+    return LIB_PATH
+
+
+def _needs_rebuild() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(INCLUDE, "planedepth_b200.h"))
+    return any(os.path.getmtime(s) > t for s in srcs)
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (building first if sources are newer and nvcc exists) and type the shared library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if _needs_rebuild():
+        from shutil import which
+
+        if which("nvcc") is not None:
+            build_library()
+        elif not os.path.exists(LIB_PATH):
+            raise PlaneDepthLibraryError(
+                "planedepth_b200: %s is missing and nvcc is not on PATH; run __graft_entry__.build()" % LIB_PATH)
+    try:
+        L = C.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise PlaneDepthLibraryError("cannot load %s: %s" % (LIB_PATH, e))
+    L.pd_version.restype = C.c_int
+    L.pd_last_error.restype = C.c_char_p
+    L.pd_launch_count.restype = C.c_int64
+    L.pd_reset_launch_count.restype = None
+    L.pd_warp_composite_workspace_bytes.restype = C.c_size_t
+    L.pd_warp_composite_workspace_bytes.argtypes = [C.POINTER(WarpDesc)]
+    L.pd_warp_composite_fwd.restype = C.c_int
+    L.pd_warp_composite_fwd.argtypes = [C.POINTER(WarpDesc), C.POINTER(WarpIn), C.POINTER(WarpOut), C.c_void_p, C.c_void_p]
+    L.pd_warp_composite_bwd.restype = C.c_int
+    L.pd_warp_composite_bwd.argtypes = [C.POINTER(WarpDesc), C.POINTER(WarpIn), C.POINTER(WarpOut), C.POINTER(WarpGradOut),
+                                        C.POINTER(WarpGradIn), C.c_void_p, C.c_void_p]
+    L.pd_photometric_workspace_bytes.restype = C.c_size_t
+    L.pd_photometric_workspace_bytes.argtypes = [C.POINTER(LossDesc)]
+    L.pd_photometric_fwd.restype = C.c_int
+    L.pd_photometric_fwd.argtypes = [C.POINTER(LossDesc), C.POINTER(LossIn), C.POINTER(LossOut), C.c_void_p, C.c_void_p]
+    L.pd_photometric_bwd.restype = C.c_int
+    L.pd_photometric_bwd.argtypes = [C.POINTER(LossDesc), C.POINTER(LossIn), C.POINTER(LossGradOut), C.POINTER(LossGradIn),
+                                     C.c_void_p, C.c_void_p]
+    if L.pd_version() != 1:
+        raise PlaneDepthLibraryError("ABI version mismatch: library %d, binding 1" % L.pd_version())
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().pd_last_error().decode("utf-8", "replace")
+        raise PlaneDepthLibraryError("%s failed (pd_status %d): %s" % (what, rc, msg))

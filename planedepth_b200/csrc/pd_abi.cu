@@ -1,0 +1,264 @@
+// C ABI of planedepth_b200 (see include/planedepth_b200.h): argument validation, kernel selection
+// and launches.  No torch / ATen dependency; everything is enqueued on the caller's stream.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "pd_loss.cuh"
+#include "pd_warp_general.cuh"
+#include "pd_warp_rows.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int64_t g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PD_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    ++g_launches;
+    return PD_OK;
+}
+
+int check_device() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(PD_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) return fail(PD_ERR_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+    if (major != 10) return fail(PD_ERR_ARCH, "planedepth_b200 is built for sm_100a only (device is sm_%d*)", major);
+    return PD_OK;
+}
+
+int validate_warp(const pd_warp_desc* d, const pd_warp_in* in) {
+    if (!d || !in) return fail(PD_ERR_ARG, "NULL descriptor");
+    if (d->B < 1 || d->N < 1 || d->H < 2 || d->W < 2) return fail(PD_ERR_SHAPE, "B,N >= 1 and H,W >= 2 required (got %d,%d,%d,%d)", d->B, d->N, d->H, d->W);
+    if (d->N > PD_MAX_PLANES) return fail(PD_ERR_SHAPE, "N=%d exceeds PD_MAX_PLANES", d->N);
+    if ((int64_t)d->H * d->W >= (1ll << 31)) return fail(PD_ERR_SHAPE, "H*W too large");
+    if (d->warp_type < PD_WARP_DISP || d->warp_type > PD_WARP_DEPTH) return fail(PD_ERR_ARG, "bad warp_type %d", d->warp_type);
+    if (!in->src || !in->logits) return fail(PD_ERR_ARG, "src / logits must not be NULL");
+    if (d->mixture && (!in->sigma || !in->tgt)) return fail(PD_ERR_ARG, "mixture needs sigma and tgt");
+    if (d->warp_type == PD_WARP_HOMOGRAPHY) {
+        if (!in->hmat || !in->cam) return fail(PD_ERR_ARG, "homography_warp needs hmat and cam");
+    } else {
+        if (!in->disp) return fail(PD_ERR_ARG, "disp_warp / depth_warp need disp");
+        if (d->warp_type == PD_WARP_DEPTH && !in->cam) return fail(PD_ERR_ARG, "depth_warp needs cam");
+        if (d->mask_dtype != PD_MASK_NONE && !in->mask) return fail(PD_ERR_ARG, "mask_dtype set but mask is NULL");
+        if (d->mask_dtype < PD_MASK_NONE || d->mask_dtype > PD_MASK_U8) return fail(PD_ERR_ARG, "bad mask_dtype");
+    }
+    return PD_OK;
+}
+
+pd::WarpParams make_params(const pd_warp_desc* d, const pd_warp_in* in) {
+    pd::WarpParams p;
+    memset(&p, 0, sizeof(p));
+    p.d = *d;
+    p.in = *in;
+    if (!in->mask) p.d.mask_dtype = PD_MASK_NONE;
+    p.wm1 = (float)(d->W - 1);
+    p.hm1 = (float)(d->H - 1);
+    p.depth_c = 0.1f * 0.58f * (float)d->W;
+    p.hw = (int64_t)d->H * d->W;
+    p.chw3 = 3 * p.hw;
+    p.warp_aligned_rows = (d->W % 32 == 0);
+    return p;
+}
+
+int64_t strided_extent(const pd_strides4& s, int B, int N, int H, int W) {
+    return (int64_t)(B - 1) * s.b + (int64_t)(N - 1) * s.n + (int64_t)(H - 1) * s.y + (int64_t)(W - 1) * s.x + 1;
+}
+
+template <int WARP, bool MIX>
+void launch_fwd_general(const pd::WarpParams& p, bool debug, cudaStream_t st) {
+    const int64_t total = (int64_t)p.d.B * p.hw;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (debug)
+        pd::warp_composite_fwd_general<WARP, MIX, true><<<grid, 256, 0, st>>>(p);
+    else
+        pd::warp_composite_fwd_general<WARP, MIX, false><<<grid, 256, 0, st>>>(p);
+}
+
+template <int WARP, bool MIX>
+void launch_bwd_general(const pd::WarpParams& p, cudaStream_t st) {
+    const int64_t total = (int64_t)p.d.B * p.hw;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    pd::warp_composite_bwd_general<WARP, MIX><<<grid, 256, 0, st>>>(p);
+}
+
+dim3 loss_grid(const pd_loss_desc* d) {
+    return dim3((d->W + pd::LT_W - 1) / pd::LT_W, (d->H + pd::LT_H - 1) / pd::LT_H, d->B);
+}
+
+int validate_loss(const pd_loss_desc* d, const pd_loss_in* in) {
+    if (!d || !in) return fail(PD_ERR_ARG, "NULL descriptor");
+    if (d->B < 1 || d->H < 2 || d->W < 2 || d->B > 65535) return fail(PD_ERR_SHAPE, "1 <= B <= 65535 and H,W >= 2 required");
+    if (d->loss_mode < PD_LOSS_L1 || d->loss_mode > PD_LOSS_SSIM_L1) return fail(PD_ERR_ARG, "bad loss_mode %d", d->loss_mode);
+    if (!in->rgb_rec || !in->tgt) return fail(PD_ERR_ARG, "rgb_rec / tgt must not be NULL");
+    if (d->has_mask_novel && !in->mask_novel) return fail(PD_ERR_ARG, "has_mask_novel set but mask_novel is NULL");
+    if (d->loss_mode == PD_LOSS_MIXTURE) {
+        if (!in->nll || (d->automask && !in->nll_auto)) return fail(PD_ERR_ARG, "mixture loss needs nll (and nll_auto with automask)");
+    } else if (d->automask && !in->src) {
+        return fail(PD_ERR_ARG, "automask needs src");
+    }
+    return PD_OK;
+}
+
+template <int MODE, typename F>
+void dispatch_flags(bool automask, bool hasmask, F&& f) {
+    if (automask) { if (hasmask) f.template operator()<MODE, true, true>(); else f.template operator()<MODE, true, false>(); }
+    else          { if (hasmask) f.template operator()<MODE, false, true>(); else f.template operator()<MODE, false, false>(); }
+}
+
+struct FwdLaunch {
+    pd::LossParams p; dim3 g; cudaStream_t st;
+    template <int MODE, bool A, bool M> void operator()() { pd::photometric_fwd_kernel<MODE, A, M><<<g, pd::LT_THREADS, 0, st>>>(p); }
+};
+struct BwdLaunch {
+    pd::LossParams p; dim3 g; cudaStream_t st;
+    template <int MODE, bool A, bool M> void operator()() { pd::photometric_bwd_kernel<MODE, A, M><<<g, pd::LT_THREADS, 0, st>>>(p); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int pd_version(void) { return PD_ABI_VERSION; }
+const char* pd_last_error(void) { return g_err; }
+int64_t pd_launch_count(void) { return g_launches; }
+void pd_reset_launch_count(void) { g_launches = 0; }
+
+size_t pd_warp_composite_workspace_bytes(const pd_warp_desc* desc) {
+    (void)desc;
+    return 0;
+}
+
+int pd_warp_composite_fwd(const pd_warp_desc* d, const pd_warp_in* in, pd_warp_out* out, void* workspace, pd_stream_t stream) {
+    (void)workspace;
+    int rc = validate_warp(d, in);
+    if (rc) return rc;
+    if (!out || !out->rgb_rec || !out->stats) return fail(PD_ERR_ARG, "rgb_rec / stats outputs must not be NULL");
+    if (d->mixture && (!out->nll || (d->automask && !out->nll_auto))) return fail(PD_ERR_ARG, "mixture needs nll (and nll_auto with automask)");
+    if ((rc = check_device())) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    pd::WarpParams p = make_params(d, in);
+    p.out = *out;
+    const bool debug = out->rgb_rec_layered || out->logit_rec || out->probability_rec || out->sigma_rec || out->pi_rec;
+    if (!debug && pd::rows_path_supported(p)) {
+        pd::launch_fwd_rows(p, st);
+        return check_launch("warp_composite_fwd_rows");
+    }
+    const bool mix = d->mixture != 0;
+    switch (d->warp_type) {
+        case PD_WARP_DISP: mix ? launch_fwd_general<PD_WARP_DISP, true>(p, debug, st) : launch_fwd_general<PD_WARP_DISP, false>(p, debug, st); break;
+        case PD_WARP_HOMOGRAPHY: mix ? launch_fwd_general<PD_WARP_HOMOGRAPHY, true>(p, debug, st) : launch_fwd_general<PD_WARP_HOMOGRAPHY, false>(p, debug, st); break;
+        default: mix ? launch_fwd_general<PD_WARP_DEPTH, true>(p, debug, st) : launch_fwd_general<PD_WARP_DEPTH, false>(p, debug, st); break;
+    }
+    return check_launch("warp_composite_fwd_general");
+}
+
+int pd_warp_composite_bwd(const pd_warp_desc* d, const pd_warp_in* in, const pd_warp_out* saved, const pd_warp_grad_out* gout,
+                          pd_warp_grad_in* gin, void* workspace, pd_stream_t stream) {
+    (void)workspace;
+    int rc = validate_warp(d, in);
+    if (rc) return rc;
+    if (!saved || !saved->rgb_rec || !saved->stats) return fail(PD_ERR_ARG, "saved rgb_rec / stats must not be NULL");
+    if (!gout || !gout->g_rgb_rec) return fail(PD_ERR_ARG, "g_rgb_rec must not be NULL");
+    if (!gin) return fail(PD_ERR_ARG, "NULL grad_in");
+    if ((rc = check_device())) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    pd::WarpParams p = make_params(d, in);
+    p.out = *saved;
+    p.gout = *gout;
+    p.gin = *gin;
+    if (!d->mixture) p.gin.g_sigma = nullptr;
+    if (d->warp_type == PD_WARP_HOMOGRAPHY) p.gin.g_disp = nullptr; else p.gin.g_hmat = nullptr;
+    const pd_strides4& gs = p.gin.g_disp_stride;
+    p.g_disp_dense = p.gin.g_disp && gs.b != 0 && gs.n != 0 && gs.y != 0 && gs.x != 0;
+
+    const size_t plane_bytes = (size_t)d->B * d->N * p.hw * sizeof(float);
+    cudaError_t e = cudaSuccess;
+    const bool rows = pd::rows_path_supported(p);
+    // scatter targets are accumulated with atomics in the general path: zero them first
+    if (!rows) {
+        if (p.gin.g_logits) e = cudaMemsetAsync(p.gin.g_logits, 0, plane_bytes, st);
+        if (e == cudaSuccess && p.gin.g_sigma) e = cudaMemsetAsync(p.gin.g_sigma, 0, plane_bytes, st);
+    }
+    if (e == cudaSuccess && p.gin.g_disp && !p.g_disp_dense)
+        e = cudaMemsetAsync(p.gin.g_disp, 0, (size_t)strided_extent(gs, d->B, d->N, d->H, d->W) * sizeof(float), st);
+    if (e == cudaSuccess && p.gin.g_hmat) e = cudaMemsetAsync(p.gin.g_hmat, 0, (size_t)d->B * d->N * 9 * sizeof(float), st);
+    if (e != cudaSuccess) return fail(PD_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    if (rows) {
+        pd::launch_bwd_rows(p, st);
+        return check_launch("warp_composite_bwd_rows");
+    }
+    const bool mix = d->mixture != 0;
+    switch (d->warp_type) {
+        case PD_WARP_DISP: mix ? launch_bwd_general<PD_WARP_DISP, true>(p, st) : launch_bwd_general<PD_WARP_DISP, false>(p, st); break;
+        case PD_WARP_HOMOGRAPHY: mix ? launch_bwd_general<PD_WARP_HOMOGRAPHY, true>(p, st) : launch_bwd_general<PD_WARP_HOMOGRAPHY, false>(p, st); break;
+        default: mix ? launch_bwd_general<PD_WARP_DEPTH, true>(p, st) : launch_bwd_general<PD_WARP_DEPTH, false>(p, st); break;
+    }
+    return check_launch("warp_composite_bwd_general");
+}
+
+// ---------------------------------------------------------------------------------------------
+// photometric term
+// ---------------------------------------------------------------------------------------------
+size_t pd_photometric_workspace_bytes(const pd_loss_desc* d) {
+    if (!d) return 0;
+    dim3 g = loss_grid(d);
+    return (size_t)g.x * g.y * g.z * sizeof(float);
+}
+
+int pd_photometric_fwd(const pd_loss_desc* d, const pd_loss_in* in, pd_loss_out* out, void* workspace, pd_stream_t stream) {
+    int rc = validate_loss(d, in);
+    if (rc) return rc;
+    if (!out || !out->ph_sum) return fail(PD_ERR_ARG, "ph_sum must not be NULL");
+    if (d->has_mask_novel && !out->pred) return fail(PD_ERR_ARG, "has_mask_novel needs the pred output");
+    if (!workspace) return fail(PD_ERR_WORKSPACE, "workspace of pd_photometric_workspace_bytes() required");
+    if ((rc = check_device())) return rc;
+    FwdLaunch L;
+    memset(&L.p, 0, sizeof(L.p));
+    L.p.d = *d; L.p.in = *in; L.p.out = *out; L.p.partials = (float*)workspace; L.p.hw = (int64_t)d->H * d->W;
+    L.g = loss_grid(d); L.st = (cudaStream_t)stream;
+    switch (d->loss_mode) {
+        case PD_LOSS_L1: dispatch_flags<PD_LOSS_L1>(d->automask, d->has_mask_novel, L); break;
+        case PD_LOSS_MIXTURE: dispatch_flags<PD_LOSS_MIXTURE>(d->automask, d->has_mask_novel, L); break;
+        default: dispatch_flags<PD_LOSS_SSIM_L1>(d->automask, d->has_mask_novel, L); break;
+    }
+    if ((rc = check_launch("photometric_fwd"))) return rc;
+    pd::reduce_partials_kernel<<<1, 1024, 0, L.st>>>(L.p.partials, (int64_t)L.g.x * L.g.y * L.g.z, out->ph_sum);
+    return check_launch("reduce_partials");
+}
+
+int pd_photometric_bwd(const pd_loss_desc* d, const pd_loss_in* in, const pd_loss_grad_out* gout, pd_loss_grad_in* gin, void* workspace,
+                       pd_stream_t stream) {
+    (void)workspace;
+    int rc = validate_loss(d, in);
+    if (rc) return rc;
+    if (!gout || !gout->g_ph_sum) return fail(PD_ERR_ARG, "g_ph_sum must not be NULL");
+    if (!gin || !gin->g_rgb_rec) return fail(PD_ERR_ARG, "g_rgb_rec must not be NULL");
+    if (d->loss_mode == PD_LOSS_MIXTURE && !gin->g_nll) return fail(PD_ERR_ARG, "mixture loss needs g_nll");
+    if ((rc = check_device())) return rc;
+    BwdLaunch L;
+    memset(&L.p, 0, sizeof(L.p));
+    L.p.d = *d; L.p.in = *in; L.p.gout = *gout; L.p.gin = *gin; L.p.hw = (int64_t)d->H * d->W;
+    L.g = loss_grid(d); L.st = (cudaStream_t)stream;
+    switch (d->loss_mode) {
+        case PD_LOSS_L1: dispatch_flags<PD_LOSS_L1>(d->automask, d->has_mask_novel, L); break;
+        case PD_LOSS_MIXTURE: dispatch_flags<PD_LOSS_MIXTURE>(d->automask, d->has_mask_novel, L); break;
+        default: dispatch_flags<PD_LOSS_SSIM_L1>(d->automask, d->has_mask_novel, L); break;
+    }
+    return check_launch("photometric_bwd");
+}
+
+}  // extern "C"

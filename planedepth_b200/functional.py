@@ -1,0 +1,238 @@
+"""torch.autograd bridges over the C ABI (include/planedepth_b200.h).
+
+PyTorch is used here for device memory, streams and autograd bookkeeping only; every tensor handed to
+the library is a raw device pointer.  There is no eager fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t: torch.Tensor, what: str) -> torch.Tensor:
+    if t.device.type != "cuda":
+        raise L.PlaneDepthLibraryError("%s must be a CUDA tensor (planedepth_b200 has no CPU path)" % what)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _strides4(t: torch.Tensor) -> L.Strides4:
+    # size-1 dimensions broadcast: give them stride 0 so the kernel may index them with any coordinate
+    s = [0 if t.size(i) == 1 else t.stride(i) for i in range(4)]
+    return L.Strides4(*s)
+
+
+def compact_expand_base(t: torch.Tensor) -> torch.Tensor:
+    """If ``t`` is an ``expand`` view of a smaller 4-d tensor (depth_decoder.py:156 hands out
+    ``disp_layered`` that way), return that base so gradients arrive in the compact shape instead of a
+    dense [B,N,H,W] buffer that autograd would have to sum afterwards.  Otherwise return ``t``."""
+    base = t._base if t._is_view() else None
+    if base is None or base.dim() != 4 or base.data_ptr() != t.data_ptr() or base.dtype != t.dtype:
+        return t
+    for i in range(4):
+        same = base.size(i) == t.size(i) and (t.size(i) == 1 or base.stride(i) == t.stride(i))
+        bcast = base.size(i) == 1 and (t.stride(i) == 0 or t.size(i) == 1)
+        if not (same or bcast):
+            return t
+    return base
+
+
+@dataclass(frozen=True)
+class WarpConfig:
+    warp_type: int
+    mixture: bool
+    automask: bool
+    disp_sign: float = 0.0
+    shape: Tuple[int, int, int, int] = (0, 0, 0, 0)  # B,N,H,W
+    layered: bool = False  # also materialise the per-plane tensors of trainer.py:582-602 (detached)
+
+
+class _WarpComposite(torch.autograd.Function):
+    """pd_warp_composite_fwd / _bwd: trainer.py:533-603 for one target side."""
+
+    @staticmethod
+    def forward(ctx, cfg: WarpConfig, src, tgt, logits, sigma, disp, mask, hmat, cam):
+        lib = L.lib()
+        B, N, H, W = cfg.shape
+        dev = logits.device
+        desc = L.WarpDesc(B=B, N=N, H=H, W=W, warp_type=cfg.warp_type, mixture=int(cfg.mixture), automask=int(cfg.automask),
+                          mask_dtype=L.PD_MASK_NONE, disp_sign=float(cfg.disp_sign), reserved0=0)
+        if disp is not None:
+            desc.disp_stride = _strides4(disp)
+        if mask is not None:
+            desc.mask_stride = _strides4(mask)
+            desc.mask_dtype = L.PD_MASK_F32 if mask.dtype == torch.float32 else L.PD_MASK_U8
+        tin = L.WarpIn(src=_ptr(src), tgt=_ptr(tgt), logits=_ptr(logits), sigma=_ptr(sigma), disp=_ptr(disp), mask=_ptr(mask),
+                       hmat=_ptr(hmat), cam=_ptr(cam))
+        ns = L.PD_STATS_MIXTURE if cfg.mixture else L.PD_STATS_PLAIN
+        rgb_rec = torch.empty(B, 3, H, W, device=dev, dtype=torch.float32)
+        stats = torch.empty(B, ns, H, W, device=dev, dtype=torch.float32)
+        nll = torch.empty(B, 1, H, W, device=dev, dtype=torch.float32) if cfg.mixture else None
+        nll_auto = torch.empty(B, 1, H, W, device=dev, dtype=torch.float32) if (cfg.mixture and cfg.automask) else None
+        out = L.WarpOut(rgb_rec=_ptr(rgb_rec), stats=_ptr(stats), nll=_ptr(nll), nll_auto=_ptr(nll_auto))
+        layered = None
+        if cfg.layered:
+            layered = {
+                "rgb_rec_layered": torch.empty(B, N, 3, H, W, device=dev),
+                "logit_rec": torch.empty(B, N, H, W, device=dev),
+                "probability_rec": torch.empty(B, N, H, W, device=dev),
+            }
+            if cfg.mixture:
+                layered["sigma_rec"] = torch.empty(B, N, H, W, device=dev)
+                layered["pi_rec"] = torch.empty(B, N, H, W, device=dev)
+            for k, v in layered.items():
+                setattr(out, k, v.data_ptr())
+        L.check(lib.pd_warp_composite_fwd(C.byref(desc), C.byref(tin), C.byref(out), None, _stream()), "pd_warp_composite_fwd")
+        ctx.cfg = cfg
+        ctx.desc = desc
+        ctx.save_for_backward(src, tgt, logits, sigma, disp, mask, hmat, cam, rgb_rec, stats)
+        ctx.layered = layered
+        outs = [rgb_rec,
+                nll if nll is not None else torch.empty(0, device=dev),
+                nll_auto if nll_auto is not None else torch.empty(0, device=dev)]
+        ctx.mark_non_differentiable(outs[2])
+        if not cfg.mixture:
+            ctx.mark_non_differentiable(outs[1])
+        names = []
+        if layered is not None:
+            for k, v in layered.items():
+                names.append(k)
+                outs.append(v)
+                ctx.mark_non_differentiable(v)
+        ctx.layer_names = names
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_nll, g_nll_auto, *unused):
+        lib = L.lib()
+        cfg = ctx.cfg
+        B, N, H, W = cfg.shape
+        src, tgt, logits, sigma, disp, mask, hmat, cam, rgb_rec, stats = ctx.saved_tensors
+        dev = logits.device
+        need = ctx.needs_input_grad  # (cfg, src, tgt, logits, sigma, disp, mask, hmat, cam)
+        g_rgb = torch.zeros_like(rgb_rec) if g_rgb is None else _f32c(g_rgb, "grad rgb_rec")
+        if cfg.mixture and g_nll is not None and g_nll.numel():
+            g_nll = _f32c(g_nll, "grad nll")
+        else:
+            g_nll = None
+        tin = L.WarpIn(src=_ptr(src), tgt=_ptr(tgt), logits=_ptr(logits), sigma=_ptr(sigma), disp=_ptr(disp), mask=_ptr(mask),
+                       hmat=_ptr(hmat), cam=_ptr(cam))
+        saved = L.WarpOut(rgb_rec=_ptr(rgb_rec), stats=_ptr(stats))
+        gout = L.WarpGradOut(g_rgb_rec=_ptr(g_rgb), g_nll=_ptr(g_nll))
+        g_logits = torch.empty_like(logits) if need[3] else None
+        g_sigma = torch.empty_like(sigma) if (cfg.mixture and sigma is not None and need[4]) else None
+        g_disp = g_hmat = None
+        gin = L.WarpGradIn(g_logits=_ptr(g_logits), g_sigma=_ptr(g_sigma))
+        if disp is not None and need[5]:
+            # same (possibly compact) shape as the input; size-1 dims are reduced inside the kernel
+            g_disp = torch.empty(disp.shape, device=dev, dtype=torch.float32)
+            gin.g_disp = g_disp.data_ptr()
+            gin.g_disp_stride = _strides4(g_disp)
+        if hmat is not None and need[7]:
+            g9 = torch.empty(B * N, 9, device=dev, dtype=torch.float32)
+            gin.g_hmat = g9.data_ptr()
+        L.check(lib.pd_warp_composite_bwd(C.byref(ctx.desc), C.byref(tin), C.byref(saved), C.byref(gout), C.byref(gin), None, _stream()),
+                "pd_warp_composite_bwd")
+        if hmat is not None and need[7]:
+            g_hmat = torch.cat([g9, torch.zeros(B * N, 3, device=dev)], 1)
+        return (None, None, None, g_logits, g_sigma, g_disp, None, g_hmat, None)
+
+
+def warp_composite(cfg: WarpConfig, src, tgt, logits, sigma=None, disp=None, mask=None, hmat=None, cam=None):
+    """Returns (rgb_rec, nll | None, nll_auto | None, layered dict | None)."""
+    src = _f32c(src, "src")
+    logits = _f32c(logits, "logits")
+    tgt = _f32c(tgt, "tgt") if (cfg.mixture and tgt is not None) else None
+    sigma = _f32c(sigma, "sigma") if cfg.mixture else None
+    if disp is not None:
+        if disp.dtype != torch.float32:
+            disp = disp.float()
+        disp = compact_expand_base(disp)
+    if mask is not None:
+        if mask.dtype == torch.bool:
+            mask = mask.view(torch.uint8)
+        elif mask.dtype not in (torch.float32, torch.uint8):
+            mask = mask.float()
+        if mask.dim() != 4:
+            raise ValueError("padding_mask must be 4-d [B,N,H,W] (broadcastable)")
+        mask = mask.detach()
+    if hmat is not None:
+        hmat = _f32c(hmat, "hmat")
+    if cam is not None:
+        cam = _f32c(cam, "cam").detach()
+    outs = _WarpComposite.apply(cfg, src.detach(), None if tgt is None else tgt.detach(), logits, sigma, disp, mask, hmat, cam)
+    rgb_rec, nll, nll_auto = outs[:3]
+    layered = None
+    if cfg.layered:
+        names = ["rgb_rec_layered", "logit_rec", "probability_rec"] + (["sigma_rec", "pi_rec"] if cfg.mixture else [])
+        layered = dict(zip(names, outs[3:]))
+    return rgb_rec, (nll if cfg.mixture else None), (nll_auto if (cfg.mixture and cfg.automask) else None), layered
+
+
+class _Photometric(torch.autograd.Function):
+    """pd_photometric_fwd / _bwd: trainer.py:720-742 (+687-699) for one target side."""
+
+    @staticmethod
+    def forward(ctx, mode: int, automask: bool, want_map: bool, rgb_rec, tgt, src, mask_novel, nll, nll_auto):
+        lib = L.lib()
+        B, _, H, W = rgb_rec.shape
+        dev = rgb_rec.device
+        desc = L.LossDesc(B=B, H=H, W=W, loss_mode=mode, automask=int(automask), has_mask_novel=int(mask_novel is not None))
+        tin = L.LossIn(rgb_rec=_ptr(rgb_rec), tgt=_ptr(tgt), src=_ptr(src), mask_novel=_ptr(mask_novel), nll=_ptr(nll), nll_auto=_ptr(nll_auto))
+        pred = torch.empty_like(rgb_rec) if mask_novel is not None else None
+        ph_map = torch.empty(B, 1, H, W, device=dev) if want_map else None
+        ph_sum = torch.empty((), device=dev, dtype=torch.float32)
+        ws = torch.empty(lib.pd_photometric_workspace_bytes(C.byref(desc)) // 4, device=dev, dtype=torch.float32)
+        out = L.LossOut(pred=_ptr(pred), ph_map=_ptr(ph_map), ph_sum=_ptr(ph_sum))
+        L.check(lib.pd_photometric_fwd(C.byref(desc), C.byref(tin), C.byref(out), ws.data_ptr(), _stream()), "pd_photometric_fwd")
+        ctx.desc = desc
+        ctx.has_pred = pred is not None
+        ctx.save_for_backward(rgb_rec, tgt, src, mask_novel, nll, nll_auto)
+        outs = (ph_sum, pred if pred is not None else torch.empty(0, device=dev), ph_map if ph_map is not None else torch.empty(0, device=dev))
+        ctx.mark_non_differentiable(outs[2])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_sum, g_pred, g_map):
+        lib = L.lib()
+        rgb_rec, tgt, src, mask_novel, nll, nll_auto = ctx.saved_tensors
+        dev = rgb_rec.device
+        g_sum = torch.zeros((), device=dev) if g_sum is None else _f32c(g_sum, "grad ph_sum")
+        g_pred = _f32c(g_pred, "grad pred") if (ctx.has_pred and g_pred is not None) else None
+        tin = L.LossIn(rgb_rec=_ptr(rgb_rec), tgt=_ptr(tgt), src=_ptr(src), mask_novel=_ptr(mask_novel), nll=_ptr(nll), nll_auto=_ptr(nll_auto))
+        g_rgb = torch.empty_like(rgb_rec)
+        g_nll = torch.empty_like(nll) if nll is not None else None
+        gout = L.LossGradOut(g_ph_sum=_ptr(g_sum), g_pred=_ptr(g_pred))
+        gin = L.LossGradIn(g_rgb_rec=_ptr(g_rgb), g_nll=_ptr(g_nll))
+        L.check(lib.pd_photometric_bwd(C.byref(ctx.desc), C.byref(tin), C.byref(gout), C.byref(gin), None, _stream()), "pd_photometric_bwd")
+        return (None, None, None, g_rgb, None, None, None, g_nll, None)
+
+
+def photometric_loss(mode: int, automask: bool, rgb_rec, tgt, src=None, mask_novel=None, nll=None, nll_auto=None, want_map=False):
+    """Returns (ph_sum 0-dim, pred [B,3,H,W], ph_map | None).  ``pred`` is ``rgb_rec`` itself (same
+    autograd node) when there is no ``mask_novel`` blend."""
+    rgb_rec = _f32c(rgb_rec, "rgb_rec")
+    tgt = _f32c(tgt, "tgt").detach()
+    need_src = automask and mode != L.PD_LOSS_MIXTURE
+    src = _f32c(src, "src").detach() if need_src else None
+    mask_novel = _f32c(mask_novel, "mask_novel").detach() if mask_novel is not None else None
+    if mode == L.PD_LOSS_MIXTURE:
+        nll = _f32c(nll, "nll")
+        nll_auto = _f32c(nll_auto, "nll_auto").detach() if automask else None
+    else:
+        nll = nll_auto = None
+    ph_sum, pred, ph_map = _Photometric.apply(mode, automask, want_map, rgb_rec, tgt, src, mask_novel, nll, nll_auto)
+    return ph_sum, (pred if mask_novel is not None else rgb_rec), (ph_map if want_map else None)

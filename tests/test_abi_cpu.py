@@ -1,0 +1,77 @@
+"""CPU: the C-ABI shared library builds for sm_100a, loads without a GPU, exports every symbol that
+include/planedepth_b200.h declares, and the ctypes mirror of each struct has the C layout."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from planedepth_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "planedepth_b200.h")
+
+
+def declared_functions():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(pd_[a-z_0-9]+)\s*\(", txt)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    lib = L.lib()
+    names = declared_functions()
+    assert set(L.EXPORTS) <= set(names)
+    for n in names:
+        assert hasattr(lib, n), "missing export %s" % n
+    assert lib.pd_version() == 1
+    assert lib.pd_last_error() is not None
+
+
+def test_ctypes_structs_match_c_layout(tmp_path):
+    structs = {
+        "pd_strides4": L.Strides4, "pd_warp_desc": L.WarpDesc, "pd_warp_in": L.WarpIn, "pd_warp_out": L.WarpOut,
+        "pd_warp_grad_out": L.WarpGradOut, "pd_warp_grad_in": L.WarpGradIn, "pd_loss_desc": L.LossDesc, "pd_loss_in": L.LossIn,
+        "pd_loss_out": L.LossOut, "pd_loss_grad_out": L.LossGradOut, "pd_loss_grad_in": L.LossGradIn,
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "planedepth_b200.h"', "int main(void){"]
+    for cname, st in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for f, _ in st._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, f, cname, f))
+    lines.append("return 0;}")
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = dict(l.split() for l in out.strip().splitlines())
+    for cname, st in structs.items():
+        assert int(got[cname]) == C.sizeof(st), cname
+        for f, _ in st._fields_:
+            assert int(got["%s.%s" % (cname, f)]) == getattr(st, f).offset, "%s.%s" % (cname, f)
+
+
+def test_argument_validation_needs_no_gpu():
+    lib = L.lib()
+    d = L.WarpDesc(B=1, N=1, H=1, W=8)
+    rc = lib.pd_warp_composite_fwd(C.byref(d), C.byref(L.WarpIn()), C.byref(L.WarpOut()), None, None)
+    assert rc == 2 and b"H,W >= 2" in lib.pd_last_error()
+    d = L.WarpDesc(B=1, N=1, H=8, W=8)
+    rc = lib.pd_warp_composite_fwd(C.byref(d), C.byref(L.WarpIn()), C.byref(L.WarpOut()), None, None)
+    assert rc == 1 and b"NULL" in lib.pd_last_error()
+    with pytest.raises(L.PlaneDepthLibraryError):
+        L.check(rc, "pd_warp_composite_fwd")
+    ld = L.LossDesc(B=1, H=8, W=8, loss_mode=7)
+    assert lib.pd_photometric_fwd(C.byref(ld), C.byref(L.LossIn()), C.byref(L.LossOut()), None, None) == 1
+
+
+def test_product_path_refuses_cpu_tensors():
+    import torch
+
+    from planedepth_b200.functional import WarpConfig, warp_composite
+
+    cfg = WarpConfig(L.PD_WARP_DISP, False, False, 1.0, (1, 2, 8, 8))
+    with pytest.raises(L.PlaneDepthLibraryError):
+        warp_composite(cfg, torch.zeros(1, 3, 8, 8), None, torch.zeros(1, 2, 8, 8), None, torch.ones(1, 2, 8, 8), None)
