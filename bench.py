@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the photometric-reconstruction hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg3]
+
+One "step" = one pass of the hot path over one synthetic batch: Trainer.pred_novel_images +
+Trainer.compute_losses (photometric term) forward AND backward (trainer.py:523-603, 701-742), at
+BASELINE.json configs[1]: batch 12/GPU, 640x192, 49 vertical planes, stereo disparity warp,
+0.85*SSIM + 0.15*L1.  The perceptual network and the smoothness term are out of the path's scope
+(cuDNN / a 1-plane stencil) and are not executed by either arm.
+
+Prints ONE JSON line (rank 0).  `value` = images/s with inputs resident in HBM (CUDA-graph replay of
+the step); `e2e` = same metric through the public API with the `inputs` dict in pinned HOST memory
+(H2D per step, as trainer.py:328-329 does) and a D2H read of the loss per step; `roofline` = achieved
+algorithmic HBM GB/s of the dominant kernel (CUDA events on the launch stream) against
+MEASURED_PEAKS.json; `cpu_baseline` = the same path on the host cores (bounded sample).
+`--impl reference` times the reference's own CPU implementation (baseline/_ref through an import shim
+when that directory travelled with the snapshot, else the oracle port).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CONFIGS = {
+    # name: (B per GPU, H, W, opt overrides, photometric mode, description)
+    "cfg2": (12, 192, 640, dict(), "ssim_l1", "cfg2: B=12/GPU 640x192 N=49 stereo disp_warp + SSIM/L1, fwd+bwd"),
+    "cfg3": (4, 384, 1280, dict(use_mixture_loss=True, plane_residual=True), None,
+             "cfg3: B=4/GPU 1280x384 N=49 disp_warp + plane_residual + Laplacian mixture, fwd+bwd"),
+}
+METRIC = "training images/sec (49-plane warp+SSIM hot path, fwd+bwd)"
+UNIT = "images/s"
+
+
+# --------------------------------------------------------------------------------------------------
+def dist_env():
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), ws
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def algorithmic_bytes(B, N, H, W, mixture):
+    """SURVEY.md §8(d) per image per target frame, fp32; X1 = H*W*4.
+    warp fwd: N(1+m) logits/sigma + 3 src + 3 rgb_rec (+3 tgt, +1 nll with mixture)
+    warp bwd: 2N(1+m) (re-read, write grads) + 3 src + 3 g_rgb_rec + 3 rgb_rec/tgt
+    loss fwd: 3 rgb_rec + 3 tgt (+1 ph map) ; loss bwd: 3 rgb_rec + 3 tgt + 3 g_rgb_rec."""
+    x1 = H * W * 4
+    m = 1 if mixture else 0
+    return {
+        "pd_warp_composite_fwd": B * x1 * (N * (1 + m) + 6 + 4 * m),
+        "pd_warp_composite_bwd": B * x1 * (2 * N * (1 + m) + 9),
+        "pd_photometric_fwd": B * x1 * 6,
+        "pd_photometric_bwd": B * x1 * 9,
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+# reference / CPU arm
+# --------------------------------------------------------------------------------------------------
+def load_reference():
+    """The unmodified reference through an import shim, if baseline/_ref travelled with the snapshot."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref, "trainer.py")):
+        return None
+    try:
+        import types
+
+        import torch.nn as nn
+
+        for name in ["tensorboardX", "IPython", "skimage", "skimage.transform", "matplotlib"]:
+            sys.modules.setdefault(name, types.ModuleType(name))
+        sys.modules["tensorboardX"].SummaryWriter = object
+        sys.modules["IPython"].embed = lambda *a, **k: None
+        sys.modules["matplotlib"].scale = None
+        sys.modules["skimage"].transform = sys.modules["skimage.transform"]
+        six = types.ModuleType("torch._six")
+        six.string_classes = (str, bytes)
+        sys.modules["torch._six"] = six
+        torch._six = six
+        # the reference calls .cuda() on helper tensors; this arm is the CPU path
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        nn.Module.cuda = lambda self, *a, **k: self
+        import PIL.Image
+
+        if not hasattr(PIL.Image, "ANTIALIAS"):
+            PIL.Image.ANTIALIAS = PIL.Image.LANCZOS
+        sys.path.insert(0, ref)
+        import layers as ref_layers
+        import trainer as ref_trainer
+
+        return ref_trainer, ref_layers
+    except Exception as e:  # pragma: no cover
+        sys.stderr.write("reference import failed (%s); using the oracle port\n" % e)
+        return None
+
+
+def cpu_step_fn(cfg_name, B_sample, seed=0):
+    """Returns (callable doing one fwd+bwd of the path on CPU for B_sample images, kind)."""
+    from types import SimpleNamespace
+
+    import torch.nn as nn
+
+    from planedepth_b200.synthetic import make_batch, make_opt
+
+    _, H, W, over, photometric, _ = CONFIGS[cfg_name]
+    opt = make_opt(**over)
+    batch = make_batch(B_sample, H, W, opt, seed=seed, device="cpu")
+    leaves = list(batch.leaves.values())
+    ref = load_reference()
+    if ref is not None:
+        ref_trainer, ref_layers = ref
+        t = object.__new__(ref_trainer.Trainer)
+        t.opt = SimpleNamespace(**vars(opt))
+        t.opt.use_ssim = photometric == "ssim_l1"
+        t.target_sides = batch.target_sides
+        t.softmax = nn.Softmax(1)
+        t.ssim = ref_layers.SSIM()
+        t.homography_warp = ref_layers.HomographyWarp(H, W)
+        t.backproject_depth = ref_layers.BackprojectDepth(H, W)
+        t.project_3d = ref_layers.Project3D(H, W)
+
+        def step():
+            out = dict(batch.outputs)
+            ref_trainer.Trainer.pred_novel_images(t, batch.inputs, out)
+            total = 0
+            for s in batch.target_sides:
+                if photometric == "ssim_l1":
+                    total = total + ref_trainer.Trainer.compute_reprojection_loss(t, out[("rgb_rec", s)], batch.inputs[("color", s)]).mean()
+                elif opt.use_mixture_loss:
+                    err = torch.abs(out[("rgb_rec_layered", s)] - batch.inputs[("color", s)][:, None]).mean(2)
+                    total = total + ref_layers.multimodal_loss(err, out[("sigma_rec", s)], out[("pi_rec", s)], dist="lap").mean()
+                else:
+                    total = total + torch.abs(out[("rgb_rec", s)] - batch.inputs[("color", s)]).mean()
+            torch.autograd.grad(total, leaves, allow_unused=True)
+            return float(total)
+
+        return step, "reference"
+    from oracle import pd_oracle as O
+
+    def step():
+        out = dict(batch.outputs)
+        O.pred_novel_images(opt, batch.target_sides, batch.inputs, out)
+        total = 0
+        for s in batch.target_sides:
+            ph, _ = O.photometric_map(opt, batch.inputs, out, s, photometric)
+            total = total + ph.mean()
+        torch.autograd.grad(total, leaves, allow_unused=True)
+        return float(total)
+
+    return step, "port"
+
+
+def time_cpu(cfg_name, B_sample, steps, warmup):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, kind = cpu_step_fn(cfg_name, B_sample)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": B_sample / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d step(s) of B=%d images of %s (fwd+bwd), %d torch threads" % (steps, B_sample, cfg_name, cores)}, dt
+
+
+def run_reference(args):
+    rank, _, ws = dist_env()
+    if rank != 0:
+        return
+    B, H, W, over, photometric, desc = CONFIGS[args.config]
+    B_sample = min(B, 4)
+    cb, dt = time_cpu(args.config, B_sample, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": desc, "sample_batch": B_sample, "device": "host CPU"},
+        "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    from planedepth_b200 import _lib, functional
+    from planedepth_b200.boundary import HotPath
+    from planedepth_b200.graph import GraphedStep, make_step
+    from planedepth_b200.synthetic import make_batch, make_opt
+
+    rank, local_rank, ws = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if ws > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.lib()
+    B, H, W, over, photometric, desc = CONFIGS[args.config]
+    opt = make_opt(**over)
+    batch = make_batch(B, H, W, opt, seed=1234 + rank, device="cpu", layout=args.layout)
+    N = batch.shape[1]
+    dev = torch.device("cuda", local_rank)
+    # static device buffers: network outputs live on the device; the `inputs` dict comes from the host
+    host_inputs = {k: v.pin_memory() for k, v in batch.inputs.items()}
+    batch_gpu = make_batch(B, H, W, opt, seed=1234 + rank, device=dev, layout=args.layout)
+    outputs, leaves_map = batch_gpu.outputs, batch_gpu.leaves
+    inputs = batch_gpu.inputs
+    leaves = list(leaves_map.values())
+    hp = HotPath(opt, batch.target_sides, pc_net=None, photometric=photometric)
+    step = make_step(hp, inputs, outputs, leaves)
+    graphed = GraphedStep(step, warmup=3)
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value: inputs resident in HBM, CUDA-graph replay -------------------------
+    for _ in range(args.warmup):
+        graphed.replay()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    lib.pd_reset_launch_count()
+    probe = step()  # one eager step to count the library launches a step performs
+    launches_per_step = lib.pd_launch_count()
+    del probe
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        graphed.replay()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    loss_val = float(graphed.result["loss"].item())
+
+    # ---------------- e2e: `inputs` dict from pinned host memory each step ----------------------
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in host_inputs.values())
+
+    def e2e_step():
+        for k, v in host_inputs.items():
+            inputs[k].copy_(v, non_blocking=True)
+        res = graphed.replay()
+        loss_host.copy_(res["loss"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    ev0.record()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    ev1.record()
+    barrier()
+    e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms_step = float(t.item()) / args.steps
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---------------- roofline: per-kernel CUDA events on the launch stream (eager pass) --------
+    functional.KERNEL_TIMELINE = []
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    functional.KERNEL_TIMELINE = []
+    n_roof = max(3, min(args.steps, 10))
+    for _ in range(n_roof):
+        step()
+    torch.cuda.synchronize()
+    per = {}
+    for name, s, e in functional.KERNEL_TIMELINE:
+        per.setdefault(name, []).append(s.elapsed_time(e))
+    functional.KERNEL_TIMELINE = None
+    avg_ms = {k: sum(v) / len(v) for k, v in per.items()}
+    dom = max(avg_ms, key=avg_ms.get)
+    alg = algorithmic_bytes(B, N, H, W, opt.use_mixture_loss)
+    peak, peak_src = peaks()
+    achieved = alg[dom] / (avg_ms[dom] * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.config, {}).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": alg[dom], "kernel_ms": avg_ms[dom],
+                "all_kernels_ms": avg_ms,
+                "all_kernels_frac": {k: alg[k] / (avg_ms[k] * 1e-3) / 1e9 / peak for k in avg_ms},
+                "step_frac": sum(alg.values()) / (ms_step * 1e-3) / 1e9 / peak}
+
+    if rank != 0:
+        if ws > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if ws == 1 and not args.no_cpu_baseline:
+        cpu, _ = time_cpu(args.config, 2, 2, 1)
+    line = {
+        "metric": METRIC, "value": B * ws / (ms_step * 1e-3), "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * ws, "planes": N, "height": H, "width": W,
+                   "photometric": photometric or ("mixture" if opt.use_mixture_loss else "l1"), "layout": args.layout,
+                   "parallelism": "dp%d (independent shards, no data-path collective)" % ws, "launch": "cuda_graph replay",
+                   "l2": "no flush: per-step working set (logits %.0f MB + grads %.0f MB) exceeds the 126 MB L2" % (
+                       B * N * H * W * 4 / 1e6, B * N * H * W * 4 / 1e6),
+                   "e2e_scope": "inputs dict pinned-host->device each step (trainer.py:328-329) + loss device->host; network outputs are device-born"},
+        "e2e": {"value": B * ws / (e2e_ms_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms_step},
+        "gpu_launches": int(launches_per_step) * args.steps,
+        "gpu_launches_per_step": int(launches_per_step),
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "loss": loss_val,
+    }
+    print(json.dumps(line), flush=True)
+    if ws > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--layout", default="reference", choices=["reference", "compact"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

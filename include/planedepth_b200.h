@@ -183,7 +183,7 @@ int pd_photometric_fwd(const pd_loss_desc* desc, const pd_loss_in* in, pd_loss_o
 int pd_photometric_bwd(const pd_loss_desc* desc, const pd_loss_in* in, const pd_loss_grad_out* gout,
                        pd_loss_grad_in* gin, void* workspace, pd_stream_t stream);
 
-/* Introspection for tests / bench: number of kernels the library has launched on this thread since
+/* Introspection for tests / bench: number of kernels the library has launched in this process since
  * the last pd_reset_launch_count() (bench.py reports it as gpu_launches). */
 int64_t pd_launch_count(void);
 void pd_reset_launch_count(void);

@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "pd_loss.cuh"
 #include "pd_warp_general.cuh"
 #include "pd_warp_rows.cuh"
@@ -12,7 +14,7 @@
 namespace {
 
 thread_local char g_err[512] = "";
-thread_local int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};  // process-wide: autograd runs backward on its own threads
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -134,8 +136,8 @@ extern "C" {
 
 int pd_version(void) { return PD_ABI_VERSION; }
 const char* pd_last_error(void) { return g_err; }
-int64_t pd_launch_count(void) { return g_launches; }
-void pd_reset_launch_count(void) { g_launches = 0; }
+int64_t pd_launch_count(void) { return g_launches.load(); }
+void pd_reset_launch_count(void) { g_launches.store(0); }
 
 size_t pd_warp_composite_workspace_bytes(const pd_warp_desc* desc) {
     (void)desc;

@@ -13,6 +13,23 @@ import torch
 from . import _lib as L
 
 
+#: when set to a list, every C-ABI call appends (name, start_event, end_event) recorded on the launch stream
+KERNEL_TIMELINE = None
+
+
+def _call(name, fn, *args):
+    """Invoke one C-ABI entry point, optionally bracketed by CUDA events on the current stream."""
+    tl = KERNEL_TIMELINE
+    if tl is None:
+        L.check(fn(*args), name)
+        return
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    L.check(fn(*args), name)
+    e.record()
+    tl.append((name, s, e))
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -95,7 +112,7 @@ class _WarpComposite(torch.autograd.Function):
                 layered["pi_rec"] = torch.empty(B, N, H, W, device=dev)
             for k, v in layered.items():
                 setattr(out, k, v.data_ptr())
-        L.check(lib.pd_warp_composite_fwd(C.byref(desc), C.byref(tin), C.byref(out), None, _stream()), "pd_warp_composite_fwd")
+        _call("pd_warp_composite_fwd", lib.pd_warp_composite_fwd, C.byref(desc), C.byref(tin), C.byref(out), None, _stream())
         ctx.cfg = cfg
         ctx.desc = desc
         ctx.save_for_backward(src, tgt, logits, sigma, disp, mask, hmat, cam, rgb_rec, stats)
@@ -144,8 +161,8 @@ class _WarpComposite(torch.autograd.Function):
         if hmat is not None and need[7]:
             g9 = torch.empty(B * N, 9, device=dev, dtype=torch.float32)
             gin.g_hmat = g9.data_ptr()
-        L.check(lib.pd_warp_composite_bwd(C.byref(ctx.desc), C.byref(tin), C.byref(saved), C.byref(gout), C.byref(gin), None, _stream()),
-                "pd_warp_composite_bwd")
+        _call("pd_warp_composite_bwd", lib.pd_warp_composite_bwd, C.byref(ctx.desc), C.byref(tin), C.byref(saved), C.byref(gout),
+              C.byref(gin), None, _stream())
         if hmat is not None and need[7]:
             g_hmat = torch.cat([g9, torch.zeros(B * N, 3, device=dev)], 1)
         return (None, None, None, g_logits, g_sigma, g_disp, None, g_hmat, None)
@@ -197,7 +214,7 @@ class _Photometric(torch.autograd.Function):
         ph_sum = torch.empty((), device=dev, dtype=torch.float32)
         ws = torch.empty(lib.pd_photometric_workspace_bytes(C.byref(desc)) // 4, device=dev, dtype=torch.float32)
         out = L.LossOut(pred=_ptr(pred), ph_map=_ptr(ph_map), ph_sum=_ptr(ph_sum))
-        L.check(lib.pd_photometric_fwd(C.byref(desc), C.byref(tin), C.byref(out), ws.data_ptr(), _stream()), "pd_photometric_fwd")
+        _call("pd_photometric_fwd", lib.pd_photometric_fwd, C.byref(desc), C.byref(tin), C.byref(out), ws.data_ptr(), _stream())
         ctx.desc = desc
         ctx.has_pred = pred is not None
         ctx.save_for_backward(rgb_rec, tgt, src, mask_novel, nll, nll_auto)
@@ -217,7 +234,7 @@ class _Photometric(torch.autograd.Function):
         g_nll = torch.empty_like(nll) if nll is not None else None
         gout = L.LossGradOut(g_ph_sum=_ptr(g_sum), g_pred=_ptr(g_pred))
         gin = L.LossGradIn(g_rgb_rec=_ptr(g_rgb), g_nll=_ptr(g_nll))
-        L.check(lib.pd_photometric_bwd(C.byref(ctx.desc), C.byref(tin), C.byref(gout), C.byref(gin), None, _stream()), "pd_photometric_bwd")
+        _call("pd_photometric_bwd", lib.pd_photometric_bwd, C.byref(ctx.desc), C.byref(tin), C.byref(gout), C.byref(gin), None, _stream())
         return (None, None, None, g_rgb, None, None, None, g_nll, None)
 
 
