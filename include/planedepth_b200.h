@@ -188,6 +188,11 @@ int pd_photometric_bwd(const pd_loss_desc* desc, const pd_loss_in* in, const pd_
 int64_t pd_launch_count(void);
 void pd_reset_launch_count(void);
 
+/* Test hook: evaluates the coordinate normalise / un-normalise round trip of `size` (trainer.py:549-551
+ * + ATen grid_sampler_unnormalize) for n coordinates with the IEEE-division form (out_exact) and with the
+ * division-free form the row-tiled kernels use (out_fast); tests require them to be bit-identical. */
+int pd_debug_roundtrip(const float* u, int64_t n, int32_t size, float* out_exact, float* out_fast, pd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

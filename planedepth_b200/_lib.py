@@ -27,7 +27,7 @@ PD_STATS_PLAIN, PD_STATS_MIXTURE = 2, 4
 EXPORTS = [
     "pd_version", "pd_last_error", "pd_launch_count", "pd_reset_launch_count",
     "pd_warp_composite_workspace_bytes", "pd_warp_composite_fwd", "pd_warp_composite_bwd",
-    "pd_photometric_workspace_bytes", "pd_photometric_fwd", "pd_photometric_bwd",
+    "pd_photometric_workspace_bytes", "pd_photometric_fwd", "pd_photometric_bwd", "pd_debug_roundtrip",
 ]
 
 
@@ -147,6 +147,8 @@ def lib() -> C.CDLL:
     L.pd_photometric_bwd.restype = C.c_int
     L.pd_photometric_bwd.argtypes = [C.POINTER(LossDesc), C.POINTER(LossIn), C.POINTER(LossGradOut), C.POINTER(LossGradIn),
                                      C.c_void_p, C.c_void_p]
+    L.pd_debug_roundtrip.restype = C.c_int
+    L.pd_debug_roundtrip.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     if L.pd_version() != 1:
         raise PlaneDepthLibraryError("ABI version mismatch: library %d, binding 1" % L.pd_version())
     _lib = L

@@ -130,6 +130,13 @@ struct BwdLaunch {
     template <int MODE, bool A, bool M> void operator()() { pd::photometric_bwd_kernel<MODE, A, M><<<g, pd::LT_THREADS, 0, st>>>(p); }
 };
 
+__global__ void debug_roundtrip_kernel(const float* __restrict__ u, int64_t n, float size_m1, float rcp, float* __restrict__ exact, float* __restrict__ fast) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    exact[i] = pd::roundtrip(u[i], size_m1);
+    fast[i] = (rcp != 0.0f) ? pd::roundtrip_fast(u[i], size_m1, rcp) : pd::roundtrip(u[i], size_m1);
+}
+
 }  // namespace
 
 extern "C" {
@@ -210,6 +217,12 @@ int pd_warp_composite_bwd(const pd_warp_desc* d, const pd_warp_in* in, const pd_
         default: mix ? launch_bwd_general<PD_WARP_DEPTH, true>(p, st) : launch_bwd_general<PD_WARP_DEPTH, false>(p, st); break;
     }
     return check_launch("warp_composite_bwd_general");
+}
+
+int pd_debug_roundtrip(const float* u, int64_t n, int32_t size, float* out_exact, float* out_fast, pd_stream_t stream) {
+    if (!u || !out_exact || !out_fast || n < 1 || size < 2) return fail(PD_ERR_ARG, "bad arguments");
+    debug_roundtrip_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(u, n, (float)(size - 1), pd::rows_rcp(size), out_exact, out_fast);
+    return check_launch("debug_roundtrip");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -15,7 +15,17 @@ constexpr float kLog2e = 1.4426950408889634f;
 
 // exp() used for softmax / Laplacian terms.  ex2.approx after an exact-rounded scale: relative error
 // ~2 ulp + 6e-8*|x|, far inside the 1e-4 parity budget (|x| <= ~100 on this path).
-__device__ __forceinline__ float fast_exp(float x) { return exp2f(x * kLog2e); }
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_exp(float x) { return fast_exp2(x * kLog2e); }
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 // The reference normalises pixel coordinates to [-1,1] (trainer.py:549-551, layers.py:179-181,
 // layers.py:231-233: p/(size-1), (p-0.5)*2) and ATen un-normalises them again
