@@ -91,7 +91,8 @@ typedef struct pd_warp_in {
 } pd_warp_in;
 
 /* Number of per-pixel fp32 statistics saved for the backward pass: [B,PD_STATS(mixture),H,W].
- * non-mixture: {max logit, sum exp}.  mixture: {max logit, sum exp, sum exp/sigma, mixture density} */
+ * non-mixture: {reference logit * log2(e), sum exp(l - ref)}.  mixture: additionally {sum exp/sigma, mixture
+ * density sum pi*lap + 1e-7}.  Opaque to callers: only pd_warp_composite_bwd reads it. */
 #define PD_STATS_PLAIN 2
 #define PD_STATS_MIXTURE 4
 

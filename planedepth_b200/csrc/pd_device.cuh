@@ -44,8 +44,9 @@ __device__ __forceinline__ float roundtrip_fast(float p, float size_m1, float rc
     float q0 = __fmul_rn(p, rcp);
     float rem = __fmaf_rn(-q0, size_m1, p);
     float q = __fmaf_rn(rem, rcp, q0);
-    float g = __fmaf_rn(q, 2.0f, -1.0f);  // (q-0.5)*2: both steps exact-or-single-rounded identically
-    return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), size_m1);
+    float g = __fmaf_rn(q, 2.0f, -1.0f);  // (q-0.5)*2: the doubling is exact, so one rounding either way
+    // ((g+1)*0.5)*(size-1) == (g+1)*((size-1)/2): the halving is exact and (size-1)/2 is representable
+    return __fmul_rn(__fadd_rn(g, 1.0f), 0.5f * size_m1);
 }
 
 struct Taps {

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) warp_composite_fwd_general(const WarpPara
     rr[p.hw] = R1 * invD;
     rr[2 * p.hw] = R2 * invD;
     float* st = p.out.stats + (int64_t)b * (MIX ? PD_STATS_MIXTURE : PD_STATS_PLAIN) * p.hw + rem;
-    st[0] = Mx;
+    st[0] = Mx * kLog2e;  // reference logit in log2 units (shared convention with the row-tiled kernels)
     st[p.hw] = S;
     if (MIX) {
         float D = Q * invS + 1e-7f;  // layers.py:466
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) warp_composite_fwd_general(const WarpPara
             plane_coords<WARP>(p, b, n, y, x, u, v, m, aux);
             Taps t = make_taps(roundtrip(u, p.wm1), roundtrip(v, p.hm1), W, H);
             Sampled s = sample_plane<MIX>(p, b, n, t, m);
-            float e = fast_exp(s.l - Mx);
+            float e = fast_exp2(fmaf(s.l, kLog2e, -Mx * kLog2e));
             const int64_t o = ((int64_t)b * N + n) * p.hw + rem;
             if (p.out.rgb_rec_layered) {
                 float* q = p.out.rgb_rec_layered + ((int64_t)b * N + n) * p.chw3 + rem;
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) warp_composite_bwd_general(const WarpPara
     const float* rp = p.out.rgb_rec + (int64_t)b * p.chw3 + rem;
     const float Gbar = g0 * __ldg(rp) + g1 * __ldg(rp + p.hw) + g2 * __ldg(rp + 2 * p.hw);
     const float* st = p.out.stats + (int64_t)b * (MIX ? PD_STATS_MIXTURE : PD_STATS_PLAIN) * p.hw + rem;
-    const float Mx = __ldg(st), invS = 1.0f / __ldg(st + p.hw);
+    const float Ml2 = __ldg(st), invS = 1.0f / __ldg(st + p.hw);
     float tr = 0, tg = 0, tb = 0, invA = 0, gD = 0, gDD = 0;
     if (MIX) {
         const float* tp = p.in.tgt + (int64_t)b * p.chw3 + rem;
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256) warp_composite_bwd_general(const WarpPara
         TapVals vl = load_taps(p.in.logits + pl, t, W);
         float cr = blend(vr, t) * m, cg = blend(vg, t) * m, cb = blend(vb, t) * m;
         float l = blend(vl, t) * m;
-        float pi = fast_exp(l - Mx) * invS;
+        float pi = fast_exp2(fmaf(l, kLog2e, -Ml2)) * invS;
         float Gn = g0 * cr + g1 * cg + g2 * cb;
         float dl, dcr, dcg, dcb, dsg = 0.0f;
         TapVals vs;
