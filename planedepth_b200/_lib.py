@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libplanedepth_b200.so")
+LIB_PATH = os.environ.get("PLANEDEPTH_B200_LIB") or os.path.join(CSRC, "libplanedepth_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = [
@@ -101,6 +101,8 @@ def build_library(verbose: bool = False) -> str:
 
 
 def _needs_rebuild() -> bool:
+    if os.environ.get("PLANEDEPTH_B200_LIB"):
+        return False  # explicit library (kernel-variant experiments): use as is
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
