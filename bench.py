@@ -37,6 +37,10 @@ CONFIGS = {
     "cfg2": (12, 192, 640, dict(), "ssim_l1", "cfg2: B=12/GPU 640x192 N=49 stereo disp_warp + SSIM/L1, fwd+bwd"),
     "cfg3": (4, 384, 1280, dict(use_mixture_loss=True, plane_residual=True), None,
              "cfg3: B=4/GPU 1280x384 N=49 disp_warp + plane_residual + Laplacian mixture, fwd+bwd"),
+    # diagnostics (not BASELINE configs)
+    "dbg_mix": (4, 384, 1280, dict(use_mixture_loss=True), None, "debug: mixture only"),
+    "dbg_res": (4, 384, 1280, dict(plane_residual=True), None, "debug: residual only"),
+    "dbg_w": (4, 384, 1280, dict(), None, "debug: 1280 wide L1"),
 }
 METRIC = "training images/sec (49-plane warp+SSIM hot path, fwd+bwd)"
 UNIT = "images/s"
@@ -177,7 +181,7 @@ def cpu_step_fn(cfg_name, B_sample, seed=0):
         t.project_3d = ref_layers.Project3D(H, W)
 
         def step():
-            out = dict(batch.outputs)
+            out = batch.attach(dict(batch.outputs))
             ref_trainer.Trainer.pred_novel_images(t, batch.inputs, out)
             total = 0
             for s in batch.target_sides:
@@ -195,7 +199,7 @@ def cpu_step_fn(cfg_name, B_sample, seed=0):
     from oracle import pd_oracle as O
 
     def step():
-        out = dict(batch.outputs)
+        out = batch.attach(dict(batch.outputs))
         O.pred_novel_images(opt, batch.target_sides, batch.inputs, out)
         total = 0
         for s in batch.target_sides:
@@ -268,8 +272,19 @@ def run_ours(args):
     inputs = batch_gpu.inputs
     leaves = list(leaves_map.values())
     hp = HotPath(opt, batch.target_sides, pc_net=None, photometric=photometric)
-    step = make_step(hp, inputs, outputs, leaves)
-    graphed = GraphedStep(step, warmup=3)
+    step = make_step(hp, inputs, outputs, leaves, batch_gpu.attach)
+    if args.no_graph:
+        class _Eager:
+            result = None
+
+            def replay(self):
+                self.result = step()
+                return self.result
+
+        graphed = _Eager()
+        graphed.replay()
+    else:
+        graphed = GraphedStep(step, warmup=3)
 
     def barrier():
         if ws > 1:
@@ -372,7 +387,7 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * ws, "planes": N, "height": H, "width": W,
                    "photometric": photometric or ("mixture" if opt.use_mixture_loss else "l1"), "layout": args.layout,
-                   "parallelism": "dp%d (independent shards, no data-path collective)" % ws, "launch": "cuda_graph replay",
+                   "parallelism": "dp%d (independent shards, no data-path collective)" % ws, "launch": "eager" if args.no_graph else "cuda_graph replay",
                    "l2": "no flush: per-step working set (logits %.0f MB + grads %.0f MB) exceeds the 126 MB L2" % (
                        B * N * H * W * 4 / 1e6, B * N * H * W * 4 / 1e6),
                    "e2e_scope": "inputs dict pinned-host->device each step (trainer.py:328-329) + loss device->host; network outputs are device-born"},
@@ -396,6 +411,7 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--layout", default="reference", choices=["reference", "compact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -17,6 +17,10 @@
 #pragma once
 #include <stdlib.h>
 
+#include <atomic>
+#include <map>
+#include <mutex>
+
 #include "pd_warp_general.cuh"
 
 namespace pd {
@@ -698,9 +702,20 @@ inline float rows_rcp(int W) { return ((W & (W - 1)) == 0) ? 0.0f : 1.0f / (floa
 inline int rows_threads(int W) { return ((W / RP + 31) / 32) * 32; }
 inline size_t rows_smem_fwd(int N, int W) { return (size_t)3 * (W + 2 * ROW_PAD) * sizeof(float) + (size_t)N * sizeof(PlaneRow); }
 
+// Opt a kernel in to > 48 KB of dynamic shared memory.  Done once per kernel and size (never again for a
+// size already granted) so that steady-state launches issue no attribute call — those are not capturable
+// into a CUDA graph.
 template <typename K>
 inline void rows_launch_cfg(K kern, size_t smem) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static std::mutex mu;
+    static std::map<const void*, size_t> granted;  // keyed by kernel: instantiations share this function's type
+    if (smem <= 48 * 1024) return;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& g = granted[(const void*)kern];
+    if (smem > g) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        g = smem;
+    }
 }
 
 template <bool MIX, int MASKMODE>

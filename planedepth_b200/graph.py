@@ -33,12 +33,14 @@ class GraphedStep:
         return self.result
 
 
-def make_step(hp, inputs, outputs, leaves: List[torch.Tensor]):
+def make_step(hp, inputs, outputs, leaves: List[torch.Tensor], attach=None):
     """One training-style step of the path: pred_novel_images + compute_losses + backward into the
     given leaves.  Gradients are returned (not accumulated) so that replays overwrite them."""
 
     def step():
         out = dict(outputs)
+        if attach is not None:
+            attach(out)  # differentiable views of the plane geometry, re-derived per step like the decoder does
         losses = hp.process(inputs, out)
         grads = torch.autograd.grad(losses["loss/total_loss"], leaves, allow_unused=True)
         res = {"loss": losses["loss/total_loss"].detach()}

@@ -75,9 +75,14 @@ def make_batch(B: int, H: int, W: int, opt, seed: int = 0, device="cpu", layout:
     if opt.plane_residual and requires_grad:
         base.requires_grad_(True)
         leaves["disp_base"] = base
-    distance = 0.1 * 0.58 * W / base[:, :, 0, 0]
+    # Derived tensors are built from the detached leaf here; `attach()` (below) installs the differentiable
+    # views inside the step, the way the decoder re-derives them every step.  (A view made here would
+    # create the leaf's gradient accumulator on the legacy default stream, which a later CUDA-graph capture
+    # of the step is not allowed to synchronise with.)
+    based = base.detach()
+    distance = 0.1 * 0.58 * W / based[:, :, 0, 0]
     norm = torch.tensor([0.0, 0.0, 1.0], device=dev)[None, None].expand(B, n_v, 3)
-    disp_layered = base.expand(-1, -1, H, W)
+    disp_layered = based.expand(-1, -1, H, W)
     ones = torch.ones(B, n_v, 1, 1, device=dev)
     padding_mask = ones.expand(-1, -1, H, W) if layout == "compact" else torch.ones(B, n_v, H, W, device=dev)
     if n_xz:
@@ -90,11 +95,11 @@ def make_batch(B: int, H: int, W: int, opt, seed: int = 0, device="cpu", layout:
             h.requires_grad_(True)
             leaves["xz_h"] = h
         xz_mask = (gy >= 1e-7).expand(-1, n_xz, -1, -1)
-        Z = h.expand(-1, -1, H, W) * 1.92 / (gy.clamp_min(1e-7) / 2.0)
+        Z = h.detach().expand(-1, -1, H, W) * 1.92 / (gy.clamp_min(1e-7) / 2.0)
         disp_layered = torch.cat([disp_layered, 0.1 * 0.58 * W / Z], 1)
         padding_mask = torch.cat([padding_mask, xz_mask], 1)
         norm = torch.cat([norm, torch.tensor([0.0, 1.0, 0.0], device=dev)[None, None].expand(B, n_xz, 3)], 1)
-        distance = torch.cat([distance, h[:, :, 0, 0]], 1)
+        distance = torch.cat([distance, h.detach()[:, :, 0, 0]], 1)
     logits = (torch.randn(B, N, H, W, generator=g).to(dev) * padding_mask).contiguous()
     logits.requires_grad_(requires_grad)
     leaves["logits"] = logits
@@ -113,4 +118,20 @@ def make_batch(B: int, H: int, W: int, opt, seed: int = 0, device="cpu", layout:
         inputs[("Rt", f)] = T
         outputs[("Rt", f)] = T
     target_sides = ([] if opt.no_stereo else ["r"]) + frames
-    return SimpleNamespace(inputs=inputs, outputs=outputs, leaves=leaves, target_sides=target_sides, shape=(B, N, H, W))
+
+    def attach(out):
+        """Install the differentiable plane-geometry views (depth_decoder.py:153-183) into `out`."""
+        if "disp_base" not in leaves:
+            return out
+        b = leaves["disp_base"]
+        dl = b.expand(-1, -1, H, W)
+        dist = 0.1 * 0.58 * W / b[:, :, 0, 0]
+        if n_xz:
+            hh = leaves["xz_h"]
+            Zg = hh.expand(-1, -1, H, W) * 1.92 / (inputs["grid"][:, 1:, :, :].clamp_min(1e-7) / 2.0)
+            dl = torch.cat([dl, 0.1 * 0.58 * W / Zg], 1)
+            dist = torch.cat([dist, hh[:, :, 0, 0]], 1)
+        out["disp_layered"], out["distance"] = dl, dist
+        return out
+
+    return SimpleNamespace(inputs=inputs, outputs=outputs, leaves=leaves, target_sides=target_sides, shape=(B, N, H, W), attach=attach)
