@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PD_ABI_VERSION 1
+#define PD_ABI_VERSION 2
 
 typedef void* pd_stream_t; /* a cudaStream_t */
 
@@ -54,6 +54,14 @@ typedef enum pd_loss_mode { PD_LOSS_L1 = 0, PD_LOSS_MIXTURE = 1, PD_LOSS_SSIM_L1
 
 typedef enum pd_mask_dtype { PD_MASK_NONE = 0, PD_MASK_F32 = 1, PD_MASK_U8 = 2 } pd_mask_dtype;
 
+/* pd_warp_desc.flags.
+ * PD_FLAG_EXACT_COORDS: reproduce, bit for bit, the fp32 rounding of the reference's coordinate
+ * normalise / un-normalise round trip (trainer.py:549-551 + ATen grid_sampler_unnormalize), which moves
+ * sample positions by a few ulp of the coordinate (<= 1.2e-4 px at W = 1280).  Without the flag the
+ * stereo disparity fast path samples at the exact positions u = x + sign*d, v = y (deviations);
+ * homography / depth warps and dense disparities always use the reference's arithmetic. */
+typedef enum pd_warp_flags { PD_FLAG_EXACT_COORDS = 1 } pd_warp_flags;
+
 typedef struct pd_strides4 {
     int64_t b, n, y, x;
 } pd_strides4;
@@ -70,7 +78,7 @@ typedef struct pd_warp_desc {
     int32_t automask;       /* mixture only: also write nll_auto (trainer.py:731-734) */
     int32_t mask_dtype;     /* pd_mask_dtype of pd_warp_in.mask */
     float disp_sign;        /* PD_WARP_DISP: +1 target 'r', -1 target 'l', 0 otherwise (trainer.py:545-548) */
-    int32_t reserved0;
+    int32_t flags;          /* bit set of pd_warp_flags */
     pd_strides4 disp_stride; /* PD_WARP_DISP / PD_WARP_DEPTH: strides of disp_layered (0 allowed:
                                 depth_decoder.py:156 hands out a stride-0 expand) */
     pd_strides4 mask_stride; /* strides of padding_mask */

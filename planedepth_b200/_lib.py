@@ -22,6 +22,8 @@ NVCC_FLAGS = [
 PD_WARP_DISP, PD_WARP_HOMOGRAPHY, PD_WARP_DEPTH = 0, 1, 2
 PD_LOSS_L1, PD_LOSS_MIXTURE, PD_LOSS_SSIM_L1 = 0, 1, 2
 PD_MASK_NONE, PD_MASK_F32, PD_MASK_U8 = 0, 1, 2
+PD_FLAG_EXACT_COORDS = 1
+ABI_VERSION = 2  # PD_ABI_VERSION in include/planedepth_b200.h
 PD_STATS_PLAIN, PD_STATS_MIXTURE = 2, 4
 
 EXPORTS = [
@@ -39,7 +41,7 @@ class WarpDesc(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("warp_type", C.c_int32), ("mixture", C.c_int32), ("automask", C.c_int32), ("mask_dtype", C.c_int32),
-        ("disp_sign", C.c_float), ("reserved0", C.c_int32),
+        ("disp_sign", C.c_float), ("flags", C.c_int32),
         ("disp_stride", Strides4), ("mask_stride", Strides4),
     ]
 
@@ -151,8 +153,8 @@ def lib() -> C.CDLL:
                                      C.c_void_p, C.c_void_p]
     L.pd_debug_roundtrip.restype = C.c_int
     L.pd_debug_roundtrip.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
-    if L.pd_version() != 1:
-        raise PlaneDepthLibraryError("ABI version mismatch: library %d, binding 1" % L.pd_version())
+    if L.pd_version() != ABI_VERSION:
+        raise PlaneDepthLibraryError("ABI version mismatch: library %d, binding %d" % (L.pd_version(), ABI_VERSION))
     _lib = L
     return L
 

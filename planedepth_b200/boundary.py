@@ -66,6 +66,9 @@ class HotPathMixin:
 
     #: also materialise the per-plane tensors of trainer.py:582-602 (costs 5*N extra planes of HBM writes)
     materialize_layered: bool = False
+    #: reproduce the fp32 rounding of the reference's coordinate normalise / un-normalise round trip bit for bit
+    #: (PD_FLAG_EXACT_COORDS); the default stereo fast path samples at the exact positions instead
+    exact_coords: bool = False
     #: photometric term: None = reference behaviour (mixture NLL if opt.use_mixture_loss else L1);
     #: "ssim_l1" = 0.85*SSIM + 0.15*L1 (compute_reprojection_loss, trainer.py:687-699) on the novel view
     photometric: Optional[str] = None
@@ -97,7 +100,7 @@ class HotPathMixin:
                 mask = outputs["padding_mask"]  # upstream dereferences an unbound local here (defect D1)
                 cam = depth_warp_params(inputs[("Rt", side)], inputs["K"], inputs["inv_K"])
             cfg = WarpConfig(warp_type=_WARP[wt], mixture=mixture, automask=automask, disp_sign=sign, shape=(B, N, H, W),
-                             layered=bool(self.materialize_layered))
+                             layered=bool(self.materialize_layered), exact_coords=bool(self.exact_coords))
             tgt = inputs[(color, side)] if mixture else None
             rgb_rec, nll, nll_auto, layered = warp_composite(
                 cfg, src, tgt, outputs["logits"], outputs.get("sigma") if mixture else None, disp, mask, hmat, cam)
@@ -186,7 +189,8 @@ class HotPath(HotPathMixin):
     """Stand-alone carrier of the attributes the two methods read from ``self`` (what tests, bench.py
     and smoke() instantiate instead of the full Trainer, whose constructor needs NCCL + KITTI)."""
 
-    def __init__(self, opt, target_sides=None, pc_net=None, photometric: Optional[str] = None, materialize_layered: bool = False):
+    def __init__(self, opt, target_sides=None, pc_net=None, photometric: Optional[str] = None, materialize_layered: bool = False,
+                 exact_coords: bool = False):
         self.opt = opt
         if target_sides is None:
             target_sides = ([] if _flag(opt, "no_stereo", False) else ["r"]) + list(_flag(opt, "novel_frame_ids", []))
@@ -194,6 +198,7 @@ class HotPath(HotPathMixin):
         self.pc_net = pc_net
         self.photometric = photometric
         self.materialize_layered = materialize_layered
+        self.exact_coords = exact_coords
 
     def process(self, inputs, outputs):
         self.pred_novel_images(inputs, outputs)

@@ -10,6 +10,7 @@
 #include "pd_loss.cuh"
 #include "pd_warp_general.cuh"
 #include "pd_warp_rows.cuh"
+#include "pd_warp_stream.cuh"
 
 namespace {
 
@@ -30,6 +31,9 @@ int check_launch(const char* what) {
     ++g_launches;
     return PD_OK;
 }
+
+// bit-faithful coordinate arithmetic requested by the caller (or forced for a whole process, for tests)
+bool exact_coords(const pd_warp_desc* d) { return (d->flags & PD_FLAG_EXACT_COORDS) || getenv("PD_EXACT_COORDS"); }
 
 int check_device() {
     int dev = 0;
@@ -162,6 +166,8 @@ int pd_warp_composite_fwd(const pd_warp_desc* d, const pd_warp_in* in, pd_warp_o
     pd::WarpParams p = make_params(d, in);
     p.out = *out;
     const bool debug = out->rgb_rec_layered || out->logit_rec || out->probability_rec || out->sigma_rec || out->pi_rec;
+    if (!debug && !exact_coords(d) && pd::ts::stream_path_supported(p) && pd::ts::launch_fwd_stream(p, st))
+        return check_launch("rows_fwd_stream");
     if (!debug && pd::rows_path_supported(p)) {
         pd::launch_fwd_rows(p, st);
         return check_launch("warp_composite_fwd_rows");
@@ -196,7 +202,8 @@ int pd_warp_composite_bwd(const pd_warp_desc* d, const pd_warp_in* in, const pd_
 
     const size_t plane_bytes = (size_t)d->B * d->N * p.hw * sizeof(float);
     cudaError_t e = cudaSuccess;
-    const bool rows = pd::rows_path_supported(p);
+    const bool streamed = !exact_coords(d) && pd::ts::stream_path_supported(p) && pd::ts::stream_bwd_fits(p);
+    const bool rows = streamed || pd::rows_path_supported(p);
     // scatter targets are accumulated with atomics in the general path: zero them first
     if (!rows) {
         if (p.gin.g_logits) e = cudaMemsetAsync(p.gin.g_logits, 0, plane_bytes, st);
@@ -206,6 +213,10 @@ int pd_warp_composite_bwd(const pd_warp_desc* d, const pd_warp_in* in, const pd_
         e = cudaMemsetAsync(p.gin.g_disp, 0, (size_t)strided_extent(gs, d->B, d->N, d->H, d->W) * sizeof(float), st);
     if (e == cudaSuccess && p.gin.g_hmat) e = cudaMemsetAsync(p.gin.g_hmat, 0, (size_t)d->B * d->N * 9 * sizeof(float), st);
     if (e != cudaSuccess) return fail(PD_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    if (streamed) {
+        if (!pd::ts::launch_bwd_stream(p, st)) return fail(PD_ERR_SHAPE, "rows_bwd_stream: no launch configuration");
+        return check_launch("rows_bwd_stream");
+    }
     if (rows) {
         pd::launch_bwd_rows(p, st);
         return check_launch("warp_composite_bwd_rows");

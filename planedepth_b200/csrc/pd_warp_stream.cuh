@@ -1,0 +1,961 @@
+// Streamed row kernels for stereo disparity warps (trainer.py:540-554) whose disparity does not vary
+// along x (vertical planes: one scalar per (image, plane); xz ground planes: one scalar per row —
+// depth_decoder.py:153-156, 163-181).  Same job as pd_warp_rows.cuh, re-organised around the B200
+// memory system:
+//   * every logit / sigma / mask row is brought into shared memory by the TMA engine
+//     (cp.async.bulk, 1-D) into a two-block ring, completion signalled on mbarriers; compute threads
+//     issue no global loads in the plane loop and the prefetch distance is 1-2 blocks of planes;
+//   * the source rgb rows are TMA-staged the same way, double-buffered across row groups;
+//   * a plane's warp is "shift by k0 = floor(d) and lerp with frac(d)": the per-(row, plane)
+//     coefficients (k0, the two weights, pre-multiplied by the row mask and by log2(e) for the logit)
+//     are computed once per row group into shared memory, so a sample costs 2 FMAs per channel;
+//   * taps are read as aligned 128-bit shared-memory windows; the softmax over planes is online with a
+//     lazily moved reference (one ex2 per sample);
+//   * the backward is a gather: per-target dL/dlogit (dL/dsigma) rows are exchanged through a
+//     double-buffered shared-memory block and each gradient row is written once with 128-bit streaming
+//     stores (no atomics, no zero-fill); one __syncthreads per block of planes in both directions.
+//
+// Coordinates: u = x + sign*d and v = y are used exactly.  The reference evaluates the same numbers
+// through an fp32 normalise / un-normalise round trip (trainer.py:549-551 + ATen
+// grid_sampler_unnormalize) that perturbs them by a few ulp of the coordinate (<= 6e-5 px at W=640,
+// 1.2e-4 px at W=1280); pd_warp_rows.cuh reproduces that perturbation bit for bit and is selected with
+// PD_FLAG_EXACT_COORDS.  DESIGN.md (deviations) quantifies the difference.
+#pragma once
+#include <stdlib.h>
+
+#include <map>
+#include <mutex>
+
+#include "pd_warp_general.cuh"
+
+namespace pd {
+namespace ts {
+
+constexpr int PAD = 12;  // zero floats on both sides of every shared-memory row (>= window size)
+
+struct __align__(16) PlaneCoef {
+    int k0;          // floor(sign * disparity), clamped so that x + k0 cannot overflow
+    float wc0, wc1;  // (1 - frac) * m, frac * m           (colour / sigma taps, gradient gather)
+    float wl0;       // wc0 * log2(e)                       (logit taps, softmax in base 2)
+    float wl1;       // wc1 * log2(e)
+    float m;         // row mask value (1 when the mask is dense or absent)
+    float pad0, pad1;
+};
+
+struct StreamCfg {
+    int rpc;      // rows per CTA iteration ("row group")
+    int tpr;      // threads per row = W / PX
+    int pitch;    // floats per shared row = W + 2 * PAD
+    int hs;       // planes per pipeline block
+    int nblk;     // blocks per row group = ceil(N / hs)
+    int ngroups;  // ceil(B * H / rpc)
+};
+
+enum { SMASK_ROW = 0, SMASK_DENSE = 1 };
+
+// ------------------------------------------------------------------------------------------------
+// mbarrier / TMA primitives (PTX; SASS: SYNCS / UBLKCP)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned)
+__device__ __forceinline__ void tma_row(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ float4 lds128(const float* q) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(q)));
+    return v;
+}
+
+template <int WF>
+__device__ __forceinline__ void load_window(const float* q, float (&v)[WF]) {
+#pragma unroll
+    for (int i = 0; i < WF / 4; ++i) {
+        float4 t = lds128(q + 4 * i);
+        v[4 * i] = t.x, v[4 * i + 1] = t.y, v[4 * i + 2] = t.z, v[4 * i + 3] = t.w;
+    }
+}
+
+template <int PX>
+__device__ __forceinline__ void load_px_global(const float* q, float (&v)[PX]) {
+#pragma unroll
+    for (int i = 0; i < PX / 4; ++i) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(q) + i);
+        v[4 * i] = t.x, v[4 * i + 1] = t.y, v[4 * i + 2] = t.z, v[4 * i + 3] = t.w;
+    }
+}
+
+template <int PX>
+__device__ __forceinline__ void store_px_global(float* q, const float (&v)[PX]) {
+#pragma unroll
+    for (int i = 0; i < PX / 4; ++i) reinterpret_cast<float4*>(q)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
+template <int PX>
+__device__ __forceinline__ void store_px_stream(float* q, const float (&v)[PX]) {
+#pragma unroll
+    for (int i = 0; i < PX / 4; ++i) __stcs(reinterpret_cast<float4*>(q) + i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory carve-up, common to both kernels
+// ------------------------------------------------------------------------------------------------
+struct Smem {
+    uint64_t* bars;   // [0,1] ring halves, [2,3] source-row buffers
+    PlaneCoef* coef;  // [2][rpc][N]
+    float* src;       // [2][rpc][3][pitch]
+    float* lring;     // [2*hs][rpc][pitch]
+    float* sring;     // mixture: [2*hs][rpc][pitch]
+    float* mring;     // dense mask: [2*hs][rpc][pitch]
+    float* dbuf;      // backward: [2][hs][NE][rpc][pitch] exchange rows (NE = 1, mixture 2)
+    float* gacc;      // backward with d/d disp: [rpc][N]
+    float* fend;      // one past the last float
+};
+
+__host__ __device__ inline size_t stream_smem_floats(const StreamCfg& c, int N, bool mix, bool dense, int ne_bwd, bool want_disp) {
+    size_t rowf = (size_t)c.rpc * c.pitch;
+    size_t f = 2 * 3 * rowf + (size_t)2 * c.hs * rowf * (1 + (mix ? 1 : 0) + (dense ? 1 : 0));
+    f += (size_t)2 * c.hs * ne_bwd * rowf;
+    if (want_disp) f += (size_t)c.rpc * N;
+    return f;
+}
+
+__host__ __device__ inline size_t stream_smem_bytes(const StreamCfg& c, int N, bool mix, bool dense, int ne_bwd, bool want_disp) {
+    return 64 + (size_t)2 * c.rpc * N * sizeof(PlaneCoef) + stream_smem_floats(c, N, mix, dense, ne_bwd, want_disp) * sizeof(float) + 16;
+}
+
+__device__ __forceinline__ Smem carve(unsigned char* raw, const StreamCfg& c, int N, bool mix, bool dense, int ne_bwd, bool want_disp) {
+    Smem s;
+    const size_t rowf = (size_t)c.rpc * c.pitch;
+    s.bars = reinterpret_cast<uint64_t*>(raw);
+    s.coef = reinterpret_cast<PlaneCoef*>(raw + 64);
+    s.src = reinterpret_cast<float*>(s.coef + (size_t)2 * c.rpc * N);
+    s.lring = s.src + 2 * 3 * rowf;
+    float* q = s.lring + (size_t)2 * c.hs * rowf;
+    s.sring = q;
+    if (mix) q += (size_t)2 * c.hs * rowf;
+    s.mring = q;
+    if (dense) q += (size_t)2 * c.hs * rowf;
+    s.dbuf = q;
+    q += (size_t)2 * c.hs * ne_bwd * rowf;
+    s.gacc = q;
+    if (want_disp) q += (size_t)c.rpc * N;
+    s.fend = q;
+    return s;
+}
+
+// The zero pads on both sides of every shared row are written once and never touched again (TMA and the
+// exchange stores only write the W interior floats); row interiors need no initialisation.
+__device__ __forceinline__ void zero_pads(const Smem& s, const StreamCfg& c, int W) {
+    const int nrows = (int)((s.gacc - s.src) / c.pitch);
+    for (int i = threadIdx.x; i < nrows * 2 * PAD; i += blockDim.x) {
+        const int rw = i / (2 * PAD), q = i - rw * 2 * PAD;
+        s.src[(size_t)rw * c.pitch + (q < PAD ? q : W + q)] = 0.0f;
+    }
+}
+
+// Producer side (one thread): TMA requests for the source rows of a row group / for one block of planes.
+struct Producer {
+    const WarpParams& p;
+    const StreamCfg& c;
+    const Smem& s;
+    int rows_total;
+    bool mix, dense;
+
+    __device__ __forceinline__ void src_rows(int it, int g) const {
+        const int W = p.d.W, H = p.d.H;
+        uint64_t* bar = s.bars + 2 + (it & 1);
+        int nrows = min(c.rpc, rows_total - g * c.rpc);
+        mbar_expect_tx(bar, (uint32_t)(nrows * 3 * W * sizeof(float)));
+        for (int r = 0; r < nrows; ++r) {
+            const int row = g * c.rpc + r, b = row / H, y = row - b * H;
+            for (int ch = 0; ch < 3; ++ch)
+                tma_row(s.src + ((size_t)((it & 1) * c.rpc + r) * 3 + ch) * c.pitch + PAD, p.in.src + (((int64_t)b * 3 + ch) * H + y) * W,
+                        (uint32_t)(W * sizeof(float)), bar);
+        }
+    }
+
+    __device__ __forceinline__ void block(int jb, int g, int j) const {
+        const int W = p.d.W, H = p.d.H, N = p.d.N;
+        const int half = jb & 1;
+        uint64_t* bar = s.bars + half;
+        const int nrows = min(c.rpc, rows_total - g * c.rpc);
+        const int n0 = j * c.hs, n1 = min(N, n0 + c.hs);
+        const int streams = 1 + (mix ? 1 : 0) + (dense ? 1 : 0);
+        mbar_expect_tx(bar, (uint32_t)((n1 - n0) * nrows * streams * W * sizeof(float)));
+        for (int n = n0; n < n1; ++n) {
+            for (int r = 0; r < nrows; ++r) {
+                const int row = g * c.rpc + r, b = row / H, y = row - b * H;
+                const size_t slot = ((size_t)(half * c.hs + (n - n0)) * c.rpc + r) * c.pitch + PAD;
+                const int64_t off = (((int64_t)b * N + n) * H + y) * W;
+                tma_row(s.lring + slot, p.in.logits + off, (uint32_t)(W * sizeof(float)), bar);
+                if (mix) tma_row(s.sring + slot, p.in.sigma + off, (uint32_t)(W * sizeof(float)), bar);
+                if (dense)
+                    tma_row(s.mring + slot, reinterpret_cast<const float*>(p.in.mask) + soff(p.d.mask_stride, b, n, y, 0), (uint32_t)(W * sizeof(float)), bar);
+            }
+        }
+    }
+};
+
+// per-(row, plane) coefficients of row group g into coef buffer `buf`
+template <int MASKMODE>
+__device__ __forceinline__ void stage_coef(const WarpParams& p, const StreamCfg& c, PlaneCoef* coef, int g, int rows_total) {
+    const int N = p.d.N, H = p.d.H, W = p.d.W;
+    for (int idx = threadIdx.x; idx < c.rpc * N; idx += blockDim.x) {
+        const int r = idx / N, n = idx - r * N;
+        const int row = g * c.rpc + r;
+        PlaneCoef k;
+        k.k0 = W + 16, k.wc0 = k.wc1 = k.wl0 = k.wl1 = 0.0f, k.m = 0.0f, k.pad0 = k.pad1 = 0.0f;
+        if (row < rows_total) {
+            const int b = row / H, y = row - b * H;
+            const float d = __ldg(p.in.disp + soff(p.d.disp_stride, b, n, y, 0));
+            const float sd = p.d.disp_sign * d;
+            const float kf = floorf(sd);
+            const bool sane = fabsf(sd) < (float)(W + 8);  // otherwise every tap is out of range
+            const float w1 = sane ? sd - kf : 0.0f;
+            const float m = (MASKMODE == SMASK_ROW) ? load_mask(p.in.mask, p.d.mask_dtype, soff(p.d.mask_stride, b, n, y, 0)) : 1.0f;
+            k.k0 = sane ? (int)kf : W + 16;
+            k.m = m;
+            k.wc1 = w1 * m;
+            k.wc0 = (1.0f - w1) * m;
+            k.wl0 = k.wc0 * kLog2e;
+            k.wl1 = k.wc1 * kLog2e;
+        }
+        coef[idx] = k;
+    }
+}
+
+__device__ __forceinline__ PlaneCoef load_coef(const PlaneCoef* q) {
+    const float4 a = lds128(reinterpret_cast<const float*>(q));
+    const float4 b = lds128(reinterpret_cast<const float*>(q) + 4);
+    PlaneCoef k;
+    k.k0 = __float_as_int(a.x), k.wc0 = a.y, k.wc1 = a.z, k.wl0 = a.w, k.wl1 = b.x, k.m = b.y;
+    return k;
+}
+
+// window base (multiple of 4, clamped into the zero pads) of taps starting at column a
+__device__ __forceinline__ int window_base(int a, int W) { return min(max(a & ~3, -PAD), W); }
+
+template <int PX>
+__device__ __forceinline__ bool all_ones(const float (&m)[PX]) {
+    unsigned acc = 0xffffffffu, orr = 0u;
+#pragma unroll
+    for (int i = 0; i < PX; ++i) acc &= __float_as_uint(m[i]), orr |= __float_as_uint(m[i]);
+    return acc == 0x3f800000u && orr == 0x3f800000u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <bool MIX, int PX>
+struct FwdAcc {
+    float Ml2[PX], S[PX], R0[PX], R1[PX], R2[PX];
+    float A[MIX ? PX : 1], Q[MIX ? PX : 1], Qa[MIX ? PX : 1];
+    float tr[MIX ? PX : 1], tg[MIX ? PX : 1], tb[MIX ? PX : 1], ea[MIX ? PX : 1];
+};
+
+template <bool MIX, int PX, int R, bool PERPIX>
+__device__ __forceinline__ void fwd_plane(const float* srow, const float* lrow, const float* sgrow, int pitch, int bc, const PlaneCoef& k,
+                                          const float (&mm)[PX], FwdAcc<MIX, PX>& a) {
+    constexpr int WF = PX + 4;
+    float v[WF], t[PX];
+    load_window<WF>(lrow + bc, v);
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+        if (PERPIX) t[i] = fmaf(fmaf(k.wl0, v[R + i], k.wl1 * v[R + i + 1]), mm[i], -a.Ml2[i]);
+        else t[i] = fmaf(k.wl0, v[R + i], fmaf(k.wl1, v[R + i + 1], -a.Ml2[i]));
+    }
+    float tmx = t[0];
+#pragma unroll
+    for (int i = 1; i < PX; ++i) tmx = fmaxf(tmx, t[i]);
+    if (tmx > 64.0f) {
+        // move the softmax reference of the pixels whose logit ran away from it (always on the first plane:
+        // the reference starts at -inf); exp2(t) cannot overflow below that threshold
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+            if (t[i] > 64.0f) {
+                float nl2 = fmaf(k.wl0, v[R + i], k.wl1 * v[R + i + 1]);
+                if (PERPIX) nl2 *= mm[i];
+                const float sc = fast_exp2(a.Ml2[i] - nl2);
+                a.S[i] *= sc, a.R0[i] *= sc, a.R1[i] *= sc, a.R2[i] *= sc;
+                if constexpr (MIX) { a.A[i] *= sc, a.Q[i] *= sc, a.Qa[i] *= sc; }
+                a.Ml2[i] = nl2;
+                t[i] = 0.0f;
+            }
+        }
+    }
+    float e[PX];
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+        e[i] = fast_exp2(t[i]);
+        a.S[i] += e[i];
+    }
+    if constexpr (!MIX) {
+        float a0[PX], a1[PX];
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+            const float em = PERPIX ? e[i] * mm[i] : e[i];
+            a0[i] = em * k.wc0, a1[i] = em * k.wc1;
+        }
+        load_window<WF>(srow + bc, v);
+#pragma unroll
+        for (int i = 0; i < PX; ++i) a.R0[i] = fmaf(a0[i], v[R + i], fmaf(a1[i], v[R + i + 1], a.R0[i]));
+        load_window<WF>(srow + pitch + bc, v);
+#pragma unroll
+        for (int i = 0; i < PX; ++i) a.R1[i] = fmaf(a0[i], v[R + i], fmaf(a1[i], v[R + i + 1], a.R1[i]));
+        load_window<WF>(srow + 2 * pitch + bc, v);
+#pragma unroll
+        for (int i = 0; i < PX; ++i) a.R2[i] = fmaf(a0[i], v[R + i], fmaf(a1[i], v[R + i + 1], a.R2[i]));
+    } else {
+        float es[PX], inv[PX], err[PX];
+        load_window<WF>(sgrow + bc, v);
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+            float s = fmaf(k.wc0, v[R + i], k.wc1 * v[R + i + 1]);
+            if (PERPIX) s *= mm[i];
+            const float sg = fminf(fmaxf(s, 0.01f), 1.0f);  // trainer.py:597
+            inv[i] = fast_rcp(sg);
+            es[i] = e[i] * inv[i];
+            a.A[i] += es[i];
+        }
+        load_window<WF>(srow + bc, v);
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+            float c = fmaf(k.wc0, v[R + i], k.wc1 * v[R + i + 1]);
+            if (PERPIX) c *= mm[i];
+            a.R0[i] = fmaf(es[i], c, a.R0[i]);
+            err[i] = fabsf(c - a.tr[i]);
+        }
+        load_window<WF>(srow + pitch + bc, v);
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+            float c = fmaf(k.wc0, v[R + i], k.wc1 * v[R + i + 1]);
+            if (PERPIX) c *= mm[i];
+            a.R1[i] = fmaf(es[i], c, a.R1[i]);
+            err[i] += fabsf(c - a.tg[i]);
+        }
+        load_window<WF>(srow + 2 * pitch + bc, v);
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+            float c = fmaf(k.wc0, v[R + i], k.wc1 * v[R + i + 1]);
+            if (PERPIX) c *= mm[i];
+            a.R2[i] = fmaf(es[i], c, a.R2[i]);
+            err[i] += fabsf(c - a.tb[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+            const float il2 = inv[i] * (kLog2e * (1.0f / 3.0f));  // err holds the channel SUM
+            const float hes = 0.5f * es[i];                      // e * 0.5 / sigma
+            a.Q[i] = fmaf(hes, fast_exp2(-err[i] * il2), a.Q[i]);  // layers.py:454-455
+            a.Qa[i] = fmaf(hes, fast_exp2(-a.ea[i] * il2), a.Qa[i]);
+        }
+    }
+}
+
+template <bool MIX, int PX, bool PERPIX>
+__device__ __forceinline__ void fwd_plane_any(const float* srow, const float* lrow, const float* sgrow, int pitch, int x0, int W, const PlaneCoef& k,
+                                              const float (&mm)[PX], FwdAcc<MIX, PX>& a) {
+    const int at = x0 + k.k0;
+    const int bc = window_base(at, W);
+    switch (at & 3) {
+        case 0: fwd_plane<MIX, PX, 0, PERPIX>(srow, lrow, sgrow, pitch, bc, k, mm, a); break;
+        case 1: fwd_plane<MIX, PX, 1, PERPIX>(srow, lrow, sgrow, pitch, bc, k, mm, a); break;
+        case 2: fwd_plane<MIX, PX, 2, PERPIX>(srow, lrow, sgrow, pitch, bc, k, mm, a); break;
+        default: fwd_plane<MIX, PX, 3, PERPIX>(srow, lrow, sgrow, pitch, bc, k, mm, a); break;
+    }
+}
+
+template <bool MIX, int MASKMODE, int PX, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParams p, const StreamCfg cfg) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr bool DENSE = (MASKMODE == SMASK_DENSE);
+    const int W = p.d.W, H = p.d.H, N = p.d.N, pitch = cfg.pitch, rpc = cfg.rpc, hs = cfg.hs, NB = cfg.nblk;
+    const int rows_total = p.d.B * H;
+    const Smem s = carve(smem_raw, cfg, N, MIX, DENSE, 0, false);
+    zero_pads(s, cfg, W);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(s.bars + i, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int nit = (cfg.ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const Producer prod{p, cfg, s, rows_total, MIX, DENSE};
+    if (threadIdx.x == 0 && nit > 0) {
+        prod.src_rows(0, blockIdx.x);
+        prod.block(0, blockIdx.x, 0);
+    }
+    const int r = threadIdx.x / cfg.tpr;
+    const int x0 = (threadIdx.x - r * cfg.tpr) * PX;
+
+    for (int it = 0; it < nit; ++it) {
+        const int g = blockIdx.x + it * gridDim.x;
+        const int row = g * rpc + r;
+        const bool active = (r < rpc) && (row < rows_total);
+        const int b = active ? row / H : 0, y = active ? row - b * H : 0;
+        const int64_t rem = (int64_t)y * W + x0;
+        stage_coef<MASKMODE>(p, cfg, s.coef + (size_t)(it & 1) * rpc * N, g, rows_total);
+
+        FwdAcc<MIX, PX> acc;
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+            acc.Ml2[i] = -INFINITY, acc.S[i] = acc.R0[i] = acc.R1[i] = acc.R2[i] = 0.0f;
+            if constexpr (MIX) acc.A[i] = acc.Q[i] = acc.Qa[i] = acc.ea[i] = 0.0f;
+        }
+        if constexpr (MIX) if (active) {
+            const float* tp = p.in.tgt + (int64_t)b * p.chw3 + rem;
+            load_px_global<PX>(tp, acc.tr);
+            load_px_global<PX>(tp + p.hw, acc.tg);
+            load_px_global<PX>(tp + 2 * p.hw, acc.tb);
+            if (p.d.automask) {
+                const float* sp = p.in.src + (int64_t)b * p.chw3 + rem;
+                float sr[PX], sg[PX], sb[PX];
+                load_px_global<PX>(sp, sr);
+                load_px_global<PX>(sp + p.hw, sg);
+                load_px_global<PX>(sp + 2 * p.hw, sb);
+#pragma unroll
+                for (int i = 0; i < PX; ++i) acc.ea[i] = fabsf(sr[i] - acc.tr[i]) + fabsf(sg[i] - acc.tg[i]) + fabsf(sb[i] - acc.tb[i]);  // channel SUM
+            }
+        }
+        const PlaneCoef* coef = s.coef + ((size_t)(it & 1) * rpc + r) * N;
+        const float* srow = s.src + ((size_t)((it & 1) * rpc + r) * 3) * pitch + PAD;
+
+        for (int j = 0; j < NB; ++j) {
+            const int jb = it * NB + j;
+            __syncthreads();  // block jb-1 fully consumed; coefficients of this group visible
+            if (threadIdx.x == 0) {
+                if (j + 1 < NB) prod.block(jb + 1, g, j + 1);
+                else if (it + 1 < nit) prod.block(jb + 1, g + gridDim.x, 0);
+                if (j == 0 && it + 1 < nit) prod.src_rows(it + 1, g + gridDim.x);
+            }
+            if (!active) continue;
+            if (j == 0) mbar_wait(s.bars + 2 + (it & 1), (it >> 1) & 1);
+            mbar_wait(s.bars + (jb & 1), (jb >> 1) & 1);
+            const int n0 = j * hs, n1 = min(N, n0 + hs);
+            for (int n = n0; n < n1; ++n) {
+                const PlaneCoef k = load_coef(coef + n);
+                const size_t slot = ((size_t)((jb & 1) * hs + (n - n0)) * rpc + r) * pitch + PAD;
+                float mm[PX] = {};
+                bool perpix = false;
+                if (DENSE) {
+                    load_window<PX>(s.mring + slot + x0, mm);
+                    perpix = !all_ones<PX>(mm);
+                }
+                if (DENSE && perpix) fwd_plane_any<MIX, PX, true>(srow, s.lring + slot, s.sring + slot, pitch, x0, W, k, mm, acc);
+                else fwd_plane_any<MIX, PX, false>(srow, s.lring + slot, s.sring + slot, pitch, x0, W, k, mm, acc);
+            }
+        }
+        if (!active) continue;
+        float o0[PX], o1[PX], o2[PX];
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+            float invD;
+            if constexpr (MIX) invD = 1.0f / acc.A[i];
+            else invD = 1.0f / acc.S[i];
+            o0[i] = acc.R0[i] * invD, o1[i] = acc.R1[i] * invD, o2[i] = acc.R2[i] * invD;
+        }
+        float* rr = p.out.rgb_rec + (int64_t)b * p.chw3 + rem;
+        store_px_global<PX>(rr, o0);
+        store_px_global<PX>(rr + p.hw, o1);
+        store_px_global<PX>(rr + 2 * p.hw, o2);
+        float* st = p.out.stats + (int64_t)b * (MIX ? PD_STATS_MIXTURE : PD_STATS_PLAIN) * p.hw + rem;
+        store_px_global<PX>(st, acc.Ml2);
+        store_px_global<PX>(st + p.hw, acc.S);
+        if constexpr (MIX) {
+            float dq[PX], nl[PX], na[PX];
+#pragma unroll
+            for (int i = 0; i < PX; ++i) {
+                const float invS = 1.0f / acc.S[i];
+                dq[i] = acc.Q[i] * invS + 1e-7f;  // layers.py:466
+                nl[i] = -logf(dq[i]);
+                na[i] = -logf(acc.Qa[i] * invS + 1e-7f);
+            }
+            store_px_global<PX>(st + 2 * p.hw, acc.A);
+            store_px_global<PX>(st + 3 * p.hw, dq);
+            store_px_global<PX>(p.out.nll + (int64_t)b * p.hw + rem, nl);
+            if (p.d.automask) store_px_global<PX>(p.out.nll_auto + (int64_t)b * p.hw + rem, na);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+template <bool MIX, int PX>
+struct BwdCtx {
+    float g0[PX], g1[PX], g2[PX], Gbar[PX], Ml2[PX], invS[PX];
+    float tr[MIX ? PX : 1], tg[MIX ? PX : 1], tb[MIX ? PX : 1], Zinv[MIX ? PX : 1], gD[MIX ? PX : 1], gDD[MIX ? PX : 1];
+};
+
+__device__ __forceinline__ float sgn(float a, float b) { return (a > b) ? 1.0f : ((a < b) ? -1.0f : 0.0f); }
+
+// phase A of one plane: dL/d(masked logit) [and dL/d(clamped-through sigma)] per target pixel into the exchange
+// rows; returns this thread's contribution to dL/d(sign*disparity) of the plane row
+template <bool MIX, bool WANT_DISP, int PX, int R, bool PERPIX>
+__device__ __forceinline__ float bwd_plane(const float* srow, const float* lrow, const float* sgrow, int pitch, int bc, const PlaneCoef& k,
+                                           const float (&mm)[PX], const BwdCtx<MIX, PX>& c, float* drow, float* frow, int x0) {
+    constexpr int WF = PX + 4;
+    float v[WF], pi[PX], Gn[PX], dlu[PX], gx[PX];
+    load_window<WF>(lrow + bc, v);
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+        float t;
+        if (PERPIX) t = fmaf(fmaf(k.wl0, v[R + i], k.wl1 * v[R + i + 1]), mm[i], -c.Ml2[i]);
+        else t = fmaf(k.wl0, v[R + i], fmaf(k.wl1, v[R + i + 1], -c.Ml2[i]));
+        pi[i] = fast_exp2(t) * c.invS[i];
+        if (WANT_DISP) dlu[i] = v[R + i + 1] - v[R + i];
+    }
+    float cr[PX], cg[PX], cb[PX], dr[WANT_DISP ? PX : 1], dg[WANT_DISP ? PX : 1], db[WANT_DISP ? PX : 1];
+    load_window<WF>(srow + bc, v);
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+        cr[i] = fmaf(k.wc0, v[R + i], k.wc1 * v[R + i + 1]);
+        if (PERPIX) cr[i] *= mm[i];
+        if (WANT_DISP) dr[i] = v[R + i + 1] - v[R + i];
+    }
+    load_window<WF>(srow + pitch + bc, v);
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+        cg[i] = fmaf(k.wc0, v[R + i], k.wc1 * v[R + i + 1]);
+        if (PERPIX) cg[i] *= mm[i];
+        if (WANT_DISP) dg[i] = v[R + i + 1] - v[R + i];
+    }
+    load_window<WF>(srow + 2 * pitch + bc, v);
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+        cb[i] = fmaf(k.wc0, v[R + i], k.wc1 * v[R + i + 1]);
+        if (PERPIX) cb[i] *= mm[i];
+        if (WANT_DISP) db[i] = v[R + i + 1] - v[R + i];
+        Gn[i] = c.g0[i] * cr[i] + c.g1[i] * cg[i] + c.g2[i] * cb[i];
+    }
+    float dl[PX], ds[MIX ? PX : 1];
+    if constexpr (!MIX) {
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+            dl[i] = pi[i] * (Gn[i] - c.Gbar[i]);
+            if (WANT_DISP) gx[i] = fmaf(dl[i], dlu[i], pi[i] * (c.g0[i] * dr[i] + c.g1[i] * dg[i] + c.g2[i] * db[i]));
+        }
+    } else {
+        load_window<WF>(sgrow + bc, v);
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+            float sraw = fmaf(k.wc0, v[R + i], k.wc1 * v[R + i + 1]);
+            if (PERPIX) sraw *= mm[i];
+            const float sg = fminf(fmaxf(sraw, 0.01f), 1.0f);
+            const float inv = fast_rcp(sg);
+            const float w = pi[i] * inv * c.Zinv[i];
+            const float err = (fabsf(cr[i] - c.tr[i]) + fabsf(cg[i] - c.tg[i]) + fabsf(cb[i] - c.tb[i])) * (1.0f / 3.0f);
+            const float lap = 0.5f * fast_exp2(-err * inv * kLog2e) * inv;
+            const float P = (Gn[i] - c.Gbar[i]) * inv * c.Zinv[i] + c.gD[i] * lap;
+            dl[i] = pi[i] * (P - c.gDD[i]);
+            const float dsgt = -(Gn[i] - c.Gbar[i]) * w * inv + c.gD[i] * pi[i] * lap * (err - sg) * inv * inv;
+            ds[i] = (sraw >= 0.01f && sraw <= 1.0f) ? dsgt : 0.0f;  // clamp backward
+            if (WANT_DISP) {
+                const float ce = -c.gD[i] * pi[i] * lap * inv * (1.0f / 3.0f);
+                const float dcr = w * c.g0[i] + ce * sgn(cr[i], c.tr[i]);
+                const float dcg = w * c.g1[i] + ce * sgn(cg[i], c.tg[i]);
+                const float dcb = w * c.g2[i] + ce * sgn(cb[i], c.tb[i]);
+                gx[i] = dcr * dr[i] + dcg * dg[i] + dcb * db[i] + dl[i] * dlu[i] + ds[i] * (v[R + i + 1] - v[R + i]);
+            }
+        }
+    }
+    float gsum = 0.0f;
+    if (PERPIX) {
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+            if (WANT_DISP) gsum = fmaf(gx[i], mm[i], gsum);
+            dl[i] *= mm[i];
+            if constexpr (MIX) ds[i] *= mm[i];
+        }
+    } else if (WANT_DISP) {
+#pragma unroll
+        for (int i = 0; i < PX; ++i) gsum += gx[i];
+        gsum *= k.m;
+    }
+#pragma unroll
+    for (int i = 0; i < PX / 4; ++i) {
+        *reinterpret_cast<float4*>(drow + x0 + 4 * i) = make_float4(dl[4 * i], dl[4 * i + 1], dl[4 * i + 2], dl[4 * i + 3]);
+        if constexpr (MIX) *reinterpret_cast<float4*>(frow + x0 + 4 * i) = make_float4(ds[4 * i], ds[4 * i + 1], ds[4 * i + 2], ds[4 * i + 3]);
+    }
+    return gsum;
+}
+
+template <bool MIX, bool WANT_DISP, int PX, bool PERPIX>
+__device__ __forceinline__ float bwd_plane_any(const float* srow, const float* lrow, const float* sgrow, int pitch, int x0, int W, const PlaneCoef& k,
+                                               const float (&mm)[PX], const BwdCtx<MIX, PX>& c, float* drow, float* frow) {
+    const int at = x0 + k.k0;
+    const int bc = window_base(at, W);
+    switch (at & 3) {
+        case 0: return bwd_plane<MIX, WANT_DISP, PX, 0, PERPIX>(srow, lrow, sgrow, pitch, bc, k, mm, c, drow, frow, x0);
+        case 1: return bwd_plane<MIX, WANT_DISP, PX, 1, PERPIX>(srow, lrow, sgrow, pitch, bc, k, mm, c, drow, frow, x0);
+        case 2: return bwd_plane<MIX, WANT_DISP, PX, 2, PERPIX>(srow, lrow, sgrow, pitch, bc, k, mm, c, drow, frow, x0);
+        default: return bwd_plane<MIX, WANT_DISP, PX, 3, PERPIX>(srow, lrow, sgrow, pitch, bc, k, mm, c, drow, frow, x0);
+    }
+}
+
+// phase B of one plane: gradient of source column j = wc0 * D[j - k0] + wc1 * D[j - k0 - 1]
+template <int PX, int R>
+__device__ __forceinline__ void gather_row(const float* drow, int bc, float w0, float w1, float (&g)[PX]) {
+    constexpr int WF = PX + 4;
+    float v[WF];
+    load_window<WF>(drow + bc, v);
+#pragma unroll
+    for (int i = 0; i < PX; ++i) g[i] = fmaf(w0, v[R + i + 1], w1 * v[R + i]);
+}
+
+template <int PX>
+__device__ __forceinline__ void gather_any(const float* drow, int x0, int W, int k0, float w0, float w1, float (&g)[PX]) {
+    const int at = x0 - k0 - 1;
+    const int bc = window_base(at, W);
+    switch (at & 3) {
+        case 0: gather_row<PX, 0>(drow, bc, w0, w1, g); break;
+        case 1: gather_row<PX, 1>(drow, bc, w0, w1, g); break;
+        case 2: gather_row<PX, 2>(drow, bc, w0, w1, g); break;
+        default: gather_row<PX, 3>(drow, bc, w0, w1, g); break;
+    }
+}
+
+template <bool MIX, int MASKMODE, bool WANT_DISP, int PX, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParams p, const StreamCfg cfg) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr bool DENSE = (MASKMODE == SMASK_DENSE);
+    constexpr int NE = MIX ? 2 : 1;
+    const int W = p.d.W, H = p.d.H, N = p.d.N, pitch = cfg.pitch, rpc = cfg.rpc, hs = cfg.hs, NB = cfg.nblk;
+    const int rows_total = p.d.B * H;
+    const Smem s = carve(smem_raw, cfg, N, MIX, DENSE, NE, WANT_DISP);
+    zero_pads(s, cfg, W);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(s.bars + i, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int nit = (cfg.ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const Producer prod{p, cfg, s, rows_total, MIX, DENSE};
+    if (threadIdx.x == 0 && nit > 0) {
+        prod.src_rows(0, blockIdx.x);
+        prod.block(0, blockIdx.x, 0);
+        if (NB > 1) prod.block(1, blockIdx.x, 1);
+        else if (nit > 1) prod.block(1, blockIdx.x + gridDim.x, 0);
+    }
+    const int r = threadIdx.x / cfg.tpr;
+    const int x0 = (threadIdx.x - r * cfg.tpr) * PX;
+    const int lane = threadIdx.x & 31;
+    const size_t rowf = (size_t)rpc * pitch;
+
+    for (int it = 0; it < nit; ++it) {
+        const int g = blockIdx.x + it * gridDim.x;
+        const int row = g * rpc + r;
+        const bool active = (r < rpc) && (row < rows_total);
+        const int b = active ? row / H : 0, y = active ? row - b * H : 0;
+        const int64_t rem = (int64_t)y * W + x0;
+        stage_coef<MASKMODE>(p, cfg, s.coef + (size_t)(it & 1) * rpc * N, g, rows_total);
+        if (WANT_DISP)
+            for (int i = threadIdx.x; i < rpc * N; i += blockDim.x) s.gacc[i] = 0.0f;
+
+        BwdCtx<MIX, PX> c;
+        if (active) {
+            const float* gp = p.gout.g_rgb_rec + (int64_t)b * p.chw3 + rem;
+            const float* rp = p.out.rgb_rec + (int64_t)b * p.chw3 + rem;
+            float ra[PX], rb[PX], rc[PX], Sv[PX];
+            load_px_global<PX>(gp, c.g0);
+            load_px_global<PX>(gp + p.hw, c.g1);
+            load_px_global<PX>(gp + 2 * p.hw, c.g2);
+            load_px_global<PX>(rp, ra);
+            load_px_global<PX>(rp + p.hw, rb);
+            load_px_global<PX>(rp + 2 * p.hw, rc);
+            const float* st = p.out.stats + (int64_t)b * (MIX ? PD_STATS_MIXTURE : PD_STATS_PLAIN) * p.hw + rem;
+            load_px_global<PX>(st, c.Ml2);
+            load_px_global<PX>(st + p.hw, Sv);
+#pragma unroll
+            for (int i = 0; i < PX; ++i) {
+                c.Gbar[i] = c.g0[i] * ra[i] + c.g1[i] * rb[i] + c.g2[i] * rc[i];
+                c.invS[i] = 1.0f / Sv[i];
+            }
+            if constexpr (MIX) {
+                const float* tp = p.in.tgt + (int64_t)b * p.chw3 + rem;
+                float Av[PX], Dv[PX], gv[PX];
+                load_px_global<PX>(tp, c.tr);
+                load_px_global<PX>(tp + p.hw, c.tg);
+                load_px_global<PX>(tp + 2 * p.hw, c.tb);
+                load_px_global<PX>(st + 2 * p.hw, Av);
+                load_px_global<PX>(st + 3 * p.hw, Dv);
+                if (p.gout.g_nll) load_px_global<PX>(p.gout.g_nll + (int64_t)b * p.hw + rem, gv);
+                else
+#pragma unroll
+                    for (int i = 0; i < PX; ++i) gv[i] = 0.0f;
+#pragma unroll
+                for (int i = 0; i < PX; ++i) {
+                    c.Zinv[i] = Sv[i] / Av[i];              // 1/Z, Z = sum pi/sigma = A/S
+                    c.gD[i] = -gv[i] / Dv[i];               // d loss / d D, nll = -log D
+                    c.gDD[i] = c.gD[i] * (Dv[i] - 1e-7f);   // = sum_k pi_k P_k
+                }
+            }
+        }
+        const PlaneCoef* coef = s.coef + ((size_t)(it & 1) * rpc + r) * N;
+        const float* srow = s.src + ((size_t)((it & 1) * rpc + r) * 3) * pitch + PAD;
+        if (it > 0) {
+            // the previous group's last gather (phase B) still reads its coefficients and exchange rows after that
+            // group's final barrier; this group's gacc zeroing / coefficient staging touches other buffers, so no
+            // extra barrier is needed here: the first barrier below orders them before any use.
+        }
+
+        for (int j = 0; j < NB; ++j) {
+            const int jb = it * NB + j;
+            const int n0 = j * hs, n1 = min(N, n0 + hs);
+            float* dblk = s.dbuf + (size_t)(jb & 1) * hs * NE * rowf;
+            if (j == 0) __syncthreads();  // coefficients / gacc of this group visible to everyone
+            if (active) {
+                if (j == 0) mbar_wait(s.bars + 2 + (it & 1), (it >> 1) & 1);
+                mbar_wait(s.bars + (jb & 1), (jb >> 1) & 1);
+            }
+            // ---------------- phase A ----------------
+            for (int n = n0; n < n1; ++n) {
+                float gsum = 0.0f;
+                if (active) {
+                    const PlaneCoef k = load_coef(coef + n);
+                    const size_t slot = ((size_t)((jb & 1) * hs + (n - n0)) * rpc + r) * pitch + PAD;
+                    float* drow = dblk + ((size_t)(n - n0) * NE * rpc + r) * pitch + PAD;
+                    float* frow = drow + rowf;
+                    float mm[PX] = {};
+                    bool perpix = false;
+                    if (DENSE) {
+                        load_window<PX>(s.mring + slot + x0, mm);
+                        perpix = !all_ones<PX>(mm);
+                    }
+                    if (DENSE && perpix) gsum = bwd_plane_any<MIX, WANT_DISP, PX, true>(srow, s.lring + slot, s.sring + slot, pitch, x0, W, k, mm, c, drow, frow);
+                    else gsum = bwd_plane_any<MIX, WANT_DISP, PX, false>(srow, s.lring + slot, s.sring + slot, pitch, x0, W, k, mm, c, drow, frow);
+                }
+                if (WANT_DISP) {
+                    // rows of a group may share a warp: reduce per row with shared-memory atomics after a warp sum
+                    // only when the whole warp belongs to one row
+                    const int r_first = (int)((threadIdx.x & ~31u) / cfg.tpr), r_last = (int)((threadIdx.x | 31u) / cfg.tpr);
+                    if (r_first == r_last) {
+                        const float sum = warp_sum(gsum);
+                        if (lane == 0 && r < rpc && sum != 0.0f) atomicAdd(s.gacc + r * N + n, sum * p.d.disp_sign);
+                    } else if (active && gsum != 0.0f) {
+                        atomicAdd(s.gacc + r * N + n, gsum * p.d.disp_sign);
+                    }
+                }
+            }
+            __syncthreads();  // exchange rows of block jb complete; ring half jb&1 free again
+            if (threadIdx.x == 0) {
+                // block jb+1 is already in flight; refill this half with block jb+2
+                const int j2 = j + 2;
+                if (j2 < NB) prod.block(jb + 2, g, j2);
+                else if (it + 1 < nit) {
+                    const int jn = j2 - NB;  // 0 or 1
+                    if (jn < NB) prod.block(jb + 2, g + gridDim.x, jn);
+                    else if (it + 2 < nit) prod.block(jb + 2, g + 2 * gridDim.x, 0);  // NB == 1
+                }
+                if (j == 0 && it + 1 < nit) prod.src_rows(it + 1, g + gridDim.x);
+            }
+            // ---------------- phase B ----------------
+            if (active) {
+                for (int n = n0; n < n1; ++n) {
+                    const PlaneCoef k = load_coef(coef + n);
+                    const float* drow = dblk + ((size_t)(n - n0) * NE * rpc + r) * pitch + PAD;
+                    const int64_t o = (((int64_t)b * N + n) * H + y) * W + x0;
+                    // with a dense mask the per-pixel mask is already folded into the exchange rows (k.m == 1)
+                    float gg[PX];
+                    if (p.gin.g_logits) {
+                        gather_any<PX>(drow, x0, W, k.k0, k.wc0, k.wc1, gg);
+                        store_px_stream<PX>(p.gin.g_logits + o, gg);
+                    }
+                    if constexpr (MIX) if (p.gin.g_sigma) {
+                        gather_any<PX>(drow + rowf, x0, W, k.k0, k.wc0, k.wc1, gg);
+                        store_px_stream<PX>(p.gin.g_sigma + o, gg);
+                    }
+                }
+            }
+        }
+        if (WANT_DISP) {
+            __syncthreads();  // every atomic of this group has landed
+            for (int i = threadIdx.x; i < rpc * N; i += blockDim.x) {
+                const int rr = i / N, n = i - rr * N;
+                const int rw = g * rpc + rr;
+                const float v = s.gacc[i];
+                if (rw < rows_total && v != 0.0f) {
+                    const int bb = rw / H, yy = rw - bb * H;
+                    atomicAdd(p.gin.g_disp + soff(p.gin.g_disp_stride, bb, n, yy, 0), v);
+                }
+            }
+            __syncthreads();  // before the next group zeroes gacc
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+inline bool ts_aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
+
+inline int stream_mask_mode(const WarpParams& p) {
+    return (p.d.mask_dtype == PD_MASK_NONE || p.d.mask_stride.x == 0) ? SMASK_ROW : SMASK_DENSE;
+}
+
+inline bool stream_path_supported(const WarpParams& p) {
+    if (p.d.warp_type != PD_WARP_DISP) return false;
+    const int W = p.d.W;
+    if (W % 4 != 0 || W < 8 || W > 2048) return false;
+    if (p.d.disp_stride.x != 0) return false;  // disparity must be constant along x
+    if (p.d.mask_dtype != PD_MASK_NONE && p.d.mask_stride.x != 0) {
+        // dense mask rows travel through TMA: fp32, unit x stride, 16-byte aligned rows
+        if (p.d.mask_dtype != PD_MASK_F32 || p.d.mask_stride.x != 1) return false;
+        if (p.d.mask_stride.y % 4 || p.d.mask_stride.n % 4 || p.d.mask_stride.b % 4 || !ts_aligned16(p.in.mask)) return false;
+    }
+    if (p.gin.g_disp && p.gin.g_disp_stride.x != 0) return false;  // d/d disp only reduced over x
+    const void* ptrs[] = {p.in.src, p.in.tgt, p.in.logits, p.in.sigma, p.out.rgb_rec, p.out.stats, p.out.nll, p.out.nll_auto,
+                          p.gout.g_rgb_rec, p.gout.g_nll, p.gin.g_logits, p.gin.g_sigma};
+    for (const void* q : ptrs)
+        if (q && !ts_aligned16(q)) return false;
+    return true;
+}
+
+inline int stream_env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+template <int PX, int THREADS>
+inline StreamCfg stream_cfg(const WarpParams& p, bool mix, bool dense, int ne_bwd, bool want_disp) {
+    StreamCfg c;
+    c.tpr = p.d.W / PX;
+    c.rpc = THREADS / c.tpr;
+    if (c.rpc < 1) c.rpc = 1;
+    if (c.rpc > 8) c.rpc = 8;
+    c.pitch = p.d.W + 2 * PAD;
+    c.hs = stream_env_int("PD_STREAM_HS", 4);
+    if (c.hs > p.d.N) c.hs = p.d.N;
+    // shrink the pipeline depth until the CTA fits the shared-memory budget (default: three CTAs per SM)
+    const size_t budget = (size_t)stream_env_int("PD_STREAM_SMEM_KB", 72) * 1024;
+    while (c.hs > 1 && stream_smem_bytes(c, p.d.N, mix, dense, ne_bwd, want_disp) > budget) --c.hs;
+    c.nblk = (p.d.N + c.hs - 1) / c.hs;
+    c.ngroups = (p.d.B * p.d.H + c.rpc - 1) / c.rpc;
+    return c;
+}
+
+template <typename K>
+inline void stream_smem_optin(K kern, size_t smem) {
+    static std::mutex mu;
+    static std::map<const void*, size_t> granted;
+    if (smem <= 48 * 1024) return;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& g = granted[(const void*)kern];
+    if (smem > g) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        g = smem;
+    }
+}
+
+inline int stream_grid(int ngroups, int threads, size_t smem, const void* kernel) {
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+    if (per_sm < 1) per_sm = 1;
+    const int cap = stream_env_int("PD_STREAM_CTAS", 0);
+    if (cap > 0 && per_sm > cap) per_sm = cap;
+    long long g = (long long)sms * per_sm;
+    return (int)(g < ngroups ? g : ngroups);
+}
+
+// THREADS is the CTA size the row groups are packed into; the launch uses rpc * tpr rounded up to a warp
+template <bool MIX, int MASKMODE, int PX, int THREADS, int MINB>
+inline bool launch_fwd_stream_t(const WarpParams& p, cudaStream_t st) {
+    const StreamCfg c = stream_cfg<PX, THREADS>(p, MIX, MASKMODE == SMASK_DENSE, 0, false);
+    const int threads = ((c.rpc * c.tpr + 31) / 32) * 32;
+    if (threads > THREADS) return false;
+    const size_t smem = stream_smem_bytes(c, p.d.N, MIX, MASKMODE == SMASK_DENSE, 0, false);
+    if (smem > 220 * 1024) return false;
+    auto kern = rows_fwd_stream<MIX, MASKMODE, PX, THREADS, MINB>;
+    stream_smem_optin(kern, smem);
+    kern<<<stream_grid(c.ngroups, threads, smem, (const void*)kern), threads, smem, st>>>(p, c);
+    return true;
+}
+
+template <bool MIX, int MASKMODE, bool WANT_DISP, int PX, int THREADS, int MINB>
+inline bool launch_bwd_stream_t(const WarpParams& p, cudaStream_t st) {
+    const StreamCfg c = stream_cfg<PX, THREADS>(p, MIX, MASKMODE == SMASK_DENSE, MIX ? 2 : 1, WANT_DISP);
+    const int threads = ((c.rpc * c.tpr + 31) / 32) * 32;
+    if (threads > THREADS) return false;
+    const size_t smem = stream_smem_bytes(c, p.d.N, MIX, MASKMODE == SMASK_DENSE, MIX ? 2 : 1, WANT_DISP);
+    if (smem > 220 * 1024) return false;
+    auto kern = rows_bwd_stream<MIX, MASKMODE, WANT_DISP, PX, THREADS, MINB>;
+    stream_smem_optin(kern, smem);
+    kern<<<stream_grid(c.ngroups, threads, smem, (const void*)kern), threads, smem, st>>>(p, c);
+    return true;
+}
+
+template <bool MIX, int MASKMODE>
+inline bool launch_fwd_stream_m(const WarpParams& p, cudaStream_t st) {
+    const int W = p.d.W;
+    if (W % 8 == 0 && W / 8 <= 160 && stream_env_int("PD_STREAM_PX8", 0)) return launch_fwd_stream_t<MIX, MASKMODE, 8, 160, MIX ? 2 : 3>(p, st);
+    if (W / 4 <= 160) return launch_fwd_stream_t<MIX, MASKMODE, 4, 160, MIX ? 3 : 4>(p, st);
+    if (W / 4 <= 320) return launch_fwd_stream_t<MIX, MASKMODE, 4, 320, MIX ? 1 : 2>(p, st);
+    return false;
+}
+
+inline bool launch_fwd_stream(const WarpParams& p, cudaStream_t st) {
+    const int mm = stream_mask_mode(p);
+    if (p.d.mixture) return mm == SMASK_ROW ? launch_fwd_stream_m<true, SMASK_ROW>(p, st) : launch_fwd_stream_m<true, SMASK_DENSE>(p, st);
+    return mm == SMASK_ROW ? launch_fwd_stream_m<false, SMASK_ROW>(p, st) : launch_fwd_stream_m<false, SMASK_DENSE>(p, st);
+}
+
+template <bool MIX, int MASKMODE, bool WANT_DISP>
+inline bool launch_bwd_stream_w(const WarpParams& p, cudaStream_t st) {
+    const int W = p.d.W;
+    if (W % 8 == 0 && W / 8 <= 160 && stream_env_int("PD_STREAM_PX8", 0)) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 8, 160, 2>(p, st);
+    if (W / 4 <= 160) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 4, 160, MIX ? 2 : 3>(p, st);
+    if (W / 4 <= 320) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 4, 320, 1>(p, st);
+    return false;
+}
+
+// true when launch_bwd_stream() will find a configuration (so that the caller may skip the zero-fill the
+// scatter kernels need)
+inline bool stream_bwd_fits(const WarpParams& p) {
+    const int W = p.d.W;
+    return (W % 8 == 0 && W / 8 <= 160) || W / 4 <= 320;
+}
+
+template <bool MIX, int MASKMODE>
+inline bool launch_bwd_stream_m(const WarpParams& p, cudaStream_t st) {
+    return p.gin.g_disp ? launch_bwd_stream_w<MIX, MASKMODE, true>(p, st) : launch_bwd_stream_w<MIX, MASKMODE, false>(p, st);
+}
+
+inline bool launch_bwd_stream(const WarpParams& p, cudaStream_t st) {
+    const int mm = stream_mask_mode(p);
+    if (p.d.mixture) return mm == SMASK_ROW ? launch_bwd_stream_m<true, SMASK_ROW>(p, st) : launch_bwd_stream_m<true, SMASK_DENSE>(p, st);
+    return mm == SMASK_ROW ? launch_bwd_stream_m<false, SMASK_ROW>(p, st) : launch_bwd_stream_m<false, SMASK_DENSE>(p, st);
+}
+
+}  // namespace ts
+}  // namespace pd

@@ -75,6 +75,7 @@ class WarpConfig:
     disp_sign: float = 0.0
     shape: Tuple[int, int, int, int] = (0, 0, 0, 0)  # B,N,H,W
     layered: bool = False  # also materialise the per-plane tensors of trainer.py:582-602 (detached)
+    exact_coords: bool = False  # PD_FLAG_EXACT_COORDS: bit-faithful coordinate round trip (slower stereo path)
 
 
 class _WarpComposite(torch.autograd.Function):
@@ -86,7 +87,7 @@ class _WarpComposite(torch.autograd.Function):
         B, N, H, W = cfg.shape
         dev = logits.device
         desc = L.WarpDesc(B=B, N=N, H=H, W=W, warp_type=cfg.warp_type, mixture=int(cfg.mixture), automask=int(cfg.automask),
-                          mask_dtype=L.PD_MASK_NONE, disp_sign=float(cfg.disp_sign), reserved0=0)
+                          mask_dtype=L.PD_MASK_NONE, disp_sign=float(cfg.disp_sign), flags=(L.PD_FLAG_EXACT_COORDS if cfg.exact_coords else 0))
         if disp is not None:
             desc.disp_stride = _strides4(disp)
         if mask is not None:

@@ -36,22 +36,29 @@ def check(got, want, atol, what, allow_frac=0.0):
     assert fb <= allow_frac, "%s: %.3g of elements off by more than %.1e (max err %.3e)" % (what, fb, atol, mx)
 
 
-def run_cuda(c, photometric=None, layered=True):
+MODES = ["layered", "fused", "fused_exact"]
+# layered:     materialises the per-plane tensors -> general (reference-arithmetic) kernels
+# fused:       product configuration: TMA-streamed row kernels wherever they apply, exact sample positions
+# fused_exact: PD_FLAG_EXACT_COORDS -> row-tiled kernels that reproduce the fp32 coordinate round trip bit for bit
+
+
+def run_cuda(c, photometric=None, mode="layered"):
     from planedepth_b200.boundary import HotPath
 
-    hp = HotPath(c.opt, c.target_sides, pc_net=pyramid_features, photometric=photometric, materialize_layered=layered)
+    layered = mode == "layered"
+    hp = HotPath(c.opt, c.target_sides, pc_net=pyramid_features, photometric=photometric, materialize_layered=layered,
+                 exact_coords=(mode == "fused_exact"))
     losses = hp.process(c.inputs, c.outputs)
     losses["loss/total_loss"].backward()
     return losses
 
 
-@pytest.mark.parametrize("layered", [True, False], ids=["layered", "fused"])
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name", CASES)
-def test_cuda_matches_reference_golden(name, layered):
-    # layered=True materialises the per-plane tensors (general kernels); layered=False is the product
-    # configuration (row-tiled fast path wherever it applies, nothing per-plane materialised)
+def test_cuda_matches_reference_golden(name, mode):
+    layered = mode == "layered"
     c = load_case(name, device="cuda")
-    losses = run_cuda(c, layered=layered)
+    losses = run_cuda(c, mode=mode)
     for k, want in c.expect.items():
         if k.startswith("out_"):
             nm, s = k[4:].split("@")
@@ -70,7 +77,7 @@ def test_cuda_matches_reference_golden(name, layered):
             check(g, want, grad_tol(k[5:]) * scale, k, allow_frac=2e-3)
 
 
-def synth_case(B, N, H, W, warp, mixture, automask, frames, mask_novel, seed, dense=False, n_xz=0, u8mask=False):
+def synth_case(B, N, H, W, warp, mixture, automask, frames, mask_novel, seed, dense=False, n_xz=0, u8mask=False, compact=False):
     """Fresh seeded inputs in the reference's dict layout (CPU tensors)."""
     from types import SimpleNamespace
 
@@ -110,6 +117,8 @@ def synth_case(B, N, H, W, warp, mixture, automask, frames, mask_novel, seed, de
         disp_layered = disp_layered + bump
     if u8mask:
         padding_mask = (rnd(B, N, H, W) > 0.1)
+    if compact:  # row-constant mask stored with a zero x stride (what a fused decoder tail would hand over)
+        padding_mask = padding_mask[..., :1].contiguous().expand(-1, -1, -1, W)
     logits = (1.5 * torch.randn(B, N, H, W, generator=g)).requires_grad_(True)
     leaves["logits"] = logits
     outputs = {"logits": logits, "disp_layered": disp_layered, "padding_mask": padding_mask, "distance": distance, "norm": norm,
@@ -142,6 +151,12 @@ CONFIGS = [
     (1, 6, 32, 64, "homography_warp", True, True, [1], True, dict(n_xz=2)),
     (1, 5, 32, 64, "depth_warp", False, False, [], False, {}),
     (1, 5, 24, 40, "depth_warp", True, True, [], True, dict(dense=True)),
+    (2, 6, 16, 44, "disp_warp", True, True, [], True, dict(n_xz=2)),             # W % 8 != 0: 4-pixel threads
+    (1, 49, 6, 640, "disp_warp", False, False, [], False, {}),                   # BASELINE width / plane count, few rows
+    (1, 13, 4, 1280, "disp_warp", True, True, [], False, dict(n_xz=3)),          # HR width, mixture
+    (3, 11, 10, 200, "disp_warp", False, True, [], True, dict(n_xz=3)),          # rows of several images share a CTA
+    (2, 9, 12, 72, "disp_warp", True, True, [], False, dict(n_xz=3, compact=True)),  # zero-stride row mask
+    (2, 9, 12, 72, "disp_warp", False, False, [], False, dict(n_xz=3, compact=True)),
 ]
 
 
@@ -176,6 +191,8 @@ def build_on(device, cfg, seed):
     if mix:
         out["sigma"] = mapping["sigma"]
     out["disp_layered"], out["distance"] = disp_layered, distance
+    if kw.get("compact"):
+        out["padding_mask"] = out["padding_mask"][..., :1].contiguous().expand(-1, -1, -1, W)
     inp = {k: (v.detach().cuda() if torch.is_tensor(v) else v) for k, v in cg.inputs.items()}
     for f in frames:
         inp[("Rt", f)] = mapping["T%d" % f]
@@ -184,18 +201,19 @@ def build_on(device, cfg, seed):
     return cg
 
 
-@pytest.mark.parametrize("layered", [True, False], ids=["layered", "fused"])
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("idx", range(len(CONFIGS)))
 @pytest.mark.parametrize("photometric", [None, "ssim_l1"])
-def test_cuda_matches_oracle(idx, photometric, layered):
+def test_cuda_matches_oracle(idx, photometric, mode):
     cfg = CONFIGS[idx]
+    layered = mode == "layered"
     if photometric == "ssim_l1" and cfg[5] and idx % 2:
         pytest.skip("ssim_l1 on top of mixture covered by the even cases")
     cc = build_on("cpu", cfg, seed=100 + idx)
     cg = build_on("cuda", cfg, seed=100 + idx)
     lo = O.hot_path(cc.opt, cc.target_sides, cc.inputs, cc.outputs, pyramid_features, loss_mode=photometric)
     lo["loss/total_loss"].backward()
-    lg = run_cuda(cg, photometric, layered)
+    lg = run_cuda(cg, photometric, mode)
     for s in cc.target_sides:
         for nm in ("rgb_rec", "rgb_rec_layered", "logit_rec", "probability_rec", "sigma_rec", "pi_rec"):
             if (nm, s) in cc.outputs and (layered or nm == "rgb_rec"):
@@ -255,7 +273,13 @@ def test_properties_at_full_size():
     hp2 = HotPath(opt, ["r"], pc_net=None, materialize_layered=False)
     out5 = {k: v for k, v in out3.items() if not isinstance(k, tuple)}
     hp2.pred_novel_images(inputs, out5)
-    assert (out5[("rgb_rec", "r")] - out3[("rgb_rec", "r")]).abs().max().item() < 1e-5
+    # (general kernels reproduce the reference's fp32 coordinate round trip, the streamed kernels sample at the exact
+    # positions: up to 6e-5 px apart at this width, times the slope of iid-random logits)
+    assert (out5[("rgb_rec", "r")] - out3[("rgb_rec", "r")]).abs().max().item() < 1e-4
+    hp3 = HotPath(opt, ["r"], pc_net=None, materialize_layered=False, exact_coords=True)
+    out6 = {k: v for k, v in out3.items() if not isinstance(k, tuple)}
+    hp3.pred_novel_images(inputs, out6)
+    assert (out6[("rgb_rec", "r")] - out3[("rgb_rec", "r")]).abs().max().item() < 1e-5
     comp = (out3[("rgb_rec_layered", "r")] * out3[("probability_rec", "r")][:, :, None]).sum(1)
     assert (comp - out3[("rgb_rec", "r")]).abs().max().item() < 1e-5
 
