@@ -2,9 +2,10 @@
 // along x (vertical planes: one scalar per (image, plane); xz ground planes: one scalar per row —
 // depth_decoder.py:153-156, 163-181).  Same job as pd_warp_rows.cuh, re-organised around the B200
 // memory system:
-//   * every logit / sigma / mask row is brought into shared memory by the TMA engine
-//     (cp.async.bulk, 1-D) into a two-block ring, completion signalled on mbarriers; compute threads
-//     issue no global loads in the plane loop and the prefetch distance is 1-2 blocks of planes;
+//   * warp-specialised CTAs: one producer warp brings every logit / sigma / mask row into a multi-stage
+//     shared-memory ring with the TMA engine (cp.async.bulk, 1-D), full / empty mbarriers per stage;
+//     consumer warps issue no global loads in the plane loop and never meet a CTA-wide barrier in the
+//     forward pass, so they drift apart by up to the ring depth;
 //   * the source rgb rows are TMA-staged the same way, double-buffered across row groups;
 //   * a plane's warp is "shift by k0 = floor(d) and lerp with frac(d)": the per-(row, plane)
 //     coefficients (k0, the two weights, pre-multiplied by the row mask and by log2(e) for the logit)
@@ -13,7 +14,7 @@
 //     lazily moved reference (one ex2 per sample);
 //   * the backward is a gather: per-target dL/dlogit (dL/dsigma) rows are exchanged through a
 //     double-buffered shared-memory block and each gradient row is written once with 128-bit streaming
-//     stores (no atomics, no zero-fill); one __syncthreads per block of planes in both directions.
+//     stores (no atomics, no zero-fill); one consumer-only named barrier per block of planes.
 //
 // Coordinates: u = x + sign*d and v = y are used exactly.  The reference evaluates the same numbers
 // through an fp32 normalise / un-normalise round trip (trainer.py:549-551 + ATen
@@ -46,10 +47,15 @@ struct StreamCfg {
     int rpc;      // rows per CTA iteration ("row group")
     int tpr;      // threads per row = W / PX
     int pitch;    // floats per shared row = W + 2 * PAD
-    int hs;       // planes per pipeline block
+    int hs;       // planes per pipeline block (= ring stage)
+    int nst;      // ring stages
     int nblk;     // blocks per row group = ceil(N / hs)
     int ngroups;  // ceil(B * H / rpc)
+    int nc;       // consumer threads (multiple of 32); the CTA has nc + 32 threads, the last warp produces
 };
+
+constexpr int MAX_STAGES = 8;
+constexpr int BAR_FULL = 0, BAR_EMPTY = MAX_STAGES, BAR_SRC = 2 * MAX_STAGES, BAR_BYTES = 256;
 
 enum { SMASK_ROW = 0, SMASK_DENSE = 1 };
 
@@ -65,6 +71,11 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// consumer-only CTA barrier (hardware barrier 1); the producer warp never joins it
+__device__ __forceinline__ void consumer_sync(int nc) { asm volatile("bar.sync 1, %0;" ::"r"(nc) : "memory"); }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -129,12 +140,12 @@ __device__ __forceinline__ void store_px_stream(float* q, const float (&v)[PX]) 
 // shared-memory carve-up, common to both kernels
 // ------------------------------------------------------------------------------------------------
 struct Smem {
-    uint64_t* bars;   // [0,1] ring halves, [2,3] source-row buffers
+    uint64_t* bars;   // BAR_FULL + stage, BAR_EMPTY + stage, BAR_SRC + {0,1}
     PlaneCoef* coef;  // [2][rpc][N]
     float* src;       // [2][rpc][3][pitch]
-    float* lring;     // [2*hs][rpc][pitch]
-    float* sring;     // mixture: [2*hs][rpc][pitch]
-    float* mring;     // dense mask: [2*hs][rpc][pitch]
+    float* lring;     // [nst*hs][rpc][pitch]
+    float* sring;     // mixture: [nst*hs][rpc][pitch]
+    float* mring;     // dense mask: [nst*hs][rpc][pitch]
     float* dbuf;      // backward: [2][hs][NE][rpc][pitch] exchange rows (NE = 1, mixture 2)
     float* gacc;      // backward with d/d disp: [rpc][N]
     float* fend;      // one past the last float
@@ -142,28 +153,28 @@ struct Smem {
 
 __host__ __device__ inline size_t stream_smem_floats(const StreamCfg& c, int N, bool mix, bool dense, int ne_bwd, bool want_disp) {
     size_t rowf = (size_t)c.rpc * c.pitch;
-    size_t f = 2 * 3 * rowf + (size_t)2 * c.hs * rowf * (1 + (mix ? 1 : 0) + (dense ? 1 : 0));
+    size_t f = 2 * 3 * rowf + (size_t)c.nst * c.hs * rowf * (1 + (mix ? 1 : 0) + (dense ? 1 : 0));
     f += (size_t)2 * c.hs * ne_bwd * rowf;
     if (want_disp) f += (size_t)c.rpc * N;
     return f;
 }
 
 __host__ __device__ inline size_t stream_smem_bytes(const StreamCfg& c, int N, bool mix, bool dense, int ne_bwd, bool want_disp) {
-    return 64 + (size_t)2 * c.rpc * N * sizeof(PlaneCoef) + stream_smem_floats(c, N, mix, dense, ne_bwd, want_disp) * sizeof(float) + 16;
+    return BAR_BYTES + (size_t)2 * c.rpc * N * sizeof(PlaneCoef) + stream_smem_floats(c, N, mix, dense, ne_bwd, want_disp) * sizeof(float) + 16;
 }
 
 __device__ __forceinline__ Smem carve(unsigned char* raw, const StreamCfg& c, int N, bool mix, bool dense, int ne_bwd, bool want_disp) {
     Smem s;
     const size_t rowf = (size_t)c.rpc * c.pitch;
     s.bars = reinterpret_cast<uint64_t*>(raw);
-    s.coef = reinterpret_cast<PlaneCoef*>(raw + 64);
+    s.coef = reinterpret_cast<PlaneCoef*>(raw + BAR_BYTES);
     s.src = reinterpret_cast<float*>(s.coef + (size_t)2 * c.rpc * N);
     s.lring = s.src + 2 * 3 * rowf;
-    float* q = s.lring + (size_t)2 * c.hs * rowf;
+    float* q = s.lring + (size_t)c.nst * c.hs * rowf;
     s.sring = q;
-    if (mix) q += (size_t)2 * c.hs * rowf;
+    if (mix) q += (size_t)c.nst * c.hs * rowf;
     s.mring = q;
-    if (dense) q += (size_t)2 * c.hs * rowf;
+    if (dense) q += (size_t)c.nst * c.hs * rowf;
     s.dbuf = q;
     q += (size_t)2 * c.hs * ne_bwd * rowf;
     s.gacc = q;
@@ -182,54 +193,11 @@ __device__ __forceinline__ void zero_pads(const Smem& s, const StreamCfg& c, int
     }
 }
 
-// Producer side (one thread): TMA requests for the source rows of a row group / for one block of planes.
-struct Producer {
-    const WarpParams& p;
-    const StreamCfg& c;
-    const Smem& s;
-    int rows_total;
-    bool mix, dense;
-
-    __device__ __forceinline__ void src_rows(int it, int g) const {
-        const int W = p.d.W, H = p.d.H;
-        uint64_t* bar = s.bars + 2 + (it & 1);
-        int nrows = min(c.rpc, rows_total - g * c.rpc);
-        mbar_expect_tx(bar, (uint32_t)(nrows * 3 * W * sizeof(float)));
-        for (int r = 0; r < nrows; ++r) {
-            const int row = g * c.rpc + r, b = row / H, y = row - b * H;
-            for (int ch = 0; ch < 3; ++ch)
-                tma_row(s.src + ((size_t)((it & 1) * c.rpc + r) * 3 + ch) * c.pitch + PAD, p.in.src + (((int64_t)b * 3 + ch) * H + y) * W,
-                        (uint32_t)(W * sizeof(float)), bar);
-        }
-    }
-
-    __device__ __forceinline__ void block(int jb, int g, int j) const {
-        const int W = p.d.W, H = p.d.H, N = p.d.N;
-        const int half = jb & 1;
-        uint64_t* bar = s.bars + half;
-        const int nrows = min(c.rpc, rows_total - g * c.rpc);
-        const int n0 = j * c.hs, n1 = min(N, n0 + c.hs);
-        const int streams = 1 + (mix ? 1 : 0) + (dense ? 1 : 0);
-        mbar_expect_tx(bar, (uint32_t)((n1 - n0) * nrows * streams * W * sizeof(float)));
-        for (int n = n0; n < n1; ++n) {
-            for (int r = 0; r < nrows; ++r) {
-                const int row = g * c.rpc + r, b = row / H, y = row - b * H;
-                const size_t slot = ((size_t)(half * c.hs + (n - n0)) * c.rpc + r) * c.pitch + PAD;
-                const int64_t off = (((int64_t)b * N + n) * H + y) * W;
-                tma_row(s.lring + slot, p.in.logits + off, (uint32_t)(W * sizeof(float)), bar);
-                if (mix) tma_row(s.sring + slot, p.in.sigma + off, (uint32_t)(W * sizeof(float)), bar);
-                if (dense)
-                    tma_row(s.mring + slot, reinterpret_cast<const float*>(p.in.mask) + soff(p.d.mask_stride, b, n, y, 0), (uint32_t)(W * sizeof(float)), bar);
-            }
-        }
-    }
-};
-
-// per-(row, plane) coefficients of row group g into coef buffer `buf`
+// per-(row, plane) coefficients of row group g (executed by the 32 lanes of the producer warp)
 template <int MASKMODE>
 __device__ __forceinline__ void stage_coef(const WarpParams& p, const StreamCfg& c, PlaneCoef* coef, int g, int rows_total) {
     const int N = p.d.N, H = p.d.H, W = p.d.W;
-    for (int idx = threadIdx.x; idx < c.rpc * N; idx += blockDim.x) {
+    for (int idx = threadIdx.x & 31; idx < c.rpc * N; idx += 32) {
         const int r = idx / N, n = idx - r * N;
         const int row = g * c.rpc + r;
         PlaneCoef k;
@@ -250,6 +218,61 @@ __device__ __forceinline__ void stage_coef(const WarpParams& p, const StreamCfg&
             k.wl1 = k.wc1 * kLog2e;
         }
         coef[idx] = k;
+    }
+}
+
+// Producer warp: walks the CTA's (row group, block) sequence; per block it waits for the ring stage to be
+// released by every consumer warp, (at a group start) stages the group's coefficients and source rows, then
+// arms the stage's full barrier with the byte count and issues one bulk copy per (plane, row, stream).
+// Releases that make reuse safe: the stage's empty barrier is armed by the consumers after their last read
+// of block jb - nst; with nst <= nblk that also covers the coefficient / source-row buffers of group it - 2.
+template <bool MIX, int MASKMODE>
+__device__ __forceinline__ void producer_loop(const WarpParams& p, const StreamCfg& c, const Smem& s, int nit) {
+    constexpr bool DENSE = (MASKMODE == SMASK_DENSE);
+    const int lane = threadIdx.x & 31;
+    const int W = p.d.W, H = p.d.H, N = p.d.N, rows_total = p.d.B * H;
+    const uint32_t rowbytes = (uint32_t)(W * sizeof(float));
+    const int streams = 1 + (MIX ? 1 : 0) + (DENSE ? 1 : 0);
+    int stage = 0, use = 0;  // use = how many times the ring wrapped
+    for (int it = 0; it < nit; ++it) {
+        const int g = blockIdx.x + it * gridDim.x;
+        const int row0 = g * c.rpc;
+        const int nrows = min(c.rpc, rows_total - row0);
+        for (int j = 0; j < c.nblk; ++j) {
+            if (use > 0) mbar_wait(s.bars + BAR_EMPTY + stage, (use - 1) & 1);
+            if (j == 0) {
+                stage_coef<MASKMODE>(p, c, s.coef + (size_t)(it & 1) * c.rpc * N, g, rows_total);
+                __syncwarp();
+                if (lane == 0) {
+                    uint64_t* bar = s.bars + BAR_SRC + (it & 1);
+                    mbar_expect_tx(bar, (uint32_t)(nrows * 3) * rowbytes);
+                    for (int r = 0; r < nrows; ++r) {
+                        const int row = row0 + r, b = row / H, y = row - b * H;
+                        const float* gp = p.in.src + ((int64_t)b * 3 * H + y) * W;
+                        float* sp = s.src + ((size_t)((it & 1) * c.rpc + r) * 3) * c.pitch + PAD;
+                        for (int ch = 0; ch < 3; ++ch) tma_row(sp + (size_t)ch * c.pitch, gp + (int64_t)ch * p.hw, rowbytes, bar);
+                    }
+                }
+            }
+            if (lane == 0) {
+                uint64_t* bar = s.bars + BAR_FULL + stage;
+                const int n0 = j * c.hs, n1 = min(N, n0 + c.hs);
+                mbar_expect_tx(bar, (uint32_t)((n1 - n0) * nrows * streams) * rowbytes);
+                for (int r = 0; r < nrows; ++r) {
+                    const int row = row0 + r, b = row / H, y = row - b * H;
+                    int64_t off = (((int64_t)b * N + n0) * H + y) * W;
+                    size_t slot = ((size_t)(stage * c.hs) * c.rpc + r) * c.pitch + PAD;
+                    for (int n = n0; n < n1; ++n) {
+                        tma_row(s.lring + slot, p.in.logits + off, rowbytes, bar);
+                        if (MIX) tma_row(s.sring + slot, p.in.sigma + off, rowbytes, bar);
+                        if (DENSE) tma_row(s.mring + slot, reinterpret_cast<const float*>(p.in.mask) + soff(p.d.mask_stride, b, n, y, 0), rowbytes, bar);
+                        off += p.hw;
+                        slot += (size_t)c.rpc * c.pitch;
+                    }
+                }
+            }
+            if (++stage == c.nst) stage = 0, ++use;
+        }
     }
 }
 
@@ -402,19 +425,25 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
     const Smem s = carve(smem_raw, cfg, N, MIX, DENSE, 0, false);
     zero_pads(s, cfg, W);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 4; ++i) mbar_init(s.bars + i, 1);
+        for (int i = 0; i < cfg.nst; ++i) {
+            mbar_init(s.bars + BAR_FULL + i, 1);
+            mbar_init(s.bars + BAR_EMPTY + i, (uint32_t)(cfg.nc / 32));
+        }
+        mbar_init(s.bars + BAR_SRC, 1);
+        mbar_init(s.bars + BAR_SRC + 1, 1);
         mbar_fence_init();
     }
     __syncthreads();
-
     const int nit = (cfg.ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const Producer prod{p, cfg, s, rows_total, MIX, DENSE};
-    if (threadIdx.x == 0 && nit > 0) {
-        prod.src_rows(0, blockIdx.x);
-        prod.block(0, blockIdx.x, 0);
+    if ((int)threadIdx.x >= cfg.nc) {
+        producer_loop<MIX, MASKMODE>(p, cfg, s, nit);
+        return;
     }
+    const int lane = threadIdx.x & 31;
     const int r = threadIdx.x / cfg.tpr;
     const int x0 = (threadIdx.x - r * cfg.tpr) * PX;
+    int stage = 0;
+    uint32_t fphase = 0;
 
     for (int it = 0; it < nit; ++it) {
         const int g = blockIdx.x + it * gridDim.x;
@@ -422,7 +451,6 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
         const bool active = (r < rpc) && (row < rows_total);
         const int b = active ? row / H : 0, y = active ? row - b * H : 0;
         const int64_t rem = (int64_t)y * W + x0;
-        stage_coef<MASKMODE>(p, cfg, s.coef + (size_t)(it & 1) * rpc * N, g, rows_total);
 
         FwdAcc<MIX, PX> acc;
 #pragma unroll
@@ -447,31 +475,30 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
         }
         const PlaneCoef* coef = s.coef + ((size_t)(it & 1) * rpc + r) * N;
         const float* srow = s.src + ((size_t)((it & 1) * rpc + r) * 3) * pitch + PAD;
+        mbar_wait(s.bars + BAR_SRC + (it & 1), (it >> 1) & 1);
 
         for (int j = 0; j < NB; ++j) {
-            const int jb = it * NB + j;
-            __syncthreads();  // block jb-1 fully consumed; coefficients of this group visible
-            if (threadIdx.x == 0) {
-                if (j + 1 < NB) prod.block(jb + 1, g, j + 1);
-                else if (it + 1 < nit) prod.block(jb + 1, g + gridDim.x, 0);
-                if (j == 0 && it + 1 < nit) prod.src_rows(it + 1, g + gridDim.x);
-            }
-            if (!active) continue;
-            if (j == 0) mbar_wait(s.bars + 2 + (it & 1), (it >> 1) & 1);
-            mbar_wait(s.bars + (jb & 1), (jb >> 1) & 1);
-            const int n0 = j * hs, n1 = min(N, n0 + hs);
-            for (int n = n0; n < n1; ++n) {
-                const PlaneCoef k = load_coef(coef + n);
-                const size_t slot = ((size_t)((jb & 1) * hs + (n - n0)) * rpc + r) * pitch + PAD;
-                float mm[PX] = {};
-                bool perpix = false;
-                if (DENSE) {
-                    load_window<PX>(s.mring + slot + x0, mm);
-                    perpix = !all_ones<PX>(mm);
+            // every consumer thread waits (also idle ones: a warp must not run ahead of the ring and arrive twice
+            // in one phase of an empty barrier); the acquire also publishes the group's coefficients
+            mbar_wait(s.bars + BAR_FULL + stage, fphase);
+            if (active) {
+                const int n0 = j * hs, n1 = min(N, n0 + hs);
+                for (int n = n0; n < n1; ++n) {
+                    const PlaneCoef k = load_coef(coef + n);
+                    const size_t slot = ((size_t)(stage * hs + (n - n0)) * rpc + r) * pitch + PAD;
+                    float mm[PX] = {};
+                    bool perpix = false;
+                    if (DENSE) {
+                        load_window<PX>(s.mring + slot + x0, mm);
+                        perpix = !all_ones<PX>(mm);
+                    }
+                    if (DENSE && perpix) fwd_plane_any<MIX, PX, true>(srow, s.lring + slot, s.sring + slot, pitch, x0, W, k, mm, acc);
+                    else fwd_plane_any<MIX, PX, false>(srow, s.lring + slot, s.sring + slot, pitch, x0, W, k, mm, acc);
                 }
-                if (DENSE && perpix) fwd_plane_any<MIX, PX, true>(srow, s.lring + slot, s.sring + slot, pitch, x0, W, k, mm, acc);
-                else fwd_plane_any<MIX, PX, false>(srow, s.lring + slot, s.sring + slot, pitch, x0, W, k, mm, acc);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s.bars + BAR_EMPTY + stage);
+            if (++stage == cfg.nst) stage = 0, fphase ^= 1;
         }
         if (!active) continue;
         float o0[PX], o1[PX], o2[PX];
@@ -653,23 +680,26 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
     const Smem s = carve(smem_raw, cfg, N, MIX, DENSE, NE, WANT_DISP);
     zero_pads(s, cfg, W);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 4; ++i) mbar_init(s.bars + i, 1);
+        for (int i = 0; i < cfg.nst; ++i) {
+            mbar_init(s.bars + BAR_FULL + i, 1);
+            mbar_init(s.bars + BAR_EMPTY + i, (uint32_t)(cfg.nc / 32));
+        }
+        mbar_init(s.bars + BAR_SRC, 1);
+        mbar_init(s.bars + BAR_SRC + 1, 1);
         mbar_fence_init();
     }
     __syncthreads();
-
     const int nit = (cfg.ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const Producer prod{p, cfg, s, rows_total, MIX, DENSE};
-    if (threadIdx.x == 0 && nit > 0) {
-        prod.src_rows(0, blockIdx.x);
-        prod.block(0, blockIdx.x, 0);
-        if (NB > 1) prod.block(1, blockIdx.x, 1);
-        else if (nit > 1) prod.block(1, blockIdx.x + gridDim.x, 0);
+    if ((int)threadIdx.x >= cfg.nc) {
+        producer_loop<MIX, MASKMODE>(p, cfg, s, nit);
+        return;
     }
+    const int lane = threadIdx.x & 31;
     const int r = threadIdx.x / cfg.tpr;
     const int x0 = (threadIdx.x - r * cfg.tpr) * PX;
-    const int lane = threadIdx.x & 31;
     const size_t rowf = (size_t)rpc * pitch;
+    int stage = 0, jb = 0;
+    uint32_t fphase = 0;
 
     for (int it = 0; it < nit; ++it) {
         const int g = blockIdx.x + it * gridDim.x;
@@ -677,9 +707,10 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
         const bool active = (r < rpc) && (row < rows_total);
         const int b = active ? row / H : 0, y = active ? row - b * H : 0;
         const int64_t rem = (int64_t)y * W + x0;
-        stage_coef<MASKMODE>(p, cfg, s.coef + (size_t)(it & 1) * rpc * N, g, rows_total);
-        if (WANT_DISP)
-            for (int i = threadIdx.x; i < rpc * N; i += blockDim.x) s.gacc[i] = 0.0f;
+        if (WANT_DISP) {
+            for (int i = threadIdx.x; i < rpc * N; i += cfg.nc) s.gacc[i] = 0.0f;
+            consumer_sync(cfg.nc);
+        }
 
         BwdCtx<MIX, PX> c;
         if (active) {
@@ -722,27 +753,18 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
         }
         const PlaneCoef* coef = s.coef + ((size_t)(it & 1) * rpc + r) * N;
         const float* srow = s.src + ((size_t)((it & 1) * rpc + r) * 3) * pitch + PAD;
-        if (it > 0) {
-            // the previous group's last gather (phase B) still reads its coefficients and exchange rows after that
-            // group's final barrier; this group's gacc zeroing / coefficient staging touches other buffers, so no
-            // extra barrier is needed here: the first barrier below orders them before any use.
-        }
+        mbar_wait(s.bars + BAR_SRC + (it & 1), (it >> 1) & 1);
 
-        for (int j = 0; j < NB; ++j) {
-            const int jb = it * NB + j;
+        for (int j = 0; j < NB; ++j, ++jb) {
             const int n0 = j * hs, n1 = min(N, n0 + hs);
             float* dblk = s.dbuf + (size_t)(jb & 1) * hs * NE * rowf;
-            if (j == 0) __syncthreads();  // coefficients / gacc of this group visible to everyone
-            if (active) {
-                if (j == 0) mbar_wait(s.bars + 2 + (it & 1), (it >> 1) & 1);
-                mbar_wait(s.bars + (jb & 1), (jb >> 1) & 1);
-            }
-            // ---------------- phase A ----------------
+            mbar_wait(s.bars + BAR_FULL + stage, fphase);
+            // ---------------- phase A: per-target gradients into the exchange rows ----------------
             for (int n = n0; n < n1; ++n) {
                 float gsum = 0.0f;
                 if (active) {
                     const PlaneCoef k = load_coef(coef + n);
-                    const size_t slot = ((size_t)((jb & 1) * hs + (n - n0)) * rpc + r) * pitch + PAD;
+                    const size_t slot = ((size_t)(stage * hs + (n - n0)) * rpc + r) * pitch + PAD;
                     float* drow = dblk + ((size_t)(n - n0) * NE * rpc + r) * pitch + PAD;
                     float* frow = drow + rowf;
                     float mm[PX] = {};
@@ -755,8 +777,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
                     else gsum = bwd_plane_any<MIX, WANT_DISP, PX, false>(srow, s.lring + slot, s.sring + slot, pitch, x0, W, k, mm, c, drow, frow);
                 }
                 if (WANT_DISP) {
-                    // rows of a group may share a warp: reduce per row with shared-memory atomics after a warp sum
-                    // only when the whole warp belongs to one row
+                    // warp sum when the whole warp works on one row, per-thread shared atomics otherwise
                     const int r_first = (int)((threadIdx.x & ~31u) / cfg.tpr), r_last = (int)((threadIdx.x | 31u) / cfg.tpr);
                     if (r_first == r_last) {
                         const float sum = warp_sum(gsum);
@@ -766,19 +787,13 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
                     }
                 }
             }
-            __syncthreads();  // exchange rows of block jb complete; ring half jb&1 free again
-            if (threadIdx.x == 0) {
-                // block jb+1 is already in flight; refill this half with block jb+2
-                const int j2 = j + 2;
-                if (j2 < NB) prod.block(jb + 2, g, j2);
-                else if (it + 1 < nit) {
-                    const int jn = j2 - NB;  // 0 or 1
-                    if (jn < NB) prod.block(jb + 2, g + gridDim.x, jn);
-                    else if (it + 2 < nit) prod.block(jb + 2, g + 2 * gridDim.x, 0);  // NB == 1
-                }
-                if (j == 0 && it + 1 < nit) prod.src_rows(it + 1, g + gridDim.x);
-            }
-            // ---------------- phase B ----------------
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s.bars + BAR_EMPTY + stage);  // the ring stage is no longer needed
+            if (++stage == cfg.nst) stage = 0, fphase ^= 1;
+            // exchange rows of block jb complete.  They are double-buffered: block jb+1 writes the other buffer, and
+            // block jb+2 is only written after the next barrier, which every thread reaches after this gather.
+            consumer_sync(cfg.nc);
+            // ---------------- phase B: gather per source column, one streaming store per row ----------------
             if (active) {
                 for (int n = n0; n < n1; ++n) {
                     const PlaneCoef k = load_coef(coef + n);
@@ -798,8 +813,8 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
             }
         }
         if (WANT_DISP) {
-            __syncthreads();  // every atomic of this group has landed
-            for (int i = threadIdx.x; i < rpc * N; i += blockDim.x) {
+            consumer_sync(cfg.nc);  // every shared atomic of this group has landed
+            for (int i = threadIdx.x; i < rpc * N; i += cfg.nc) {
                 const int rr = i / N, n = i - rr * N;
                 const int rw = g * rpc + rr;
                 const float v = s.gacc[i];
@@ -808,7 +823,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
                     atomicAdd(p.gin.g_disp + soff(p.gin.g_disp_stride, bb, n, yy, 0), v);
                 }
             }
-            __syncthreads();  // before the next group zeroes gacc
+            consumer_sync(cfg.nc);  // before the next group zeroes gacc
         }
     }
 }
@@ -853,12 +868,21 @@ inline StreamCfg stream_cfg(const WarpParams& p, bool mix, bool dense, int ne_bw
     if (c.rpc < 1) c.rpc = 1;
     if (c.rpc > 8) c.rpc = 8;
     c.pitch = p.d.W + 2 * PAD;
+    c.nc = ((c.rpc * c.tpr + 31) / 32) * 32;
     c.hs = stream_env_int("PD_STREAM_HS", 4);
     if (c.hs > p.d.N) c.hs = p.d.N;
-    // shrink the pipeline depth until the CTA fits the shared-memory budget (default: three CTAs per SM)
+    c.nst = stream_env_int("PD_STREAM_NST", 3);
+    if (c.nst > MAX_STAGES) c.nst = MAX_STAGES;
+    if (c.nst < 1) c.nst = 1;
+    // shrink the pipeline until the CTA fits the shared-memory budget (default: three CTAs per SM)
     const size_t budget = (size_t)stream_env_int("PD_STREAM_SMEM_KB", 72) * 1024;
-    while (c.hs > 1 && stream_smem_bytes(c, p.d.N, mix, dense, ne_bwd, want_disp) > budget) --c.hs;
+    while (stream_smem_bytes(c, p.d.N, mix, dense, ne_bwd, want_disp) > budget) {
+        if (c.nst > 2) --c.nst;
+        else if (c.hs > 1) --c.hs;
+        else break;
+    }
     c.nblk = (p.d.N + c.hs - 1) / c.hs;
+    if (c.nst > c.nblk) c.nst = c.nblk;  // reuse of the per-group buffers relies on nst <= nblk (see producer_loop)
     c.ngroups = (p.d.B * p.d.H + c.rpc - 1) / c.rpc;
     return c;
 }
@@ -888,11 +912,11 @@ inline int stream_grid(int ngroups, int threads, size_t smem, const void* kernel
     return (int)(g < ngroups ? g : ngroups);
 }
 
-// THREADS is the CTA size the row groups are packed into; the launch uses rpc * tpr rounded up to a warp
+// THREADS = consumer threads the row groups are packed into + the producer warp
 template <bool MIX, int MASKMODE, int PX, int THREADS, int MINB>
 inline bool launch_fwd_stream_t(const WarpParams& p, cudaStream_t st) {
-    const StreamCfg c = stream_cfg<PX, THREADS>(p, MIX, MASKMODE == SMASK_DENSE, 0, false);
-    const int threads = ((c.rpc * c.tpr + 31) / 32) * 32;
+    const StreamCfg c = stream_cfg<PX, THREADS - 32>(p, MIX, MASKMODE == SMASK_DENSE, 0, false);
+    const int threads = c.nc + 32;
     if (threads > THREADS) return false;
     const size_t smem = stream_smem_bytes(c, p.d.N, MIX, MASKMODE == SMASK_DENSE, 0, false);
     if (smem > 220 * 1024) return false;
@@ -904,8 +928,8 @@ inline bool launch_fwd_stream_t(const WarpParams& p, cudaStream_t st) {
 
 template <bool MIX, int MASKMODE, bool WANT_DISP, int PX, int THREADS, int MINB>
 inline bool launch_bwd_stream_t(const WarpParams& p, cudaStream_t st) {
-    const StreamCfg c = stream_cfg<PX, THREADS>(p, MIX, MASKMODE == SMASK_DENSE, MIX ? 2 : 1, WANT_DISP);
-    const int threads = ((c.rpc * c.tpr + 31) / 32) * 32;
+    const StreamCfg c = stream_cfg<PX, THREADS - 32>(p, MIX, MASKMODE == SMASK_DENSE, MIX ? 2 : 1, WANT_DISP);
+    const int threads = c.nc + 32;
     if (threads > THREADS) return false;
     const size_t smem = stream_smem_bytes(c, p.d.N, MIX, MASKMODE == SMASK_DENSE, MIX ? 2 : 1, WANT_DISP);
     if (smem > 220 * 1024) return false;
@@ -918,9 +942,9 @@ inline bool launch_bwd_stream_t(const WarpParams& p, cudaStream_t st) {
 template <bool MIX, int MASKMODE>
 inline bool launch_fwd_stream_m(const WarpParams& p, cudaStream_t st) {
     const int W = p.d.W;
-    if (W % 8 == 0 && W / 8 <= 160 && stream_env_int("PD_STREAM_PX8", 0)) return launch_fwd_stream_t<MIX, MASKMODE, 8, 160, MIX ? 2 : 3>(p, st);
-    if (W / 4 <= 160) return launch_fwd_stream_t<MIX, MASKMODE, 4, 160, MIX ? 3 : 4>(p, st);
-    if (W / 4 <= 320) return launch_fwd_stream_t<MIX, MASKMODE, 4, 320, MIX ? 1 : 2>(p, st);
+    if (W % 8 == 0 && W / 8 <= 160 && stream_env_int("PD_STREAM_PX8", 0)) return launch_fwd_stream_t<MIX, MASKMODE, 8, 192, 2>(p, st);
+    if (W / 4 <= 160) return launch_fwd_stream_t<MIX, MASKMODE, 4, 192, MIX ? 2 : 4>(p, st);
+    if (W / 4 <= 320) return launch_fwd_stream_t<MIX, MASKMODE, 4, 352, 1>(p, st);
     return false;
 }
 
@@ -933,9 +957,9 @@ inline bool launch_fwd_stream(const WarpParams& p, cudaStream_t st) {
 template <bool MIX, int MASKMODE, bool WANT_DISP>
 inline bool launch_bwd_stream_w(const WarpParams& p, cudaStream_t st) {
     const int W = p.d.W;
-    if (W % 8 == 0 && W / 8 <= 160 && stream_env_int("PD_STREAM_PX8", 0)) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 8, 160, 2>(p, st);
-    if (W / 4 <= 160) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 4, 160, MIX ? 2 : 3>(p, st);
-    if (W / 4 <= 320) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 4, 320, 1>(p, st);
+    if (W % 8 == 0 && W / 8 <= 160 && stream_env_int("PD_STREAM_PX8", 0)) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 8, 192, 1>(p, st);
+    if (W / 4 <= 160) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 4, 192, MIX ? 2 : 3>(p, st);
+    if (W / 4 <= 320) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 4, 352, 1>(p, st);
     return false;
 }
 

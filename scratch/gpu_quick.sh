@@ -4,7 +4,7 @@ TAG=${1:-q}
 O=gpurun_out
 mkdir -p $O
 timeout 600 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"
-tail -15 $O/${TAG}_pytest.log
+tail -5 $O/${TAG}_pytest.log
 run() {  # name, env...
   local name=$1; shift
   env "$@" timeout 300 python bench.py --config ${CFG:-cfg2} --steps 10 --warmup 3 --layout ${LAYOUT:-compact} --no-cpu-baseline > $O/${TAG}_$name.json 2> $O/${TAG}_$name.err
@@ -17,15 +17,6 @@ except Exception as e:
     print("$name FAILED", e); print(open("$O/${TAG}_$name.err").read()[-800:])
 PY
 }
-run exact PD_EXACT_COORDS=1
-run stream_default X=1
-run px4 PD_STREAM_PX4=1
-run px4_hs2 PD_STREAM_PX4=1 PD_STREAM_HS=2
-run px4_hs8 PD_STREAM_PX4=1 PD_STREAM_HS=8 PD_STREAM_SMEM_KB=110
-run px8_hs2 PD_STREAM_HS=2
-run px8_big PD_STREAM_SMEM_KB=110
-LAYOUT=reference run dense_default X=1
-LAYOUT=reference run dense_px4 PD_STREAM_PX4=1
-CFG=cfg3 LAYOUT=compact run cfg3_compact X=1
-CFG=cfg3 LAYOUT=reference run cfg3_dense X=1
-CFG=cfg3 LAYOUT=compact run cfg3_exact PD_EXACT_COORDS=1
+if [ -f scratch/variants.txt ]; then
+  while read -r line; do [ -z "$line" ] && continue; eval "run $line"; done < scratch/variants.txt
+fi
