@@ -40,7 +40,8 @@ struct __align__(16) PlaneCoef {
     float wl0;       // wc0 * log2(e)                       (logit taps, softmax in base 2)
     float wl1;       // wc1 * log2(e)
     float m;         // row mask value (1 when the mask is dense or absent)
-    float pad0, pad1;
+    int k4;          // k0 * 4: the shift in bytes
+    float pad1;
 };
 
 struct StreamCfg {
@@ -76,6 +77,24 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // consumer-only CTA barrier (hardware barrier 1); the producer warp never joins it
 __device__ __forceinline__ void consumer_sync(int nc) { asm volatile("bar.sync 1, %0;" ::"r"(nc) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -104,6 +123,25 @@ __device__ __forceinline__ float4 lds128(const float* q) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(q)));
     return v;
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
+// WF consecutive floats from the 16-byte aligned shared address a
+template <int WF>
+__device__ __forceinline__ void load_window(uint32_t a, float (&v)[WF]) {
+#pragma unroll
+    for (int i = 0; i < WF / 4; ++i) {
+        float4 t = lds128(a + 16 * i);
+        v[4 * i] = t.x, v[4 * i + 1] = t.y, v[4 * i + 2] = t.z, v[4 * i + 3] = t.w;
+    }
 }
 
 template <int WF>
@@ -201,7 +239,7 @@ __device__ __forceinline__ void stage_coef(const WarpParams& p, const StreamCfg&
         const int r = idx / N, n = idx - r * N;
         const int row = g * c.rpc + r;
         PlaneCoef k;
-        k.k0 = W + 16, k.wc0 = k.wc1 = k.wl0 = k.wl1 = 0.0f, k.m = 0.0f, k.pad0 = k.pad1 = 0.0f;
+        k.k0 = W + 16, k.wc0 = k.wc1 = k.wl0 = k.wl1 = 0.0f, k.m = 0.0f, k.pad1 = 0.0f;
         if (row < rows_total) {
             const int b = row / H, y = row - b * H;
             const float d = __ldg(p.in.disp + soff(p.d.disp_stride, b, n, y, 0));
@@ -217,6 +255,7 @@ __device__ __forceinline__ void stage_coef(const WarpParams& p, const StreamCfg&
             k.wl0 = k.wc0 * kLog2e;
             k.wl1 = k.wc1 * kLog2e;
         }
+        k.k4 = k.k0 * 4;
         coef[idx] = k;
     }
 }
@@ -276,16 +315,17 @@ __device__ __forceinline__ void producer_loop(const WarpParams& p, const StreamC
     }
 }
 
-__device__ __forceinline__ PlaneCoef load_coef(const PlaneCoef* q) {
-    const float4 a = lds128(reinterpret_cast<const float*>(q));
-    const float4 b = lds128(reinterpret_cast<const float*>(q) + 4);
+__device__ __forceinline__ PlaneCoef load_coef(uint32_t a32) {
+    const float4 a = lds128(a32);
+    const float4 b = lds128(a32 + 16);
     PlaneCoef k;
-    k.k0 = __float_as_int(a.x), k.wc0 = a.y, k.wc1 = a.z, k.wl0 = a.w, k.wl1 = b.x, k.m = b.y;
+    k.k0 = __float_as_int(a.x), k.wc0 = a.y, k.wc1 = a.z, k.wl0 = a.w, k.wl1 = b.x, k.m = b.y, k.k4 = __float_as_int(b.z);
     return k;
 }
 
-// window base (multiple of 4, clamped into the zero pads) of taps starting at column a
-__device__ __forceinline__ int window_base(int a, int W) { return min(max(a & ~3, -PAD), W); }
+// byte offset (multiple of 16, clamped into the zero pads) of the window holding the taps that start at byte
+// offset at4 of a row
+__device__ __forceinline__ int window_off(int at4, int W4) { return min(max(at4 & ~15, -4 * PAD), W4); }
 
 template <int PX>
 __device__ __forceinline__ bool all_ones(const float (&m)[PX]) {
@@ -306,11 +346,12 @@ struct FwdAcc {
 };
 
 template <bool MIX, int PX, int R, bool PERPIX>
-__device__ __forceinline__ void fwd_plane(const float* srow, const float* lrow, const float* sgrow, int pitch, int bc, const PlaneCoef& k,
+__device__ __forceinline__ void fwd_plane(uint32_t srow, uint32_t lrow, uint32_t sgrow, uint32_t pitch4, const PlaneCoef& k,
                                           const float (&mm)[PX], FwdAcc<MIX, PX>& a) {
+    // srow / lrow / sgrow: shared addresses of the (already window-aligned) first float of the tap windows
     constexpr int WF = PX + 4;
     float v[WF], t[PX];
-    load_window<WF>(lrow + bc, v);
+    load_window<WF>(lrow, v);
 #pragma unroll
     for (int i = 0; i < PX; ++i) {
         if (PERPIX) t[i] = fmaf(fmaf(k.wl0, v[R + i], k.wl1 * v[R + i + 1]), mm[i], -a.Ml2[i]);
@@ -348,18 +389,18 @@ __device__ __forceinline__ void fwd_plane(const float* srow, const float* lrow, 
             const float em = PERPIX ? e[i] * mm[i] : e[i];
             a0[i] = em * k.wc0, a1[i] = em * k.wc1;
         }
-        load_window<WF>(srow + bc, v);
+        load_window<WF>(srow, v);
 #pragma unroll
         for (int i = 0; i < PX; ++i) a.R0[i] = fmaf(a0[i], v[R + i], fmaf(a1[i], v[R + i + 1], a.R0[i]));
-        load_window<WF>(srow + pitch + bc, v);
+        load_window<WF>(srow + pitch4, v);
 #pragma unroll
         for (int i = 0; i < PX; ++i) a.R1[i] = fmaf(a0[i], v[R + i], fmaf(a1[i], v[R + i + 1], a.R1[i]));
-        load_window<WF>(srow + 2 * pitch + bc, v);
+        load_window<WF>(srow + 2 * pitch4, v);
 #pragma unroll
         for (int i = 0; i < PX; ++i) a.R2[i] = fmaf(a0[i], v[R + i], fmaf(a1[i], v[R + i + 1], a.R2[i]));
     } else {
         float es[PX], inv[PX], err[PX];
-        load_window<WF>(sgrow + bc, v);
+        load_window<WF>(sgrow, v);
 #pragma unroll
         for (int i = 0; i < PX; ++i) {
             float s = fmaf(k.wc0, v[R + i], k.wc1 * v[R + i + 1]);
@@ -369,7 +410,7 @@ __device__ __forceinline__ void fwd_plane(const float* srow, const float* lrow, 
             es[i] = e[i] * inv[i];
             a.A[i] += es[i];
         }
-        load_window<WF>(srow + bc, v);
+        load_window<WF>(srow, v);
 #pragma unroll
         for (int i = 0; i < PX; ++i) {
             float c = fmaf(k.wc0, v[R + i], k.wc1 * v[R + i + 1]);
@@ -377,7 +418,7 @@ __device__ __forceinline__ void fwd_plane(const float* srow, const float* lrow, 
             a.R0[i] = fmaf(es[i], c, a.R0[i]);
             err[i] = fabsf(c - a.tr[i]);
         }
-        load_window<WF>(srow + pitch + bc, v);
+        load_window<WF>(srow + pitch4, v);
 #pragma unroll
         for (int i = 0; i < PX; ++i) {
             float c = fmaf(k.wc0, v[R + i], k.wc1 * v[R + i + 1]);
@@ -385,7 +426,7 @@ __device__ __forceinline__ void fwd_plane(const float* srow, const float* lrow, 
             a.R1[i] = fmaf(es[i], c, a.R1[i]);
             err[i] += fabsf(c - a.tg[i]);
         }
-        load_window<WF>(srow + 2 * pitch + bc, v);
+        load_window<WF>(srow + 2 * pitch4, v);
 #pragma unroll
         for (int i = 0; i < PX; ++i) {
             float c = fmaf(k.wc0, v[R + i], k.wc1 * v[R + i + 1]);
@@ -403,16 +444,18 @@ __device__ __forceinline__ void fwd_plane(const float* srow, const float* lrow, 
     }
 }
 
+// at4 = byte offset of the first tap inside the row; the windows start at the aligned offset below it
 template <bool MIX, int PX, bool PERPIX>
-__device__ __forceinline__ void fwd_plane_any(const float* srow, const float* lrow, const float* sgrow, int pitch, int x0, int W, const PlaneCoef& k,
+__device__ __forceinline__ void fwd_plane_any(uint32_t srow, uint32_t lrow, uint32_t sgrow, uint32_t pitch4, int at4, int W4, const PlaneCoef& k,
                                               const float (&mm)[PX], FwdAcc<MIX, PX>& a) {
-    const int at = x0 + k.k0;
-    const int bc = window_base(at, W);
-    switch (at & 3) {
-        case 0: fwd_plane<MIX, PX, 0, PERPIX>(srow, lrow, sgrow, pitch, bc, k, mm, a); break;
-        case 1: fwd_plane<MIX, PX, 1, PERPIX>(srow, lrow, sgrow, pitch, bc, k, mm, a); break;
-        case 2: fwd_plane<MIX, PX, 2, PERPIX>(srow, lrow, sgrow, pitch, bc, k, mm, a); break;
-        default: fwd_plane<MIX, PX, 3, PERPIX>(srow, lrow, sgrow, pitch, bc, k, mm, a); break;
+    const int wo = window_off(at4, W4);
+    srow += wo, lrow += wo, sgrow += wo;
+    if (at4 & 8) {
+        if (at4 & 4) fwd_plane<MIX, PX, 3, PERPIX>(srow, lrow, sgrow, pitch4, k, mm, a);
+        else fwd_plane<MIX, PX, 2, PERPIX>(srow, lrow, sgrow, pitch4, k, mm, a);
+    } else {
+        if (at4 & 4) fwd_plane<MIX, PX, 1, PERPIX>(srow, lrow, sgrow, pitch4, k, mm, a);
+        else fwd_plane<MIX, PX, 0, PERPIX>(srow, lrow, sgrow, pitch4, k, mm, a);
     }
 }
 
@@ -442,6 +485,11 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
     const int lane = threadIdx.x & 31;
     const int r = threadIdx.x / cfg.tpr;
     const int x0 = (threadIdx.x - r * cfg.tpr) * PX;
+    // 32-bit shared-window addresses of the row interiors (byte units from here on)
+    const uint32_t bars = smem_u32(s.bars), coef0 = smem_u32(s.coef), src0 = smem_u32(s.src + PAD), lring0 = smem_u32(s.lring + PAD);
+    const uint32_t pitch4 = (uint32_t)pitch * 4u, rowpitch4 = (uint32_t)rpc * pitch4;
+    const uint32_t sdelta = (uint32_t)((s.sring - s.lring) * sizeof(float)), mdelta = (uint32_t)((s.mring - s.lring) * sizeof(float));
+    const int x04 = x0 * 4, W4 = W * 4;
     int stage = 0;
     uint32_t fphase = 0;
 
@@ -473,31 +521,31 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
                 for (int i = 0; i < PX; ++i) acc.ea[i] = fabsf(sr[i] - acc.tr[i]) + fabsf(sg[i] - acc.tg[i]) + fabsf(sb[i] - acc.tb[i]);  // channel SUM
             }
         }
-        const PlaneCoef* coef = s.coef + ((size_t)(it & 1) * rpc + r) * N;
-        const float* srow = s.src + ((size_t)((it & 1) * rpc + r) * 3) * pitch + PAD;
-        mbar_wait(s.bars + BAR_SRC + (it & 1), (it >> 1) & 1);
+        uint32_t coef_a = coef0 + (uint32_t)(((it & 1) * rpc + r) * N) * (uint32_t)sizeof(PlaneCoef);
+        const uint32_t srow = src0 + (uint32_t)(((it & 1) * rpc + r) * 3) * pitch4;
+        mbar_wait(bars + 8 * (BAR_SRC + (it & 1)), (it >> 1) & 1);
 
         for (int j = 0; j < NB; ++j) {
             // every consumer thread waits (also idle ones: a warp must not run ahead of the ring and arrive twice
             // in one phase of an empty barrier); the acquire also publishes the group's coefficients
-            mbar_wait(s.bars + BAR_FULL + stage, fphase);
+            mbar_wait(bars + 8 * (BAR_FULL + stage), fphase);
             if (active) {
-                const int n0 = j * hs, n1 = min(N, n0 + hs);
-                for (int n = n0; n < n1; ++n) {
-                    const PlaneCoef k = load_coef(coef + n);
-                    const size_t slot = ((size_t)(stage * hs + (n - n0)) * rpc + r) * pitch + PAD;
+                const int np = min(hs, N - j * hs);
+                uint32_t lrow = lring0 + (uint32_t)(stage * hs * rpc + r) * pitch4;
+                for (int q = 0; q < np; ++q, lrow += rowpitch4, coef_a += (uint32_t)sizeof(PlaneCoef)) {
+                    const PlaneCoef k = load_coef(coef_a);
                     float mm[PX] = {};
                     bool perpix = false;
                     if (DENSE) {
-                        load_window<PX>(s.mring + slot + x0, mm);
+                        load_window<PX>(lrow + mdelta + x04, mm);
                         perpix = !all_ones<PX>(mm);
                     }
-                    if (DENSE && perpix) fwd_plane_any<MIX, PX, true>(srow, s.lring + slot, s.sring + slot, pitch, x0, W, k, mm, acc);
-                    else fwd_plane_any<MIX, PX, false>(srow, s.lring + slot, s.sring + slot, pitch, x0, W, k, mm, acc);
+                    if (DENSE && perpix) fwd_plane_any<MIX, PX, true>(srow, lrow, lrow + sdelta, pitch4, x04 + k.k4, W4, k, mm, acc);
+                    else fwd_plane_any<MIX, PX, false>(srow, lrow, lrow + sdelta, pitch4, x04 + k.k4, W4, k, mm, acc);
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(s.bars + BAR_EMPTY + stage);
+            if (lane == 0) mbar_arrive(bars + 8 * (BAR_EMPTY + stage));
             if (++stage == cfg.nst) stage = 0, fphase ^= 1;
         }
         if (!active) continue;
@@ -547,11 +595,13 @@ __device__ __forceinline__ float sgn(float a, float b) { return (a > b) ? 1.0f :
 // phase A of one plane: dL/d(masked logit) [and dL/d(clamped-through sigma)] per target pixel into the exchange
 // rows; returns this thread's contribution to dL/d(sign*disparity) of the plane row
 template <bool MIX, bool WANT_DISP, int PX, int R, bool PERPIX>
-__device__ __forceinline__ float bwd_plane(const float* srow, const float* lrow, const float* sgrow, int pitch, int bc, const PlaneCoef& k,
-                                           const float (&mm)[PX], const BwdCtx<MIX, PX>& c, float* drow, float* frow, int x0) {
+__device__ __forceinline__ float bwd_plane(uint32_t srow, uint32_t lrow, uint32_t sgrow, uint32_t pitch4, const PlaneCoef& k,
+                                           const float (&mm)[PX], const BwdCtx<MIX, PX>& c, uint32_t dst, uint32_t fdelta) {
+    // srow / lrow / sgrow: window-aligned shared addresses; dst: this thread's slot in the exchange row of dL/dlogit,
+    // dst + fdelta the one of dL/dsigma
     constexpr int WF = PX + 4;
     float v[WF], pi[PX], Gn[PX], dlu[PX], gx[PX];
-    load_window<WF>(lrow + bc, v);
+    load_window<WF>(lrow, v);
 #pragma unroll
     for (int i = 0; i < PX; ++i) {
         float t;
@@ -561,21 +611,21 @@ __device__ __forceinline__ float bwd_plane(const float* srow, const float* lrow,
         if (WANT_DISP) dlu[i] = v[R + i + 1] - v[R + i];
     }
     float cr[PX], cg[PX], cb[PX], dr[WANT_DISP ? PX : 1], dg[WANT_DISP ? PX : 1], db[WANT_DISP ? PX : 1];
-    load_window<WF>(srow + bc, v);
+    load_window<WF>(srow, v);
 #pragma unroll
     for (int i = 0; i < PX; ++i) {
         cr[i] = fmaf(k.wc0, v[R + i], k.wc1 * v[R + i + 1]);
         if (PERPIX) cr[i] *= mm[i];
         if (WANT_DISP) dr[i] = v[R + i + 1] - v[R + i];
     }
-    load_window<WF>(srow + pitch + bc, v);
+    load_window<WF>(srow + pitch4, v);
 #pragma unroll
     for (int i = 0; i < PX; ++i) {
         cg[i] = fmaf(k.wc0, v[R + i], k.wc1 * v[R + i + 1]);
         if (PERPIX) cg[i] *= mm[i];
         if (WANT_DISP) dg[i] = v[R + i + 1] - v[R + i];
     }
-    load_window<WF>(srow + 2 * pitch + bc, v);
+    load_window<WF>(srow + 2 * pitch4, v);
 #pragma unroll
     for (int i = 0; i < PX; ++i) {
         cb[i] = fmaf(k.wc0, v[R + i], k.wc1 * v[R + i + 1]);
@@ -591,7 +641,7 @@ __device__ __forceinline__ float bwd_plane(const float* srow, const float* lrow,
             if (WANT_DISP) gx[i] = fmaf(dl[i], dlu[i], pi[i] * (c.g0[i] * dr[i] + c.g1[i] * dg[i] + c.g2[i] * db[i]));
         }
     } else {
-        load_window<WF>(sgrow + bc, v);
+        load_window<WF>(sgrow, v);
 #pragma unroll
         for (int i = 0; i < PX; ++i) {
             float sraw = fmaf(k.wc0, v[R + i], k.wc1 * v[R + i + 1]);
@@ -629,44 +679,45 @@ __device__ __forceinline__ float bwd_plane(const float* srow, const float* lrow,
     }
 #pragma unroll
     for (int i = 0; i < PX / 4; ++i) {
-        *reinterpret_cast<float4*>(drow + x0 + 4 * i) = make_float4(dl[4 * i], dl[4 * i + 1], dl[4 * i + 2], dl[4 * i + 3]);
-        if constexpr (MIX) *reinterpret_cast<float4*>(frow + x0 + 4 * i) = make_float4(ds[4 * i], ds[4 * i + 1], ds[4 * i + 2], ds[4 * i + 3]);
+        sts128(dst + 16 * i, dl[4 * i], dl[4 * i + 1], dl[4 * i + 2], dl[4 * i + 3]);
+        if constexpr (MIX) sts128(dst + fdelta + 16 * i, ds[4 * i], ds[4 * i + 1], ds[4 * i + 2], ds[4 * i + 3]);
     }
     return gsum;
 }
 
 template <bool MIX, bool WANT_DISP, int PX, bool PERPIX>
-__device__ __forceinline__ float bwd_plane_any(const float* srow, const float* lrow, const float* sgrow, int pitch, int x0, int W, const PlaneCoef& k,
-                                               const float (&mm)[PX], const BwdCtx<MIX, PX>& c, float* drow, float* frow) {
-    const int at = x0 + k.k0;
-    const int bc = window_base(at, W);
-    switch (at & 3) {
-        case 0: return bwd_plane<MIX, WANT_DISP, PX, 0, PERPIX>(srow, lrow, sgrow, pitch, bc, k, mm, c, drow, frow, x0);
-        case 1: return bwd_plane<MIX, WANT_DISP, PX, 1, PERPIX>(srow, lrow, sgrow, pitch, bc, k, mm, c, drow, frow, x0);
-        case 2: return bwd_plane<MIX, WANT_DISP, PX, 2, PERPIX>(srow, lrow, sgrow, pitch, bc, k, mm, c, drow, frow, x0);
-        default: return bwd_plane<MIX, WANT_DISP, PX, 3, PERPIX>(srow, lrow, sgrow, pitch, bc, k, mm, c, drow, frow, x0);
+__device__ __forceinline__ float bwd_plane_any(uint32_t srow, uint32_t lrow, uint32_t sgrow, uint32_t pitch4, int at4, int W4, const PlaneCoef& k,
+                                               const float (&mm)[PX], const BwdCtx<MIX, PX>& c, uint32_t dst, uint32_t fdelta) {
+    const int wo = window_off(at4, W4);
+    srow += wo, lrow += wo, sgrow += wo;
+    if (at4 & 8) {
+        if (at4 & 4) return bwd_plane<MIX, WANT_DISP, PX, 3, PERPIX>(srow, lrow, sgrow, pitch4, k, mm, c, dst, fdelta);
+        return bwd_plane<MIX, WANT_DISP, PX, 2, PERPIX>(srow, lrow, sgrow, pitch4, k, mm, c, dst, fdelta);
     }
+    if (at4 & 4) return bwd_plane<MIX, WANT_DISP, PX, 1, PERPIX>(srow, lrow, sgrow, pitch4, k, mm, c, dst, fdelta);
+    return bwd_plane<MIX, WANT_DISP, PX, 0, PERPIX>(srow, lrow, sgrow, pitch4, k, mm, c, dst, fdelta);
 }
 
 // phase B of one plane: gradient of source column j = wc0 * D[j - k0] + wc1 * D[j - k0 - 1]
 template <int PX, int R>
-__device__ __forceinline__ void gather_row(const float* drow, int bc, float w0, float w1, float (&g)[PX]) {
+__device__ __forceinline__ void gather_row(uint32_t dwin, float w0, float w1, float (&g)[PX]) {
     constexpr int WF = PX + 4;
     float v[WF];
-    load_window<WF>(drow + bc, v);
+    load_window<WF>(dwin, v);
 #pragma unroll
     for (int i = 0; i < PX; ++i) g[i] = fmaf(w0, v[R + i + 1], w1 * v[R + i]);
 }
 
+// drow: shared address of the exchange row interior; at4 = 4 * (x0 - k0 - 1)
 template <int PX>
-__device__ __forceinline__ void gather_any(const float* drow, int x0, int W, int k0, float w0, float w1, float (&g)[PX]) {
-    const int at = x0 - k0 - 1;
-    const int bc = window_base(at, W);
-    switch (at & 3) {
-        case 0: gather_row<PX, 0>(drow, bc, w0, w1, g); break;
-        case 1: gather_row<PX, 1>(drow, bc, w0, w1, g); break;
-        case 2: gather_row<PX, 2>(drow, bc, w0, w1, g); break;
-        default: gather_row<PX, 3>(drow, bc, w0, w1, g); break;
+__device__ __forceinline__ void gather_any(uint32_t drow, int at4, int W4, float w0, float w1, float (&g)[PX]) {
+    const uint32_t dwin = drow + window_off(at4, W4);
+    if (at4 & 8) {
+        if (at4 & 4) gather_row<PX, 3>(dwin, w0, w1, g);
+        else gather_row<PX, 2>(dwin, w0, w1, g);
+    } else {
+        if (at4 & 4) gather_row<PX, 1>(dwin, w0, w1, g);
+        else gather_row<PX, 0>(dwin, w0, w1, g);
     }
 }
 
@@ -697,7 +748,11 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
     const int lane = threadIdx.x & 31;
     const int r = threadIdx.x / cfg.tpr;
     const int x0 = (threadIdx.x - r * cfg.tpr) * PX;
-    const size_t rowf = (size_t)rpc * pitch;
+    const uint32_t bars = smem_u32(s.bars), coef0 = smem_u32(s.coef), src0 = smem_u32(s.src + PAD), lring0 = smem_u32(s.lring + PAD);
+    const uint32_t dbuf0 = smem_u32(s.dbuf + PAD);
+    const uint32_t pitch4 = (uint32_t)pitch * 4u, rowpitch4 = (uint32_t)rpc * pitch4;
+    const uint32_t sdelta = (uint32_t)((s.sring - s.lring) * sizeof(float)), mdelta = (uint32_t)((s.mring - s.lring) * sizeof(float));
+    const int x04 = x0 * 4, W4 = W * 4;
     int stage = 0, jb = 0;
     uint32_t fphase = 0;
 
@@ -751,62 +806,70 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
                 }
             }
         }
-        const PlaneCoef* coef = s.coef + ((size_t)(it & 1) * rpc + r) * N;
-        const float* srow = s.src + ((size_t)((it & 1) * rpc + r) * 3) * pitch + PAD;
-        mbar_wait(s.bars + BAR_SRC + (it & 1), (it >> 1) & 1);
+        const uint32_t coef_g = coef0 + (uint32_t)(((it & 1) * rpc + r) * N) * (uint32_t)sizeof(PlaneCoef);
+        const uint32_t srow = src0 + (uint32_t)(((it & 1) * rpc + r) * 3) * pitch4;
+        mbar_wait(bars + 8 * (BAR_SRC + (it & 1)), (it >> 1) & 1);
 
         for (int j = 0; j < NB; ++j, ++jb) {
-            const int n0 = j * hs, n1 = min(N, n0 + hs);
-            float* dblk = s.dbuf + (size_t)(jb & 1) * hs * NE * rowf;
-            mbar_wait(s.bars + BAR_FULL + stage, fphase);
+            const int n0 = j * hs, np = min(hs, N - n0);
+            // exchange rows of this block: [plane][NE][rpc][pitch], double-buffered over blocks
+            const uint32_t dblk = dbuf0 + (uint32_t)((jb & 1) * hs * NE * rpc + r) * pitch4;
+            mbar_wait(bars + 8 * (BAR_FULL + stage), fphase);
             // ---------------- phase A: per-target gradients into the exchange rows ----------------
-            for (int n = n0; n < n1; ++n) {
-                float gsum = 0.0f;
-                if (active) {
-                    const PlaneCoef k = load_coef(coef + n);
-                    const size_t slot = ((size_t)(stage * hs + (n - n0)) * rpc + r) * pitch + PAD;
-                    float* drow = dblk + ((size_t)(n - n0) * NE * rpc + r) * pitch + PAD;
-                    float* frow = drow + rowf;
-                    float mm[PX] = {};
-                    bool perpix = false;
-                    if (DENSE) {
-                        load_window<PX>(s.mring + slot + x0, mm);
-                        perpix = !all_ones<PX>(mm);
+            {
+                uint32_t lrow = lring0 + (uint32_t)(stage * hs * rpc + r) * pitch4;
+                uint32_t coef_a = coef_g + (uint32_t)n0 * (uint32_t)sizeof(PlaneCoef);
+                uint32_t drow = dblk;
+                for (int q = 0; q < np; ++q, lrow += rowpitch4, coef_a += (uint32_t)sizeof(PlaneCoef), drow += NE * rowpitch4) {
+                    float gsum = 0.0f;
+                    if (active) {
+                        const PlaneCoef k = load_coef(coef_a);
+                        float mm[PX] = {};
+                        bool perpix = false;
+                        if (DENSE) {
+                            load_window<PX>(lrow + mdelta + x04, mm);
+                            perpix = !all_ones<PX>(mm);
+                        }
+                        if (DENSE && perpix)
+                            gsum = bwd_plane_any<MIX, WANT_DISP, PX, true>(srow, lrow, lrow + sdelta, pitch4, x04 + k.k4, W4, k, mm, c, drow + x04, rowpitch4);
+                        else
+                            gsum = bwd_plane_any<MIX, WANT_DISP, PX, false>(srow, lrow, lrow + sdelta, pitch4, x04 + k.k4, W4, k, mm, c, drow + x04, rowpitch4);
                     }
-                    if (DENSE && perpix) gsum = bwd_plane_any<MIX, WANT_DISP, PX, true>(srow, s.lring + slot, s.sring + slot, pitch, x0, W, k, mm, c, drow, frow);
-                    else gsum = bwd_plane_any<MIX, WANT_DISP, PX, false>(srow, s.lring + slot, s.sring + slot, pitch, x0, W, k, mm, c, drow, frow);
-                }
-                if (WANT_DISP) {
-                    // warp sum when the whole warp works on one row, per-thread shared atomics otherwise
-                    const int r_first = (int)((threadIdx.x & ~31u) / cfg.tpr), r_last = (int)((threadIdx.x | 31u) / cfg.tpr);
-                    if (r_first == r_last) {
-                        const float sum = warp_sum(gsum);
-                        if (lane == 0 && r < rpc && sum != 0.0f) atomicAdd(s.gacc + r * N + n, sum * p.d.disp_sign);
-                    } else if (active && gsum != 0.0f) {
-                        atomicAdd(s.gacc + r * N + n, gsum * p.d.disp_sign);
+                    if (WANT_DISP) {
+                        // warp sum when the whole warp works on one row, per-thread shared atomics otherwise
+                        const int n = n0 + q;
+                        const int r_first = (int)((threadIdx.x & ~31u) / cfg.tpr), r_last = (int)((threadIdx.x | 31u) / cfg.tpr);
+                        if (r_first == r_last) {
+                            const float sum = warp_sum(gsum);
+                            if (lane == 0 && r < rpc && sum != 0.0f) atomicAdd(s.gacc + r * N + n, sum * p.d.disp_sign);
+                        } else if (active && gsum != 0.0f) {
+                            atomicAdd(s.gacc + r * N + n, gsum * p.d.disp_sign);
+                        }
                     }
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(s.bars + BAR_EMPTY + stage);  // the ring stage is no longer needed
+            if (lane == 0) mbar_arrive(bars + 8 * (BAR_EMPTY + stage));  // the ring stage is no longer needed
             if (++stage == cfg.nst) stage = 0, fphase ^= 1;
             // exchange rows of block jb complete.  They are double-buffered: block jb+1 writes the other buffer, and
             // block jb+2 is only written after the next barrier, which every thread reaches after this gather.
             consumer_sync(cfg.nc);
             // ---------------- phase B: gather per source column, one streaming store per row ----------------
             if (active) {
-                for (int n = n0; n < n1; ++n) {
-                    const PlaneCoef k = load_coef(coef + n);
-                    const float* drow = dblk + ((size_t)(n - n0) * NE * rpc + r) * pitch + PAD;
-                    const int64_t o = (((int64_t)b * N + n) * H + y) * W + x0;
+                uint32_t coef_a = coef_g + (uint32_t)n0 * (uint32_t)sizeof(PlaneCoef);
+                uint32_t drow = dblk;
+                int64_t o = (((int64_t)b * N + n0) * H + y) * W + x0;
+                for (int q = 0; q < np; ++q, coef_a += (uint32_t)sizeof(PlaneCoef), drow += NE * rowpitch4, o += p.hw) {
+                    const PlaneCoef k = load_coef(coef_a);
                     // with a dense mask the per-pixel mask is already folded into the exchange rows (k.m == 1)
+                    const int at4 = x04 - k.k4 - 4;
                     float gg[PX];
                     if (p.gin.g_logits) {
-                        gather_any<PX>(drow, x0, W, k.k0, k.wc0, k.wc1, gg);
+                        gather_any<PX>(drow, at4, W4, k.wc0, k.wc1, gg);
                         store_px_stream<PX>(p.gin.g_logits + o, gg);
                     }
                     if constexpr (MIX) if (p.gin.g_sigma) {
-                        gather_any<PX>(drow + rowf, x0, W, k.k0, k.wc0, k.wc1, gg);
+                        gather_any<PX>(drow + rowpitch4, at4, W4, k.wc0, k.wc1, gg);
                         store_px_stream<PX>(p.gin.g_sigma + o, gg);
                     }
                 }
