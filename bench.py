@@ -37,6 +37,11 @@ CONFIGS = {
     "cfg2": (12, 192, 640, dict(), "ssim_l1", "cfg2: B=12/GPU 640x192 N=49 stereo disp_warp + SSIM/L1, fwd+bwd"),
     "cfg3": (4, 384, 1280, dict(use_mixture_loss=True, plane_residual=True), None,
              "cfg3: B=4/GPU 1280x384 N=49 disp_warp + plane_residual + Laplacian mixture, fwd+bwd"),
+    # per-GPU shapes of the multi-GPU BASELINE configs (parity / diagnostics; the bench line is cfg2)
+    "cfg4": (12, 192, 640, dict(warp_type="homography_warp", xz_levels=14, novel_frame_ids=[-1, 1], automask=True), None,
+             "cfg4 (per GPU): B=12 640x192 N=49+14 homography_warp, frames [r,-1,1], automask L1, fwd+bwd"),
+    "cfg5": (8, 384, 1280, dict(use_mixture_loss=True, plane_residual=True, xz_levels=14, self_distillation=1.0), None,
+             "cfg5 (per GPU): B=8 1280x384 N=49+14 disp_warp + mixture + mask_novel blend, fwd+bwd"),
     # diagnostics (not BASELINE configs)
     "dbg_mix": (4, 384, 1280, dict(use_mixture_loss=True), None, "debug: mixture only"),
     "dbg_res": (4, 384, 1280, dict(plane_residual=True), None, "debug: residual only"),
@@ -47,11 +52,6 @@ UNIT = "images/s"
 
 
 # --------------------------------------------------------------------------------------------------
-def dist_env():
-    ws = int(os.environ.get("WORLD_SIZE", "1"))
-    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), ws
-
-
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -226,7 +226,9 @@ def time_cpu(cfg_name, B_sample, steps, warmup):
 
 
 def run_reference(args):
-    rank, _, ws = dist_env()
+    from planedepth_b200 import dist as D
+
+    rank, _, ws = D.env()
     if rank != 0:
         return
     B, H, W, over, photometric, desc = CONFIGS[args.config]
@@ -249,11 +251,12 @@ def run_ours(args):
     import torch.distributed as dist
 
     from planedepth_b200 import _lib, functional
+    from planedepth_b200 import dist as D
     from planedepth_b200.boundary import HotPath
     from planedepth_b200.graph import GraphedStep, make_step
     from planedepth_b200.synthetic import make_batch, make_opt
 
-    rank, local_rank, ws = dist_env()
+    rank, local_rank, ws = D.env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
@@ -262,16 +265,20 @@ def run_ours(args):
     lib = _lib.lib()
     B, H, W, over, photometric, desc = CONFIGS[args.config]
     opt = make_opt(**over)
-    batch = make_batch(B, H, W, opt, seed=1234 + rank, device="cpu", layout=args.layout)
+    mnov = opt.self_distillation > 0  # the SD stage hands over outputs["mask_novel"] (trainer.py:404-466)
+    opt.self_distillation = 0.0      # its |disp - disp_pp| term belongs to the decoder tail, not to this path
+    seed = D.shard_seed(1234, rank)
+    batch = make_batch(B, H, W, opt, seed=seed, device="cpu", layout=args.layout, mask_novel=mnov)
     N = batch.shape[1]
     dev = torch.device("cuda", local_rank)
     # static device buffers: network outputs live on the device; the `inputs` dict comes from the host
     host_inputs = {k: v.pin_memory() for k, v in batch.inputs.items()}
-    batch_gpu = make_batch(B, H, W, opt, seed=1234 + rank, device=dev, layout=args.layout)
+    batch_gpu = make_batch(B, H, W, opt, seed=seed, device=dev, layout=args.layout, mask_novel=mnov)
     outputs, leaves_map = batch_gpu.outputs, batch_gpu.leaves
     inputs = batch_gpu.inputs
     leaves = list(leaves_map.values())
-    hp = HotPath(opt, batch.target_sides, pc_net=None, photometric=photometric)
+    # the integration patch promises x-constant disparities whenever the decoder has no yz planes
+    hp = HotPath(opt, batch.target_sides, pc_net=None, photometric=photometric, disp_rowwise=(getattr(opt, "yz_levels", 0) == 0))
     step = make_step(hp, inputs, outputs, leaves, batch_gpu.attach)
     if args.no_graph:
         class _Eager:
@@ -287,9 +294,7 @@ def run_ours(args):
         graphed = GraphedStep(step, warmup=3)
 
     def barrier():
-        if ws > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        D.barrier(ws, cuda=True)
 
     # ---------------- value: inputs resident in HBM, CUDA-graph replay -------------------------
     for _ in range(args.warmup):
@@ -309,23 +314,48 @@ def run_ours(args):
         graphed.replay()
     ev1.record()
     barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if ws > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    ms_step = D.max_over_ranks(ev0.elapsed_time(ev1), ws, dev) / args.steps
     loss_val = float(graphed.result["loss"].item())
 
-    # ---------------- e2e: `inputs` dict from pinned host memory each step ----------------------
+    # ---------------- e2e: the path's host-born inputs from pinned host memory each step ---------
+    # The tensors of the `inputs` dict this path reads (source + target colours; K / inv_K / Rt for the
+    # homography warp) start every step in pinned HOST memory, as they do when they come out of the data loader
+    # (trainer.py:328-329 copies them with .to(device)); logits / sigma / plane geometry are network outputs and are
+    # device-born in the reference too.  The H2D copy of step i+1 runs on a copy stream while step i computes
+    # (one staging set, events both ways); the loss comes back to the host every step.
+    color = "color"
+    read_keys = [(color, "l")] + [(color, sd) for sd in batch.target_sides]
+    if opt.warp_type != "disp_warp":
+        read_keys += ["K", "inv_K"] + [("Rt", sd) for sd in batch.target_sides]
+    read_keys = [k for k in dict.fromkeys(read_keys) if k in host_inputs]
+    host_sel = {k: host_inputs[k] for k in read_keys}
+    staging = {k: torch.empty_like(inputs[k]) for k in read_keys}
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-    h2d = sum(v.numel() * v.element_size() for v in host_inputs.values())
+    h2d = sum(v.numel() * v.element_size() for v in host_sel.values())
+    copy_stream = torch.cuda.Stream()
+    copied, consumed = torch.cuda.Event(), torch.cuda.Event()
+
+    def enqueue_h2d():
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed)
+            for k, v in host_sel.items():
+                staging[k].copy_(v, non_blocking=True)
+            copied.record(copy_stream)
+
+    consumed.record()
+    enqueue_h2d()
 
     def e2e_step():
-        for k, v in host_inputs.items():
-            inputs[k].copy_(v, non_blocking=True)
+        main = torch.cuda.current_stream()
+        main.wait_event(copied)
+        for k in read_keys:
+            inputs[k].copy_(staging[k], non_blocking=True)
+        consumed.record(main)
+        enqueue_h2d()  # next step's inputs travel while this step computes
         res = graphed.replay()
         loss_host.copy_(res["loss"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        main.synchronize()
+        return float(loss_host)
 
     for _ in range(args.warmup):
         e2e_step()
@@ -337,10 +367,8 @@ def run_ours(args):
     ev1.record()
     barrier()
     e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
-    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-    if ws > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms_step = float(t.item()) / args.steps
+    e2e_ms_step = D.max_over_ranks(e2e_ms, ws, dev) / args.steps
+    copy_stream.synchronize()
     clk = clocks.stop() if rank == 0 else None
 
     # ---------------- roofline: per-kernel CUDA events on the launch stream (eager pass) --------
@@ -359,7 +387,8 @@ def run_ours(args):
     functional.KERNEL_TIMELINE = None
     avg_ms = {k: sum(v) / len(v) for k, v in per.items()}
     dom = max(avg_ms, key=avg_ms.get)
-    alg = algorithmic_bytes(B, N, H, W, opt.use_mixture_loss)
+    alg = algorithmic_bytes(B, N, H, W, opt.use_mixture_loss)  # per launch (= per target side)
+    n_calls = {k: len(v) / n_roof for k, v in per.items()}  # launches per step
     peak, peak_src = peaks()
     achieved = alg[dom] / (avg_ms[dom] * 1e-3) / 1e9
     traffic = None
@@ -373,7 +402,8 @@ def run_ours(args):
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": alg[dom], "kernel_ms": avg_ms[dom],
                 "all_kernels_ms": avg_ms,
                 "all_kernels_frac": {k: alg[k] / (avg_ms[k] * 1e-3) / 1e9 / peak for k in avg_ms},
-                "step_frac": sum(alg.values()) / (ms_step * 1e-3) / 1e9 / peak}
+                "launches_per_step": n_calls,
+                "step_frac": sum(alg[k] * n_calls.get(k, 0) for k in alg) / (ms_step * 1e-3) / 1e9 / peak}
 
     if rank != 0:
         if ws > 1:
@@ -383,15 +413,16 @@ def run_ours(args):
     if ws == 1 and not args.no_cpu_baseline:
         cpu, _ = time_cpu(args.config, 2, 2, 1)
     line = {
-        "metric": METRIC, "value": B * ws / (ms_step * 1e-3), "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": D.aggregate_throughput(B, ws, ms_step), "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * ws, "planes": N, "height": H, "width": W,
                    "photometric": photometric or ("mixture" if opt.use_mixture_loss else "l1"), "layout": args.layout,
                    "parallelism": "dp%d (independent shards, no data-path collective)" % ws, "launch": "eager" if args.no_graph else "cuda_graph replay",
                    "l2": "no flush: per-step working set (logits %.0f MB + grads %.0f MB) exceeds the 126 MB L2" % (
                        B * N * H * W * 4 / 1e6, B * N * H * W * 4 / 1e6),
-                   "e2e_scope": "inputs dict pinned-host->device each step (trainer.py:328-329) + loss device->host; network outputs are device-born"},
-        "e2e": {"value": B * ws / (e2e_ms_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                   "e2e_scope": "per step: H2D of the path's host-born inputs (%s) from pinned memory on a copy stream overlapped with the previous step, "
+                                "D2H of the loss; logits/sigma/plane geometry are network outputs (device-born)" % ", ".join(str(k) for k in read_keys)},
+        "e2e": {"value": D.aggregate_throughput(B, ws, e2e_ms_step), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms_step},
         "gpu_launches": int(launches_per_step) * args.steps,
         "gpu_launches_per_step": int(launches_per_step),

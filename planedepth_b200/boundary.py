@@ -46,11 +46,32 @@ def homography_params(distance, norm, T, K, inv_K):
     t = T[:, None, :3, 3:4]
     n = norm.to(torch.float32).reshape(B, N, 1, 3)
     H_s2t = K[:, None, :3, :3] @ ((R + (t @ n) / distance.reshape(B, N, 1, 1)) @ inv_K[:, None, :3, :3])
-    H_t2s = torch.inverse(H_s2t)
+    if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+        H_t2s = inverse3x3(H_s2t)  # LU-based inverses synchronise; see inverse3x3
+    else:
+        H_t2s = torch.inverse(H_s2t)  # the reference's own op (layers.py:220): same LU rounding, same gradients
     Rn = (R @ n.transpose(-1, -2)).reshape(B * N, 3)
     hmat = torch.cat([H_t2s.reshape(B * N, 9), Rn.detach()], 1)
     cam = inv_K[:, :3, :3].reshape(B, 9)
     return hmat, cam
+
+
+def inverse3x3(M):
+    """Batched 3x3 inverse by cofactors (layers.py:220 calls torch.inverse): a few elementwise kernels that
+    CUDA graphs can capture (the LU-based torch.inverse synchronises) and autograd differentiates.  Evaluated in
+    fp64: pixel-unit homographies mix entries of 1e-3 and 1e3 and the cofactor differences cancel badly in fp32
+    (B*N tiny matrices; the cost is nil)."""
+    dt = M.dtype
+    M = M.double()
+    a, b, c = M[..., 0, 0], M[..., 0, 1], M[..., 0, 2]
+    d, e, f = M[..., 1, 0], M[..., 1, 1], M[..., 1, 2]
+    g, h, i = M[..., 2, 0], M[..., 2, 1], M[..., 2, 2]
+    A, Bc, Cc = e * i - f * h, f * g - d * i, d * h - e * g
+    det = a * A + b * Bc + c * Cc
+    adj = torch.stack([A, c * h - b * i, b * f - c * e,
+                       Bc, a * i - c * g, c * d - a * f,
+                       Cc, b * g - a * h, a * e - b * d], -1).reshape(M.shape)
+    return (adj / det[..., None, None]).to(dt)
 
 
 def depth_warp_params(T, K, inv_K):
@@ -58,6 +79,26 @@ def depth_warp_params(T, K, inv_K):
     B = K.shape[0]
     P = (K @ T)[:, :3, :]
     return torch.cat([inv_K[:, :3, :3].reshape(B, 9), P.reshape(B, 12)], 1)
+
+
+class _RowwiseView(torch.autograd.Function):
+    """``x[..., :1].expand_as(x)`` for a tensor whose values do not vary along the last axis, without autograd's
+    zero-filled dense gradient: the backward spreads the x-reduced gradient evenly (as a stride-0 view), which
+    sums to the same total through whatever x-constant construction produced ``x``."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.w = x.shape[3]
+        return x[..., :1].expand(-1, -1, -1, ctx.w)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g.sum(3, keepdim=True) / ctx.w).expand(-1, -1, -1, ctx.w)
+
+
+def rowwise_view(disp):
+    """Zero-x-stride alias of a dense but x-constant ``disp_layered`` (see HotPathMixin.disp_rowwise)."""
+    return _RowwiseView.apply(disp)
 
 
 class HotPathMixin:
@@ -69,6 +110,13 @@ class HotPathMixin:
     #: reproduce the fp32 rounding of the reference's coordinate normalise / un-normalise round trip bit for bit
     #: (PD_FLAG_EXACT_COORDS); the default stereo fast path samples at the exact positions instead
     exact_coords: bool = False
+    #: Promise that ``outputs["disp_layered"]`` does not vary along x even though it is stored densely.  PlaneDepth's
+    #: DepthDecoder emits one disparity per (image, plane) for vertical planes and one per row for xz ground planes
+    #: (depth_decoder.py:153-183) but hands the 49+14 set over as a dense [B,N,H,W] ``cat``; only yz planes
+    #: (--yz_levels > 0, :209-236) vary with x.  An integrator sets this to ``opt.yz_levels == 0``;
+    #: the stereo fast path then reads column 0 only.  Left False, x-constancy is only used when the strides prove it
+    #: (the stride-0 expand of depth_decoder.py:156), and dense tensors take the per-pixel kernels.
+    disp_rowwise: bool = False
     #: photometric term: None = reference behaviour (mixture NLL if opt.use_mixture_loss else L1);
     #: "ssim_l1" = 0.85*SSIM + 0.15*L1 (compute_reprojection_loss, trainer.py:687-699) on the novel view
     photometric: Optional[str] = None
@@ -93,6 +141,8 @@ class HotPathMixin:
                 disp = outputs["disp_layered"]
                 mask = outputs["padding_mask"]
                 sign = 1.0 if side == "r" else (-1.0 if side == "l" else 0.0)
+                if self.disp_rowwise and disp.dim() == 4 and disp.stride(3) != 0 and disp.shape[3] > 1:
+                    disp = rowwise_view(disp)
             elif wt == "homography_warp":
                 hmat, cam = homography_params(outputs["distance"], outputs["norm"], outputs[("Rt", side)], inputs["K"], inputs["inv_K"])
             else:
@@ -190,7 +240,7 @@ class HotPath(HotPathMixin):
     and smoke() instantiate instead of the full Trainer, whose constructor needs NCCL + KITTI)."""
 
     def __init__(self, opt, target_sides=None, pc_net=None, photometric: Optional[str] = None, materialize_layered: bool = False,
-                 exact_coords: bool = False):
+                 exact_coords: bool = False, disp_rowwise: bool = False):
         self.opt = opt
         if target_sides is None:
             target_sides = ([] if _flag(opt, "no_stereo", False) else ["r"]) + list(_flag(opt, "novel_frame_ids", []))
@@ -199,6 +249,7 @@ class HotPath(HotPathMixin):
         self.photometric = photometric
         self.materialize_layered = materialize_layered
         self.exact_coords = exact_coords
+        self.disp_rowwise = disp_rowwise
 
     def process(self, inputs, outputs):
         self.pred_novel_images(inputs, outputs)

@@ -154,9 +154,16 @@ class _WarpComposite(torch.autograd.Function):
         g_sigma = torch.empty_like(sigma) if (cfg.mixture and sigma is not None and need[4]) else None
         g_disp = g_hmat = None
         gin = L.WarpGradIn(g_logits=_ptr(g_logits), g_sigma=_ptr(g_sigma))
+        spread = 1
         if disp is not None and need[5]:
-            # same (possibly compact) shape as the input; size-1 dims are reduced inside the kernel
-            g_disp = torch.empty(disp.shape, device=dev, dtype=torch.float32)
+            # broadcast dimensions of the input (size 1 or stride 0) are reduced inside the kernel: the buffer is
+            # compact there, and the result is handed back spread evenly over the broadcast extent (a stride-0
+            # view), so that autograd's expand-backward sums it to the reduced value again
+            shape = [1 if (disp.size(i) == 1 or disp.stride(i) == 0) else disp.size(i) for i in range(4)]
+            for i in range(4):
+                if shape[i] == 1:
+                    spread *= disp.size(i)
+            g_disp = torch.empty(shape, device=dev, dtype=torch.float32)
             gin.g_disp = g_disp.data_ptr()
             gin.g_disp_stride = _strides4(g_disp)
         if hmat is not None and need[7]:
@@ -166,6 +173,8 @@ class _WarpComposite(torch.autograd.Function):
               C.byref(gin), None, _stream())
         if hmat is not None and need[7]:
             g_hmat = torch.cat([g9, torch.zeros(B * N, 3, device=dev)], 1)
+        if g_disp is not None and tuple(g_disp.shape) != tuple(disp.shape):
+            g_disp = (g_disp / spread if spread > 1 else g_disp).expand(disp.shape)
         return (None, None, None, g_logits, g_sigma, g_disp, None, g_hmat, None)
 
 

@@ -94,10 +94,18 @@ def make_batch(B: int, H: int, W: int, opt, seed: int = 0, device="cpu", layout:
         if opt.plane_residual and requires_grad:
             h.requires_grad_(True)
             leaves["xz_h"] = h
-        xz_mask = (gy >= 1e-7).expand(-1, n_xz, -1, -1)
-        Z = h.detach().expand(-1, -1, H, W) * 1.92 / (gy.clamp_min(1e-7) / 2.0)
-        disp_layered = torch.cat([disp_layered, 0.1 * 0.58 * W / Z], 1)
-        padding_mask = torch.cat([padding_mask, xz_mask], 1)
+        if layout == "compact":
+            # one value per (image, plane, row), expanded along x with a zero stride
+            gyc = gy[..., :1]
+            xz_mask = (gyc >= 1e-7).expand(-1, n_xz, -1, -1).float()
+            Z = h.detach().expand(-1, -1, H, 1) * 1.92 / (gyc.clamp_min(1e-7) / 2.0)
+            disp_layered = torch.cat([based.expand(-1, -1, H, 1), 0.1 * 0.58 * W / Z], 1).expand(-1, -1, -1, W)
+            padding_mask = torch.cat([ones.expand(-1, -1, H, 1), xz_mask], 1).expand(-1, -1, -1, W)
+        else:
+            xz_mask = (gy >= 1e-7).expand(-1, n_xz, -1, -1)
+            Z = h.detach().expand(-1, -1, H, W) * 1.92 / (gy.clamp_min(1e-7) / 2.0)
+            disp_layered = torch.cat([disp_layered, 0.1 * 0.58 * W / Z], 1)
+            padding_mask = torch.cat([padding_mask, xz_mask], 1)
         norm = torch.cat([norm, torch.tensor([0.0, 1.0, 0.0], device=dev)[None, None].expand(B, n_xz, 3)], 1)
         distance = torch.cat([distance, h.detach()[:, :, 0, 0]], 1)
     logits = (torch.randn(B, N, H, W, generator=g).to(dev) * padding_mask).contiguous()
@@ -128,8 +136,13 @@ def make_batch(B: int, H: int, W: int, opt, seed: int = 0, device="cpu", layout:
         dist = 0.1 * 0.58 * W / b[:, :, 0, 0]
         if n_xz:
             hh = leaves["xz_h"]
-            Zg = hh.expand(-1, -1, H, W) * 1.92 / (inputs["grid"][:, 1:, :, :].clamp_min(1e-7) / 2.0)
-            dl = torch.cat([dl, 0.1 * 0.58 * W / Zg], 1)
+            if layout == "compact":
+                gyc = inputs["grid"][:, 1:, :, :1]
+                Zg = hh.expand(-1, -1, H, 1) * 1.92 / (gyc.clamp_min(1e-7) / 2.0)
+                dl = torch.cat([b.expand(-1, -1, H, 1), 0.1 * 0.58 * W / Zg], 1).expand(-1, -1, -1, W)
+            else:
+                Zg = hh.expand(-1, -1, H, W) * 1.92 / (inputs["grid"][:, 1:, :, :].clamp_min(1e-7) / 2.0)
+                dl = torch.cat([dl, 0.1 * 0.58 * W / Zg], 1)
             dist = torch.cat([dist, hh[:, :, 0, 0]], 1)
         out["disp_layered"], out["distance"] = dl, dist
         return out

@@ -42,12 +42,12 @@ MODES = ["layered", "fused", "fused_exact"]
 # fused_exact: PD_FLAG_EXACT_COORDS -> row-tiled kernels that reproduce the fp32 coordinate round trip bit for bit
 
 
-def run_cuda(c, photometric=None, mode="layered"):
+def run_cuda(c, photometric=None, mode="layered", rowwise=False):
     from planedepth_b200.boundary import HotPath
 
     layered = mode == "layered"
     hp = HotPath(c.opt, c.target_sides, pc_net=pyramid_features, photometric=photometric, materialize_layered=layered,
-                 exact_coords=(mode == "fused_exact"))
+                 exact_coords=(mode == "fused_exact"), disp_rowwise=rowwise)
     losses = hp.process(c.inputs, c.outputs)
     losses["loss/total_loss"].backward()
     return losses
@@ -227,6 +227,31 @@ def test_cuda_matches_oracle(idx, photometric, mode):
         assert gg is not None, "no CUDA gradient for %s" % k
         scale = float(leaf.grad.abs().max()) + 1e-12
         check(gg, leaf.grad, grad_tol(k) * scale, "grad_" + k, allow_frac=2e-3)
+
+
+@pytest.mark.parametrize("mode", ["fused", "fused_exact"])
+@pytest.mark.parametrize("idx", [2, 8, 11])
+def test_rowwise_promise_on_dense_cat_layout(idx, mode):
+    """49+14-style plane sets arrive as a dense [B,N,H,W] cat (depth_decoder.py:181): with the integrator's
+    promise ``disp_rowwise`` the fast path reads column 0 and hands the gradient back spread over x."""
+    from planedepth_b200 import _lib
+
+    cfg = CONFIGS[idx]
+    assert cfg[9].get("n_xz") and not cfg[9].get("dense")
+    cc = build_on("cpu", cfg, seed=300 + idx)
+    cg = build_on("cuda", cfg, seed=300 + idx)
+    assert cg.outputs["disp_layered"].stride(3) == 1
+    lo = O.hot_path(cc.opt, cc.target_sides, cc.inputs, cc.outputs, pyramid_features)
+    lo["loss/total_loss"].backward()
+    lg = run_cuda(cg, None, mode, rowwise=True)
+    check(cg.outputs[("rgb_rec", "r")], cc.outputs[("rgb_rec", "r")], TOL, "rgb_rec", allow_frac=2e-4)
+    for k in lo:
+        check(lg[k], lo[k], TOL, k)
+    for k, leaf in cc.leaves.items():
+        if leaf.grad is None:
+            continue
+        scale = float(leaf.grad.abs().max()) + 1e-12
+        check(cg.leaves[k].grad, leaf.grad, grad_tol(k) * scale, "grad_" + k, allow_frac=2e-3)
 
 
 def test_properties_at_full_size():
