@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PD_ABI_VERSION 2
+#define PD_ABI_VERSION 3
 
 typedef void* pd_stream_t; /* a cudaStream_t */
 
@@ -174,6 +174,10 @@ typedef struct pd_loss_out {
     float* pred;   /* [B,3,H,W] blended prediction; required iff has_mask_novel (else pred == rgb_rec) */
     float* ph_map; /* [B,1,H,W] optional per-pixel photometric term (NULL = skip) */
     float* ph_sum; /* [1] */
+    /* Unit gradients, produced by the forward pass while its tiles are on chip and consumed by
+     * pd_photometric_bwd (NULL = the caller will not differentiate): */
+    float* g_unit;     /* [B,3,H,W] d ph_sum / d rgb_rec        (L1, SSIM_L1) */
+    float* g_unit_nll; /* [B,1,H,W] d ph_sum / d nll            (MIXTURE)     */
 } pd_loss_out;
 
 typedef struct pd_loss_grad_out {
@@ -189,8 +193,10 @@ typedef struct pd_loss_grad_in {
 size_t pd_photometric_workspace_bytes(const pd_loss_desc* desc);
 int pd_photometric_fwd(const pd_loss_desc* desc, const pd_loss_in* in, pd_loss_out* out, void* workspace,
                        pd_stream_t stream);
-int pd_photometric_bwd(const pd_loss_desc* desc, const pd_loss_in* in, const pd_loss_grad_out* gout,
-                       pd_loss_grad_in* gin, void* workspace, pd_stream_t stream);
+/* g_rgb_rec = g_ph_sum * saved->g_unit + g_pred * mask_novel ; g_nll = g_ph_sum * saved->g_unit_nll.
+ * Only in->mask_novel is read from `in` (iff has_mask_novel). */
+int pd_photometric_bwd(const pd_loss_desc* desc, const pd_loss_in* in, const pd_loss_out* saved,
+                       const pd_loss_grad_out* gout, pd_loss_grad_in* gin, void* workspace, pd_stream_t stream);
 
 /* Introspection for tests / bench: number of kernels the library has launched in this process since
  * the last pd_reset_launch_count() (bench.py reports it as gpu_launches). */

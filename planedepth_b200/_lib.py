@@ -23,7 +23,7 @@ PD_WARP_DISP, PD_WARP_HOMOGRAPHY, PD_WARP_DEPTH = 0, 1, 2
 PD_LOSS_L1, PD_LOSS_MIXTURE, PD_LOSS_SSIM_L1 = 0, 1, 2
 PD_MASK_NONE, PD_MASK_F32, PD_MASK_U8 = 0, 1, 2
 PD_FLAG_EXACT_COORDS = 1
-ABI_VERSION = 2  # PD_ABI_VERSION in include/planedepth_b200.h
+ABI_VERSION = 3  # PD_ABI_VERSION in include/planedepth_b200.h
 PD_STATS_PLAIN, PD_STATS_MIXTURE = 2, 4
 
 EXPORTS = [
@@ -74,7 +74,7 @@ class LossIn(C.Structure):
 
 
 class LossOut(C.Structure):
-    _fields_ = [(k, C.c_void_p) for k in ("pred", "ph_map", "ph_sum")]
+    _fields_ = [(k, C.c_void_p) for k in ("pred", "ph_map", "ph_sum", "g_unit", "g_unit_nll")]
 
 
 class LossGradOut(C.Structure):
@@ -149,7 +149,7 @@ def lib() -> C.CDLL:
     L.pd_photometric_fwd.restype = C.c_int
     L.pd_photometric_fwd.argtypes = [C.POINTER(LossDesc), C.POINTER(LossIn), C.POINTER(LossOut), C.c_void_p, C.c_void_p]
     L.pd_photometric_bwd.restype = C.c_int
-    L.pd_photometric_bwd.argtypes = [C.POINTER(LossDesc), C.POINTER(LossIn), C.POINTER(LossGradOut), C.POINTER(LossGradIn),
+    L.pd_photometric_bwd.argtypes = [C.POINTER(LossDesc), C.POINTER(LossIn), C.POINTER(LossOut), C.POINTER(LossGradOut), C.POINTER(LossGradIn),
                                      C.c_void_p, C.c_void_p]
     L.pd_debug_roundtrip.restype = C.c_int
     L.pd_debug_roundtrip.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]

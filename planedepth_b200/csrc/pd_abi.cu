@@ -6,6 +6,8 @@
 #include <string.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
 
 #include "pd_loss.cuh"
 #include "pd_warp_general.cuh"
@@ -105,12 +107,25 @@ dim3 loss_grid(const pd_loss_desc* d) {
     return dim3((d->W + pd::LT_W - 1) / pd::LT_W, (d->H + pd::LT_H - 1) / pd::LT_H, d->B);
 }
 
+// persistent grid of the elementwise kernels
+unsigned ew_grid(int64_t work_items) {
+    const int64_t want = (work_items + pd::EW_THREADS - 1) / pd::EW_THREADS;
+    const int64_t cap = 148 * 8;
+    return (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
 int validate_loss(const pd_loss_desc* d, const pd_loss_in* in) {
     if (!d || !in) return fail(PD_ERR_ARG, "NULL descriptor");
     if (d->B < 1 || d->H < 2 || d->W < 2 || d->B > 65535) return fail(PD_ERR_SHAPE, "1 <= B <= 65535 and H,W >= 2 required");
     if (d->loss_mode < PD_LOSS_L1 || d->loss_mode > PD_LOSS_SSIM_L1) return fail(PD_ERR_ARG, "bad loss_mode %d", d->loss_mode);
-    if (!in->rgb_rec || !in->tgt) return fail(PD_ERR_ARG, "rgb_rec / tgt must not be NULL");
     if (d->has_mask_novel && !in->mask_novel) return fail(PD_ERR_ARG, "has_mask_novel set but mask_novel is NULL");
+    return PD_OK;
+}
+
+int validate_loss_fwd(const pd_loss_desc* d, const pd_loss_in* in) {
+    int rc = validate_loss(d, in);
+    if (rc) return rc;
+    if (!in->rgb_rec || !in->tgt) return fail(PD_ERR_ARG, "rgb_rec / tgt must not be NULL");
     if (d->loss_mode == PD_LOSS_MIXTURE) {
         if (!in->nll || (d->automask && !in->nll_auto)) return fail(PD_ERR_ARG, "mixture loss needs nll (and nll_auto with automask)");
     } else if (d->automask && !in->src) {
@@ -119,20 +134,32 @@ int validate_loss(const pd_loss_desc* d, const pd_loss_in* in) {
     return PD_OK;
 }
 
-template <int MODE, typename F>
-void dispatch_flags(bool automask, bool hasmask, F&& f) {
-    if (automask) { if (hasmask) f.template operator()<MODE, true, true>(); else f.template operator()<MODE, true, false>(); }
-    else          { if (hasmask) f.template operator()<MODE, false, true>(); else f.template operator()<MODE, false, false>(); }
+template <typename K>
+void loss_smem_optin(K kern, size_t smem) {
+    static std::mutex mu;
+    static std::map<const void*, size_t> granted;
+    if (smem <= 48 * 1024) return;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& g = granted[(const void*)kern];
+    if (smem > g) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        g = smem;
+    }
 }
 
-struct FwdLaunch {
-    pd::LossParams p; dim3 g; cudaStream_t st;
-    template <int MODE, bool A, bool M> void operator()() { pd::photometric_fwd_kernel<MODE, A, M><<<g, pd::LT_THREADS, 0, st>>>(p); }
-};
-struct BwdLaunch {
-    pd::LossParams p; dim3 g; cudaStream_t st;
-    template <int MODE, bool A, bool M> void operator()() { pd::photometric_bwd_kernel<MODE, A, M><<<g, pd::LT_THREADS, 0, st>>>(p); }
-};
+template <bool AUTO, bool HASMASK, bool WANT_G>
+void launch_ssim(const pd::LossParams& p, dim3 g, cudaStream_t st) {
+    const size_t smem = pd::ssim_smem_bytes(AUTO, WANT_G);
+    auto kern = pd::ssim_l1_fwd_kernel<AUTO, HASMASK, WANT_G>;
+    loss_smem_optin(kern, smem);
+    kern<<<g, pd::LT_THREADS, smem, st>>>(p);
+}
+
+template <int MODE, bool AUTO, bool HASMASK>
+void launch_ew(const pd::LossParams& p, unsigned g, bool want_g, cudaStream_t st) {
+    if (want_g) pd::elementwise_fwd_kernel<MODE, AUTO, HASMASK, true><<<g, pd::EW_THREADS, 0, st>>>(p);
+    else pd::elementwise_fwd_kernel<MODE, AUTO, HASMASK, false><<<g, pd::EW_THREADS, 0, st>>>(p);
+}
 
 __global__ void debug_roundtrip_kernel(const float* __restrict__ u, int64_t n, float size_m1, float rcp, float* __restrict__ exact, float* __restrict__ fast) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -242,47 +269,77 @@ int pd_debug_roundtrip(const float* u, int64_t n, int32_t size, float* out_exact
 size_t pd_photometric_workspace_bytes(const pd_loss_desc* d) {
     if (!d) return 0;
     dim3 g = loss_grid(d);
-    return (size_t)g.x * g.y * g.z * sizeof(float);
+    const size_t tiles = (size_t)g.x * g.y * g.z, ew = 148 * 8;
+    return (tiles > ew ? tiles : ew) * sizeof(float);
 }
 
 int pd_photometric_fwd(const pd_loss_desc* d, const pd_loss_in* in, pd_loss_out* out, void* workspace, pd_stream_t stream) {
-    int rc = validate_loss(d, in);
+    int rc = validate_loss_fwd(d, in);
     if (rc) return rc;
     if (!out || !out->ph_sum) return fail(PD_ERR_ARG, "ph_sum must not be NULL");
     if (d->has_mask_novel && !out->pred) return fail(PD_ERR_ARG, "has_mask_novel needs the pred output");
     if (!workspace) return fail(PD_ERR_WORKSPACE, "workspace of pd_photometric_workspace_bytes() required");
     if ((rc = check_device())) return rc;
-    FwdLaunch L;
-    memset(&L.p, 0, sizeof(L.p));
-    L.p.d = *d; L.p.in = *in; L.p.out = *out; L.p.partials = (float*)workspace; L.p.hw = (int64_t)d->H * d->W;
-    L.g = loss_grid(d); L.st = (cudaStream_t)stream;
-    switch (d->loss_mode) {
-        case PD_LOSS_L1: dispatch_flags<PD_LOSS_L1>(d->automask, d->has_mask_novel, L); break;
-        case PD_LOSS_MIXTURE: dispatch_flags<PD_LOSS_MIXTURE>(d->automask, d->has_mask_novel, L); break;
-        default: dispatch_flags<PD_LOSS_SSIM_L1>(d->automask, d->has_mask_novel, L); break;
+    cudaStream_t st = (cudaStream_t)stream;
+    pd::LossParams p;
+    memset(&p, 0, sizeof(p));
+    p.d = *d; p.in = *in; p.out = *out; p.partials = (float*)workspace; p.hw = (int64_t)d->H * d->W;
+    const bool a = d->automask != 0, m = d->has_mask_novel != 0;
+    int64_t nparts;
+    if (d->loss_mode == PD_LOSS_SSIM_L1) {
+        const bool wg = out->g_unit != nullptr;
+        const dim3 g = loss_grid(d);
+        nparts = (int64_t)g.x * g.y * g.z;
+        if (a) { if (m) { wg ? launch_ssim<true, true, true>(p, g, st) : launch_ssim<true, true, false>(p, g, st); }
+                 else   { wg ? launch_ssim<true, false, true>(p, g, st) : launch_ssim<true, false, false>(p, g, st); } }
+        else   { if (m) { wg ? launch_ssim<false, true, true>(p, g, st) : launch_ssim<false, true, false>(p, g, st); }
+                 else   { wg ? launch_ssim<false, false, true>(p, g, st) : launch_ssim<false, false, false>(p, g, st); } }
+    } else {
+        const unsigned g = ew_grid((int64_t)d->B * p.hw);
+        nparts = g;
+        if (d->loss_mode == PD_LOSS_MIXTURE) {
+            const bool wg = out->g_unit_nll != nullptr;
+            if (a) { m ? launch_ew<PD_LOSS_MIXTURE, true, true>(p, g, wg, st) : launch_ew<PD_LOSS_MIXTURE, true, false>(p, g, wg, st); }
+            else   { m ? launch_ew<PD_LOSS_MIXTURE, false, true>(p, g, wg, st) : launch_ew<PD_LOSS_MIXTURE, false, false>(p, g, wg, st); }
+        } else {
+            const bool wg = out->g_unit != nullptr;
+            if (a) { m ? launch_ew<PD_LOSS_L1, true, true>(p, g, wg, st) : launch_ew<PD_LOSS_L1, true, false>(p, g, wg, st); }
+            else   { m ? launch_ew<PD_LOSS_L1, false, true>(p, g, wg, st) : launch_ew<PD_LOSS_L1, false, false>(p, g, wg, st); }
+        }
     }
     if ((rc = check_launch("photometric_fwd"))) return rc;
-    pd::reduce_partials_kernel<<<1, 1024, 0, L.st>>>(L.p.partials, (int64_t)L.g.x * L.g.y * L.g.z, out->ph_sum);
+    pd::reduce_partials_kernel<<<1, 1024, 0, st>>>(p.partials, nparts, out->ph_sum);
     return check_launch("reduce_partials");
 }
 
-int pd_photometric_bwd(const pd_loss_desc* d, const pd_loss_in* in, const pd_loss_grad_out* gout, pd_loss_grad_in* gin, void* workspace,
-                       pd_stream_t stream) {
+int pd_photometric_bwd(const pd_loss_desc* d, const pd_loss_in* in, const pd_loss_out* saved, const pd_loss_grad_out* gout,
+                       pd_loss_grad_in* gin, void* workspace, pd_stream_t stream) {
     (void)workspace;
     int rc = validate_loss(d, in);
     if (rc) return rc;
     if (!gout || !gout->g_ph_sum) return fail(PD_ERR_ARG, "g_ph_sum must not be NULL");
     if (!gin || !gin->g_rgb_rec) return fail(PD_ERR_ARG, "g_rgb_rec must not be NULL");
-    if (d->loss_mode == PD_LOSS_MIXTURE && !gin->g_nll) return fail(PD_ERR_ARG, "mixture loss needs g_nll");
+    const bool mix = d->loss_mode == PD_LOSS_MIXTURE;
+    if (!saved || (mix ? !saved->g_unit_nll : !saved->g_unit)) return fail(PD_ERR_ARG, "the unit gradient saved by pd_photometric_fwd is required");
+    if (mix && !gin->g_nll) return fail(PD_ERR_ARG, "mixture loss needs g_nll");
     if ((rc = check_device())) return rc;
-    BwdLaunch L;
-    memset(&L.p, 0, sizeof(L.p));
-    L.p.d = *d; L.p.in = *in; L.p.gout = *gout; L.p.gin = *gin; L.p.hw = (int64_t)d->H * d->W;
-    L.g = loss_grid(d); L.st = (cudaStream_t)stream;
-    switch (d->loss_mode) {
-        case PD_LOSS_L1: dispatch_flags<PD_LOSS_L1>(d->automask, d->has_mask_novel, L); break;
-        case PD_LOSS_MIXTURE: dispatch_flags<PD_LOSS_MIXTURE>(d->automask, d->has_mask_novel, L); break;
-        default: dispatch_flags<PD_LOSS_SSIM_L1>(d->automask, d->has_mask_novel, L); break;
+    cudaStream_t st = (cudaStream_t)stream;
+    pd::LossParams p;
+    memset(&p, 0, sizeof(p));
+    p.d = *d; p.in = *in; p.out = *saved; p.gout = *gout; p.gin = *gin; p.hw = (int64_t)d->H * d->W;
+    const bool m = d->has_mask_novel != 0;
+    const void* ptrs[] = {in->mask_novel, saved->g_unit, saved->g_unit_nll, gout->g_pred, gin->g_rgb_rec, gin->g_nll};
+    bool v4 = (p.hw % 4 == 0);
+    for (const void* q : ptrs) v4 = v4 && (!q || (reinterpret_cast<uintptr_t>(q) & 15) == 0);
+    if (v4) {
+        p.total4 = (int64_t)d->B * p.hw / 4;
+        const unsigned g = ew_grid(p.total4);
+        if (mix) { m ? pd::photometric_bwd_kernel_v4<true, true><<<g, pd::EW_THREADS, 0, st>>>(p) : pd::photometric_bwd_kernel_v4<true, false><<<g, pd::EW_THREADS, 0, st>>>(p); }
+        else     { m ? pd::photometric_bwd_kernel_v4<false, true><<<g, pd::EW_THREADS, 0, st>>>(p) : pd::photometric_bwd_kernel_v4<false, false><<<g, pd::EW_THREADS, 0, st>>>(p); }
+    } else {
+        const unsigned g = ew_grid((int64_t)d->B * p.hw);
+        if (mix) { m ? pd::photometric_bwd_kernel<true, true><<<g, pd::EW_THREADS, 0, st>>>(p) : pd::photometric_bwd_kernel<true, false><<<g, pd::EW_THREADS, 0, st>>>(p); }
+        else     { m ? pd::photometric_bwd_kernel<false, true><<<g, pd::EW_THREADS, 0, st>>>(p) : pd::photometric_bwd_kernel<false, false><<<g, pd::EW_THREADS, 0, st>>>(p); }
     }
     return check_launch("photometric_bwd");
 }

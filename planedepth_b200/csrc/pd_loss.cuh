@@ -1,12 +1,25 @@
 // Photometric term of Trainer.compute_losses for one target side (trainer.py:720-742), plus the
 // 0.85*SSIM + 0.15*L1 mode of compute_reprojection_loss (trainer.py:687-699, layers.py:276-306).
-// One 32x8 pixel tile per CTA; SSIM windows are evaluated from a reflect-padded shared-memory tile.
+//
+// The forward kernels produce, next to the loss sum, the UNIT gradient d(ph_sum)/d(rgb_rec) (and
+// d(ph_sum)/d(nll) in mixture mode) while the tiles they need are still in shared memory; the backward
+// is then a pure streaming pass  g_rgb_rec = g_ph_sum * unit + g_pred * m  (autograd replays the
+// pads / pools / clamps of layers.py:292-306 instead).
+//
+// SSIM mode: one 8x64-pixel tile per CTA; stage 1 loads the reflect-padded (tile+2) values of pred /
+// target (/ source for the automask) into shared memory, stage 2 evaluates the 3x3 window statistics of
+// the (tile+1) window centres and turns each into the three coefficients of its derivative
+//   d ssim_term(centre) / d pred(cell) = A + B * pred(cell) + C * tgt(cell)
+// (already gated by the automask min and scaled by 0.85/3), stage 3 gathers the 9 centres around every
+// tile pixel with the reflect-padding multiplicities.
 #pragma once
 #include "pd_device.cuh"
 
 namespace pd {
 
-constexpr int LT_W = 32, LT_H = 8, LT_THREADS = LT_W * LT_H;
+constexpr int LT_W = 64, LT_H = 8, LT_THREADS = 256;
+constexpr int LT_PW = LT_W + 4, LT_PH = LT_H + 4;  // padded values: tile + 2 on every side
+constexpr int LT_CW = LT_W + 2, LT_CH = LT_H + 2;  // window centres: tile + 1 on every side
 constexpr float kC1 = 0.01f * 0.01f, kC2 = 0.03f * 0.03f;  // layers.py:289-290
 
 struct LossParams {
@@ -15,8 +28,9 @@ struct LossParams {
     pd_loss_out out;
     pd_loss_grad_out gout;
     pd_loss_grad_in gin;
-    float* partials;  // [gridDim.x*gridDim.y*gridDim.z]
+    float* partials;  // [number of CTAs]
     int64_t hw;
+    int64_t total4;   // elementwise kernels: number of 4-pixel groups (0 = scalar tail handling only)
 };
 
 __device__ __forceinline__ int reflect(int i, int n) {  // nn.ReflectionPad2d(1) index map
@@ -69,176 +83,102 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return t;  // valid in thread 0
 }
 
-// Loads the (LT_H+2*HALO) x (LT_W+2*HALO) reflect-padded tiles of pred / tgt / src for one channel set.
-template <int HALO, bool NEED_SRC, bool HASMASK>
-__device__ __forceinline__ void load_tiles(const LossParams& p, int b, int ty0, int tx0, float* sP, float* sT, float* sS) {
-    constexpr int PW = LT_W + 2 * HALO, PH = LT_H + 2 * HALO;
-    const int H = p.d.H, W = p.d.W;
-    for (int i = threadIdx.x; i < PW * PH; i += LT_THREADS) {
-        int ly = i / PW, lx = i - ly * PW;
-        // padded coordinate -> image coordinate; clamp first so far-outside halo cells stay addressable
-        int gy = reflect(min(max(ty0 + ly - HALO, -1), H), H);
-        int gx = reflect(min(max(tx0 + lx - HALO, -1), W), W);
-        gy = min(max(gy, 0), H - 1);
-        gx = min(max(gx, 0), W - 1);
-        int64_t o = (int64_t)gy * W + gx;
-        float m = HASMASK ? __ldg(p.in.mask_novel + (int64_t)b * p.hw + o) : 1.0f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            int64_t oc = ((int64_t)b * 3 + c) * p.hw + o;
-            float t = __ldg(p.in.tgt + oc), r = __ldg(p.in.rgb_rec + oc);
-            sT[c * PW * PH + i] = t;
-            sP[c * PW * PH + i] = HASMASK ? blend_pred(r, t, m) : r;
-            if (NEED_SRC) sS[c * PW * PH + i] = __ldg(p.in.src + oc);
-        }
-    }
-}
+__device__ __forceinline__ float sgnf(float d) { return (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f); }
 
 // ------------------------------------------------------------------------------------------------
-// forward
+// SSIM + L1 forward (with unit gradient)
 // ------------------------------------------------------------------------------------------------
-template <int MODE, bool AUTO, bool HASMASK>
-__global__ void __launch_bounds__(LT_THREADS) photometric_fwd_kernel(const LossParams p) {
-    constexpr bool SSIM = (MODE == PD_LOSS_SSIM_L1);
-    constexpr int PW = LT_W + 2, PH = LT_H + 2;
-    __shared__ float sP[SSIM ? 3 * PW * PH : 1], sT[SSIM ? 3 * PW * PH : 1], sS[(SSIM && AUTO) ? 3 * PW * PH : 1];
+inline size_t ssim_smem_bytes(bool automask, bool want_g) {
+    return sizeof(float) * ((size_t)(automask ? 9 : 6) * LT_PW * LT_PH + (want_g ? (size_t)10 * LT_CW * LT_CH : 0));
+}
+
+template <bool AUTO, bool HASMASK, bool WANT_G>
+__global__ void __launch_bounds__(LT_THREADS) ssim_l1_fwd_kernel(const LossParams p) {
+    constexpr int PW = LT_PW, PH = LT_PH, CW = LT_CW, CH = LT_CH;
+    extern __shared__ __align__(16) float lsm[];  // ssim_smem_bytes(AUTO, WANT_G)
+    float* sP = lsm;
+    float* sT = sP + 3 * PW * PH;
+    float* sS = sT + 3 * PW * PH;
+    float* cA = sS + (AUTO ? 3 * PW * PH : 0);
+    float* cB = cA + (WANT_G ? 3 * CW * CH : 0);
+    float* cC = cB + (WANT_G ? 3 * CW * CH : 0);
+    float* gate = cC + (WANT_G ? 3 * CW * CH : 0);
     __shared__ float red[LT_THREADS / 32];
     const int H = p.d.H, W = p.d.W;
     const int b = blockIdx.z, ty0 = blockIdx.y * LT_H, tx0 = blockIdx.x * LT_W;
-    const int ly = threadIdx.x / LT_W, lx = threadIdx.x % LT_W;
-    const int y = ty0 + ly, x = tx0 + lx;
-    const bool live = (y < H) && (x < W);
-    if (SSIM) {
-        load_tiles<1, AUTO, HASMASK>(p, b, ty0, tx0, sP, sT, sS);
-        __syncthreads();
-    }
-    float ph = 0.0f;
-    if (live) {
-        const int64_t o = (int64_t)y * W + x;
+    const float k3 = 1.0f / 3.0f;
+
+    // ---- stage 1: reflect-padded tiles (padded coordinate -> image coordinate; cells further than one pixel outside
+    // the image are never read by a centre inside it, they only need to stay addressable)
+    for (int i = threadIdx.x; i < PW * PH; i += LT_THREADS) {
+        const int ly = i / PW, lx = i - ly * PW;
+        int gy = reflect(min(max(ty0 + ly - 2, -1), H), H);
+        int gx = reflect(min(max(tx0 + lx - 2, -1), W), W);
+        gy = min(max(gy, 0), H - 1);
+        gx = min(max(gx, 0), W - 1);
+        const int64_t o = (int64_t)gy * W + gx;
         const float m = HASMASK ? __ldg(p.in.mask_novel + (int64_t)b * p.hw + o) : 1.0f;
-        if (MODE == PD_LOSS_MIXTURE) {
-            ph = __ldg(p.in.nll + (int64_t)b * p.hw + o);
-            if (AUTO) ph = fminf(ph, __ldg(p.in.nll_auto + (int64_t)b * p.hw + o));
-            if (HASMASK) ph *= m;
-            if (HASMASK) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    int64_t oc = ((int64_t)b * 3 + c) * p.hw + o;
-                    p.out.pred[oc] = blend_pred(__ldg(p.in.rgb_rec + oc), __ldg(p.in.tgt + oc), m);
-                }
-            }
-        } else {
+        for (int c = 0; c < 3; ++c) {
+            const int64_t oc = ((int64_t)b * 3 + c) * p.hw + o;
+            const float t = __ldg(p.in.tgt + oc), r = __ldg(p.in.rgb_rec + oc);
+            sT[c * PW * PH + i] = t;
+            sP[c * PW * PH + i] = HASMASK ? blend_pred(r, t, m) : r;
+            if (AUTO) sS[c * PW * PH + i] = __ldg(p.in.src + oc);
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 2: window centres of the tile and of the ring around it
+    float ph_acc = 0.0f;
+    for (int i = threadIdx.x; i < CW * CH; i += LT_THREADS) {
+        const int cyl = i / CW, cxl = i - cyl * CW;
+        const int qy = ty0 + cyl - 1, qx = tx0 + cxl - 1;
+        const bool inside = (qy >= 0) && (qy < H) && (qx >= 0) && (qx < W);
+        float a[3] = {0, 0, 0}, bb[3] = {0, 0, 0}, cc[3] = {0, 0, 0};
+        float g = 0.0f;
+        if (inside) {
+            const int cy = cyl + 1, cx = cxl + 1;  // position in the padded tile
             float l1 = 0, l1a = 0, ss = 0, ssa = 0;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                int64_t oc = ((int64_t)b * 3 + c) * p.hw + o;
-                float t = __ldg(p.in.tgt + oc), r = __ldg(p.in.rgb_rec + oc);
-                float pr = HASMASK ? blend_pred(r, t, m) : r;
-                if (HASMASK) p.out.pred[oc] = pr;
-                l1 += fabsf(pr - t);
-                float s = 0.0f;
-                if (AUTO) {
-                    s = __ldg(p.in.src + oc);
-                    l1a += fabsf(s - t);
+                const float* X = sP + c * PW * PH;
+                const float* Y = sT + c * PW * PH;
+                const WinStats w = win_stats(X, Y, cy, cx, PW);
+                float n, d;
+                const float v = ssim_val(w, n, d);
+                ss += fminf(fmaxf(v, 0.0f), 1.0f);
+                l1 += fabsf(X[cy * PW + cx] - Y[cy * PW + cx]);
+                if (WANT_G && v >= 0.0f && v <= 1.0f) {  // clamp backward
+                    const float a1 = 2.0f * w.mx * w.my + kC1, a2 = 2.0f * w.sxy + kC2;
+                    const float b1 = w.mx * w.mx + w.my * w.my + kC1, b2 = w.sx + w.sy + kC2;
+                    const float id = 1.0f / d, nd2 = n * id * id;
+                    const float k9 = 1.0f / 9.0f;
+                    bb[c] = nd2 * b1 * k9;
+                    cc[c] = -a1 * id * k9;
+                    a[c] = k9 * ((a1 - a2) * w.my * id + nd2 * (b2 - b1) * w.mx);
                 }
-                if (SSIM) {
-                    float n, d;
-                    const int cy = ly + 1, cx = lx + 1;
-                    float v = ssim_val(win_stats(sP + c * PW * PH, sT + c * PW * PH, cy, cx, PW), n, d);
-                    ss += fminf(fmaxf(v, 0.0f), 1.0f);
-                    if (AUTO) {
-                        float va = ssim_val(win_stats(sS + c * PW * PH, sT + c * PW * PH, cy, cx, PW), n, d);
-                        ssa += fminf(fmaxf(va, 0.0f), 1.0f);
-                    }
+                if (AUTO) {
+                    const float* S = sS + c * PW * PH;
+                    float na, da;
+                    const float va = ssim_val(win_stats(S, Y, cy, cx, PW), na, da);
+                    ssa += fminf(fmaxf(va, 0.0f), 1.0f);
+                    l1a += fabsf(S[cy * PW + cx] - Y[cy * PW + cx]);
                 }
             }
-            const float k3 = 1.0f / 3.0f;
-            ph = SSIM ? (0.85f * (ss * k3) + 0.15f * (l1 * k3)) : l1 * k3;
+            float ph = 0.85f * (ss * k3) + 0.15f * (l1 * k3);
+            g = 1.0f;
             if (AUTO) {
-                float pa = SSIM ? (0.85f * (ssa * k3) + 0.15f * (l1a * k3)) : l1a * k3;
+                const float pa = 0.85f * (ssa * k3) + 0.15f * (l1a * k3);
+                if (!(ph <= pa)) g = 0.0f;  // min() routes the gradient to the first minimum
                 ph = fminf(ph, pa);
             }
-        }
-        if (p.out.ph_map) p.out.ph_map[(int64_t)b * p.hw + o] = ph;
-    }
-    float tot = block_sum(ph, red);
-    if (threadIdx.x == 0) p.partials[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
-}
-
-// deterministic second stage: one CTA sums the per-tile partials in a fixed order
-__global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ partials, int64_t n, float* __restrict__ out) {
-    __shared__ float red[32];
-    float acc = 0.0f;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += partials[i];
-    float t = block_sum(acc, red);
-    if (threadIdx.x == 0) *out = t;
-}
-
-// ------------------------------------------------------------------------------------------------
-// backward
-// ------------------------------------------------------------------------------------------------
-template <int MODE, bool AUTO, bool HASMASK>
-__global__ void __launch_bounds__(LT_THREADS) photometric_bwd_kernel(const LossParams p) {
-    constexpr bool SSIM = (MODE == PD_LOSS_SSIM_L1);
-    constexpr int PW = LT_W + 4, PH = LT_H + 4;  // padded values: tile + 2
-    constexpr int CW = LT_W + 2, CH = LT_H + 2;  // window centres: tile + 1
-    __shared__ float sP[SSIM ? 3 * PW * PH : 1], sT[SSIM ? 3 * PW * PH : 1], sS[(SSIM && AUTO) ? 3 * PW * PH : 1];
-    __shared__ float cA[SSIM ? 3 * CW * CH : 1], cB[SSIM ? 3 * CW * CH : 1], cC[SSIM ? 3 * CW * CH : 1];
-    __shared__ float gate[SSIM ? CW * CH : 1];
-    const int H = p.d.H, W = p.d.W;
-    const int b = blockIdx.z, ty0 = blockIdx.y * LT_H, tx0 = blockIdx.x * LT_W;
-    const int ly = threadIdx.x / LT_W, lx = threadIdx.x % LT_W;
-    const int y = ty0 + ly, x = tx0 + lx;
-    const bool live = (y < H) && (x < W);
-    const float gph = __ldg(p.gout.g_ph_sum);
-    const float k3 = 1.0f / 3.0f;
-
-    if (SSIM) {
-        load_tiles<2, AUTO, HASMASK>(p, b, ty0, tx0, sP, sT, sS);
-        __syncthreads();
-        // per-centre coefficients: d ssim_term / d pred_i = A + B*pred_i + C*tgt_i for the 9 window cells
-        for (int i = threadIdx.x; i < CW * CH; i += LT_THREADS) {
-            int cyl = i / CW, cxl = i - cyl * CW;
-            int qy = ty0 + cyl - 1, qx = tx0 + cxl - 1;
-            bool inside = (qy >= 0) && (qy < H) && (qx >= 0) && (qx < W);
-            float a[3] = {0, 0, 0}, bb[3] = {0, 0, 0}, cc[3] = {0, 0, 0};
-            float g = 0.0f;
-            if (inside) {
-                const int cy = cyl + 1, cx = cxl + 1;  // position in the padded tile
-                float l1 = 0, l1a = 0, ss = 0, ssa = 0;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float* X = sP + c * PW * PH;
-                    const float* Y = sT + c * PW * PH;
-                    WinStats w = win_stats(X, Y, cy, cx, PW);
-                    float n, d;
-                    float v = ssim_val(w, n, d);
-                    ss += fminf(fmaxf(v, 0.0f), 1.0f);
-                    l1 += fabsf(X[cy * PW + cx] - Y[cy * PW + cx]);
-                    if (v >= 0.0f && v <= 1.0f) {  // clamp backward
-                        float a1 = 2.0f * w.mx * w.my + kC1, a2 = 2.0f * w.sxy + kC2;
-                        float b1 = w.mx * w.mx + w.my * w.my + kC1, b2 = w.sx + w.sy + kC2;
-                        float id = 1.0f / d, nd2 = n * id * id;
-                        const float k9 = 1.0f / 9.0f;
-                        bb[c] = nd2 * b1 * k9;
-                        cc[c] = -a1 * id * k9;
-                        a[c] = k9 * ((a1 - a2) * w.my * id + nd2 * (b2 - b1) * w.mx);
-                    }
-                    if (AUTO) {
-                        const float* S = sS + c * PW * PH;
-                        float na, da;
-                        float va = ssim_val(win_stats(S, Y, cy, cx, PW), na, da);
-                        ssa += fminf(fmaxf(va, 0.0f), 1.0f);
-                        l1a += fabsf(S[cy * PW + cx] - Y[cy * PW + cx]);
-                    }
-                }
-                g = gph;
-                if (AUTO) {
-                    float ph = 0.85f * (ss * k3) + 0.15f * (l1 * k3);
-                    float pa = 0.85f * (ssa * k3) + 0.15f * (l1a * k3);
-                    if (!(ph <= pa)) g = 0.0f;  // min() routes the gradient to the first minimum
-                }
+            if (cyl >= 1 && cyl <= LT_H && cxl >= 1 && cxl <= LT_W) {  // a pixel of this tile
+                ph_acc += ph;
+                if (p.out.ph_map) p.out.ph_map[(int64_t)b * p.hw + (int64_t)qy * W + qx] = ph;
             }
+        }
+        if (WANT_G) {
             gate[i] = g;
             const float ks = g * 0.85f * k3;
 #pragma unroll
@@ -248,68 +188,185 @@ __global__ void __launch_bounds__(LT_THREADS) photometric_bwd_kernel(const LossP
                 cC[c * CW * CH + i] = cc[c] * ks;
             }
         }
+    }
+    if (WANT_G) {
         __syncthreads();
-    }
-    if (!live) return;
-    const int64_t o = (int64_t)y * W + x;
-    const float m = HASMASK ? __ldg(p.in.mask_novel + (int64_t)b * p.hw + o) : 1.0f;
-    if (MODE == PD_LOSS_MIXTURE) {
-        float nl = __ldg(p.in.nll + (int64_t)b * p.hw + o);
-        bool sel = true;
-        if (AUTO) sel = nl <= __ldg(p.in.nll_auto + (int64_t)b * p.hw + o);
-        p.gin.g_nll[(int64_t)b * p.hw + o] = sel ? gph * m : 0.0f;
+        // ---- stage 3: unit gradient of every tile pixel
+        for (int i = threadIdx.x; i < LT_W * LT_H; i += LT_THREADS) {
+            const int ly = i / LT_W, lx = i - ly * LT_W;
+            const int y = ty0 + ly, x = tx0 + lx;
+            if (y >= H || x >= W) continue;
+            const int64_t o = (int64_t)y * W + x;
+            const float m = HASMASK ? __ldg(p.in.mask_novel + (int64_t)b * p.hw + o) : 1.0f;
+            const float gsel = gate[(ly + 1) * CW + lx + 1];
+            // multiplicities of the reflected copies of row y / column x inside the neighbouring windows
+            float wy[3], wx[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            int64_t oc = ((int64_t)b * 3 + c) * p.hw + o;
-            float ge = p.gout.g_pred ? __ldg(p.gout.g_pred + oc) : 0.0f;
-            p.gin.g_rgb_rec[oc] = ge * m;
+            for (int d = -1; d <= 1; ++d) {
+                const int qy = y + d, qx = x + d;
+                wy[d + 1] = (qy < 0 || qy >= H) ? 0.0f : 1.0f + ((y == 1 && qy == 0) ? 1.0f : 0.0f) + ((y == H - 2 && qy == H - 1) ? 1.0f : 0.0f);
+                wx[d + 1] = (qx < 0 || qx >= W) ? 0.0f : 1.0f + ((x == 1 && qx == 0) ? 1.0f : 0.0f) + ((x == W - 2 && qx == W - 1) ? 1.0f : 0.0f);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float pr = sP[c * PW * PH + (ly + 2) * PW + lx + 2], tg = sT[c * PW * PH + (ly + 2) * PW + lx + 2];
+                float sa = 0, sb = 0, sc = 0;
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const int ci = c * CW * CH + (ly + 1 + dy) * CW + (lx + 1 + dx);
+                        const float wgt = wy[dy + 1] * wx[dx + 1];
+                        sa = fmaf(wgt, cA[ci], sa), sb = fmaf(wgt, cB[ci], sb), sc = fmaf(wgt, cC[ci], sc);
+                    }
+                float g = gsel * (0.15f * k3) * sgnf(pr - tg) + sa + sb * pr + sc * tg;
+                if (HASMASK) g *= m;
+                p.out.g_unit[((int64_t)b * 3 + c) * p.hw + o] = g;
+            }
         }
-        return;
     }
-    float gsel = gph;
-    float pr[3], tg[3];
-    {
-        float l1 = 0, l1a = 0;
+    if (HASMASK) {
+        // blended prediction for the consumers outside the path (perceptual term, logging)
+        for (int i = threadIdx.x; i < LT_W * LT_H; i += LT_THREADS) {
+            const int ly = i / LT_W, lx = i - ly * LT_W;
+            const int y = ty0 + ly, x = tx0 + lx;
+            if (y >= H || x >= W) continue;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            int64_t oc = ((int64_t)b * 3 + c) * p.hw + o;
-            tg[c] = __ldg(p.in.tgt + oc);
-            float r = __ldg(p.in.rgb_rec + oc);
-            pr[c] = HASMASK ? blend_pred(r, tg[c], m) : r;
-            l1 += fabsf(pr[c] - tg[c]);
-            if (AUTO && !SSIM) l1a += fabsf(__ldg(p.in.src + oc) - tg[c]);
+            for (int c = 0; c < 3; ++c) p.out.pred[((int64_t)b * 3 + c) * p.hw + (int64_t)y * W + x] = sP[c * PW * PH + (ly + 2) * PW + lx + 2];
         }
-        if (SSIM) gsel = gate[(ly + 1) * CW + lx + 1];
-        else if (AUTO && !(l1 * k3 <= l1a * k3)) gsel = 0.0f;
     }
+    const float tot = block_sum(ph_acc, red);
+    if (threadIdx.x == 0) p.partials[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
+}
+
+// ------------------------------------------------------------------------------------------------
+// L1 / mixture forward (elementwise), with unit gradients
+// ------------------------------------------------------------------------------------------------
+constexpr int EW_THREADS = 256;
+
+template <int MODE, bool AUTO, bool HASMASK, bool WANT_G>
+__global__ void __launch_bounds__(EW_THREADS) elementwise_fwd_kernel(const LossParams p) {
+    __shared__ float red[EW_THREADS / 32];
+    const int64_t total = (int64_t)p.d.B * p.hw;
+    float acc = 0.0f;
+    for (int64_t pix = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; pix < total; pix += (int64_t)gridDim.x * EW_THREADS) {
+        const int b = (int)(pix / p.hw);
+        const int64_t o = pix - (int64_t)b * p.hw;
+        const float m = HASMASK ? __ldg(p.in.mask_novel + pix) : 1.0f;
+        float ph;
+        if (MODE == PD_LOSS_MIXTURE) {
+            ph = __ldg(p.in.nll + pix);
+            float g = 1.0f;
+            if (AUTO) {
+                const float pa = __ldg(p.in.nll_auto + pix);
+                if (!(ph <= pa)) g = 0.0f;
+                ph = fminf(ph, pa);
+            }
+            if (HASMASK) ph *= m, g *= m;
+            if (WANT_G) p.out.g_unit_nll[pix] = g;
+            if (HASMASK) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        int64_t oc = ((int64_t)b * 3 + c) * p.hw + o;
-        float diff = pr[c] - tg[c];
-        float sg = (diff > 0.0f) ? 1.0f : ((diff < 0.0f) ? -1.0f : 0.0f);
-        float g = gsel * (SSIM ? 0.15f : 1.0f) * k3 * sg;
-        if (SSIM) {
-            float sa = 0, sb = 0, sc = 0;
-#pragma unroll
-            for (int dy = -1; dy <= 1; ++dy) {
-                int qy = y + dy;
-                if (qy < 0 || qy >= H) continue;
-                // how many padded rows that mirror onto row y lie inside centre qy's window
-                float wy = 1.0f + ((y == 1 && qy == 0) ? 1.0f : 0.0f) + ((y == H - 2 && qy == H - 1) ? 1.0f : 0.0f);
-#pragma unroll
-                for (int dx = -1; dx <= 1; ++dx) {
-                    int qx = x + dx;
-                    if (qx < 0 || qx >= W) continue;
-                    float wx = 1.0f + ((x == 1 && qx == 0) ? 1.0f : 0.0f) + ((x == W - 2 && qx == W - 1) ? 1.0f : 0.0f);
-                    int ci = c * CW * CH + (ly + 1 + dy) * CW + (lx + 1 + dx);
-                    float wgt = wy * wx;
-                    sa = fmaf(wgt, cA[ci], sa), sb = fmaf(wgt, cB[ci], sb), sc = fmaf(wgt, cC[ci], sc);
+                for (int c = 0; c < 3; ++c) {
+                    const int64_t oc = ((int64_t)b * 3 + c) * p.hw + o;
+                    p.out.pred[oc] = blend_pred(__ldg(p.in.rgb_rec + oc), __ldg(p.in.tgt + oc), m);
                 }
             }
-            g += sa + sb * pr[c] + sc * tg[c];
+        } else {
+            float l1 = 0, l1a = 0, sg[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int64_t oc = ((int64_t)b * 3 + c) * p.hw + o;
+                const float t = __ldg(p.in.tgt + oc), r = __ldg(p.in.rgb_rec + oc);
+                const float pr = HASMASK ? blend_pred(r, t, m) : r;
+                if (HASMASK) p.out.pred[oc] = pr;
+                l1 += fabsf(pr - t);
+                sg[c] = sgnf(pr - t);
+                if (AUTO) l1a += fabsf(__ldg(p.in.src + oc) - t);
+            }
+            const float k3 = 1.0f / 3.0f;
+            ph = l1 * k3;
+            float g = k3;
+            if (AUTO) {
+                const float pa = l1a * k3;
+                if (!(ph <= pa)) g = 0.0f;
+                ph = fminf(ph, pa);
+            }
+            if (WANT_G) {
+                if (HASMASK) g *= m;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) p.out.g_unit[((int64_t)b * 3 + c) * p.hw + o] = g * sg[c];
+            }
         }
-        if (p.gout.g_pred) g += __ldg(p.gout.g_pred + oc);
-        p.gin.g_rgb_rec[oc] = HASMASK ? g * m : g;
+        if (p.out.ph_map) p.out.ph_map[pix] = ph;
+        acc += ph;
+    }
+    const float tot = block_sum(acc, red);
+    if (threadIdx.x == 0) p.partials[blockIdx.x] = tot;
+}
+
+// deterministic second stage: one CTA sums the per-CTA partials in a fixed order
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ partials, int64_t n, float* __restrict__ out) {
+    __shared__ float red[32];
+    float acc = 0.0f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += partials[i];
+    float t = block_sum(acc, red);
+    if (threadIdx.x == 0) *out = t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: g_rgb_rec = g_ph_sum * unit + g_pred * m        (streaming, 4 pixels per thread when aligned)
+//           g_nll     = g_ph_sum * unit_nll                 (mixture)
+// ------------------------------------------------------------------------------------------------
+template <bool MIXTURE, bool HASMASK>
+__global__ void __launch_bounds__(EW_THREADS) photometric_bwd_kernel(const LossParams p) {
+    const float gph = __ldg(p.gout.g_ph_sum);
+    const int64_t total = (int64_t)p.d.B * p.hw;
+    for (int64_t pix = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; pix < total; pix += (int64_t)gridDim.x * EW_THREADS) {
+        const int b = (int)(pix / p.hw);
+        const int64_t o = pix - (int64_t)b * p.hw;
+        const float m = HASMASK ? __ldg(p.in.mask_novel + pix) : 1.0f;
+        if (MIXTURE) p.gin.g_nll[pix] = gph * __ldg(p.out.g_unit_nll + pix);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int64_t oc = ((int64_t)b * 3 + c) * p.hw + o;
+            float g = MIXTURE ? 0.0f : gph * __ldg(p.out.g_unit + oc);
+            if (p.gout.g_pred) {
+                const float ge = __ldg(p.gout.g_pred + oc);
+                g += HASMASK ? ge * m : ge;
+            }
+            p.gin.g_rgb_rec[oc] = g;
+        }
+    }
+}
+
+// same, 4 consecutive pixels per thread (H*W % 4 == 0 and 16-byte aligned pointers)
+template <bool MIXTURE, bool HASMASK>
+__global__ void __launch_bounds__(EW_THREADS) photometric_bwd_kernel_v4(const LossParams p) {
+    const float gph = __ldg(p.gout.g_ph_sum);
+    const int64_t hw4 = p.hw / 4;
+    for (int64_t q = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; q < p.total4; q += (int64_t)gridDim.x * EW_THREADS) {
+        const int b = (int)(q / hw4);
+        const int64_t o4 = q - (int64_t)b * hw4;
+        float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (HASMASK) m = __ldg(reinterpret_cast<const float4*>(p.in.mask_novel) + q);
+        if (MIXTURE) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(p.out.g_unit_nll) + q);
+            reinterpret_cast<float4*>(p.gin.g_nll)[q] = make_float4(gph * u.x, gph * u.y, gph * u.z, gph * u.w);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int64_t oc4 = ((int64_t)b * 3 + c) * hw4 + o4;
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!MIXTURE) {
+                const float4 u = __ldg(reinterpret_cast<const float4*>(p.out.g_unit) + oc4);
+                g = make_float4(gph * u.x, gph * u.y, gph * u.z, gph * u.w);
+            }
+            if (p.gout.g_pred) {
+                const float4 ge = __ldg(reinterpret_cast<const float4*>(p.gout.g_pred) + oc4);
+                g.x = fmaf(ge.x, m.x, g.x), g.y = fmaf(ge.y, m.y, g.y), g.z = fmaf(ge.z, m.z, g.z), g.w = fmaf(ge.w, m.w, g.w);
+            }
+            reinterpret_cast<float4*>(p.gin.g_rgb_rec)[oc4] = g;
+        }
     }
 }
 

@@ -210,24 +210,32 @@ def warp_composite(cfg: WarpConfig, src, tgt, logits, sigma=None, disp=None, mas
 
 
 class _Photometric(torch.autograd.Function):
-    """pd_photometric_fwd / _bwd: trainer.py:720-742 (+687-699) for one target side."""
+    """pd_photometric_fwd / _bwd: trainer.py:720-742 (+687-699) for one target side.  The forward also produces the
+    unit gradient d ph_sum / d rgb_rec (d ph_sum / d nll in mixture mode) while its tiles are on chip; the backward
+    is a streaming scale-and-add."""
 
     @staticmethod
     def forward(ctx, mode: int, automask: bool, want_map: bool, rgb_rec, tgt, src, mask_novel, nll, nll_auto):
         lib = L.lib()
         B, _, H, W = rgb_rec.shape
         dev = rgb_rec.device
+        mixture = mode == L.PD_LOSS_MIXTURE
         desc = L.LossDesc(B=B, H=H, W=W, loss_mode=mode, automask=int(automask), has_mask_novel=int(mask_novel is not None))
         tin = L.LossIn(rgb_rec=_ptr(rgb_rec), tgt=_ptr(tgt), src=_ptr(src), mask_novel=_ptr(mask_novel), nll=_ptr(nll), nll_auto=_ptr(nll_auto))
         pred = torch.empty_like(rgb_rec) if mask_novel is not None else None
         ph_map = torch.empty(B, 1, H, W, device=dev) if want_map else None
         ph_sum = torch.empty((), device=dev, dtype=torch.float32)
+        need_grad = any(ctx.needs_input_grad)
+        g_unit = torch.empty_like(rgb_rec) if (need_grad and not mixture) else None
+        g_unit_nll = torch.empty(B, 1, H, W, device=dev) if (need_grad and mixture) else None
         ws = torch.empty(lib.pd_photometric_workspace_bytes(C.byref(desc)) // 4, device=dev, dtype=torch.float32)
-        out = L.LossOut(pred=_ptr(pred), ph_map=_ptr(ph_map), ph_sum=_ptr(ph_sum))
+        out = L.LossOut(pred=_ptr(pred), ph_map=_ptr(ph_map), ph_sum=_ptr(ph_sum), g_unit=_ptr(g_unit), g_unit_nll=_ptr(g_unit_nll))
         _call("pd_photometric_fwd", lib.pd_photometric_fwd, C.byref(desc), C.byref(tin), C.byref(out), ws.data_ptr(), _stream())
         ctx.desc = desc
         ctx.has_pred = pred is not None
-        ctx.save_for_backward(rgb_rec, tgt, src, mask_novel, nll, nll_auto)
+        ctx.mixture = mixture
+        ctx.shape = (B, H, W)
+        ctx.save_for_backward(mask_novel, g_unit, g_unit_nll)
         outs = (ph_sum, pred if pred is not None else torch.empty(0, device=dev), ph_map if ph_map is not None else torch.empty(0, device=dev))
         ctx.mark_non_differentiable(outs[2])
         return outs
@@ -235,16 +243,19 @@ class _Photometric(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_sum, g_pred, g_map):
         lib = L.lib()
-        rgb_rec, tgt, src, mask_novel, nll, nll_auto = ctx.saved_tensors
-        dev = rgb_rec.device
+        mask_novel, g_unit, g_unit_nll = ctx.saved_tensors
+        B, H, W = ctx.shape
+        dev = (g_unit if g_unit is not None else g_unit_nll).device
         g_sum = torch.zeros((), device=dev) if g_sum is None else _f32c(g_sum, "grad ph_sum")
         g_pred = _f32c(g_pred, "grad pred") if (ctx.has_pred and g_pred is not None) else None
-        tin = L.LossIn(rgb_rec=_ptr(rgb_rec), tgt=_ptr(tgt), src=_ptr(src), mask_novel=_ptr(mask_novel), nll=_ptr(nll), nll_auto=_ptr(nll_auto))
-        g_rgb = torch.empty_like(rgb_rec)
-        g_nll = torch.empty_like(nll) if nll is not None else None
+        tin = L.LossIn(mask_novel=_ptr(mask_novel))
+        saved = L.LossOut(g_unit=_ptr(g_unit), g_unit_nll=_ptr(g_unit_nll))
+        g_rgb = torch.empty(B, 3, H, W, device=dev, dtype=torch.float32)
+        g_nll = torch.empty(B, 1, H, W, device=dev, dtype=torch.float32) if ctx.mixture else None
         gout = L.LossGradOut(g_ph_sum=_ptr(g_sum), g_pred=_ptr(g_pred))
         gin = L.LossGradIn(g_rgb_rec=_ptr(g_rgb), g_nll=_ptr(g_nll))
-        _call("pd_photometric_bwd", lib.pd_photometric_bwd, C.byref(ctx.desc), C.byref(tin), C.byref(gout), C.byref(gin), None, _stream())
+        _call("pd_photometric_bwd", lib.pd_photometric_bwd, C.byref(ctx.desc), C.byref(tin), C.byref(saved), C.byref(gout), C.byref(gin), None,
+              _stream())
         return (None, None, None, g_rgb, None, None, None, g_nll, None)
 
 

@@ -25,7 +25,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert set(L.EXPORTS) <= set(names)
     for n in names:
         assert hasattr(lib, n), "missing export %s" % n
-    assert lib.pd_version() == 2
+    assert lib.pd_version() == L.ABI_VERSION
     assert lib.pd_last_error() is not None
 
 
