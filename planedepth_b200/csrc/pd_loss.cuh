@@ -110,82 +110,142 @@ __global__ void __launch_bounds__(LT_THREADS) ssim_l1_fwd_kernel(const LossParam
 
     // ---- stage 1: reflect-padded tiles (padded coordinate -> image coordinate; cells further than one pixel outside
     // the image are never read by a centre inside it, they only need to stay addressable)
-    for (int i = threadIdx.x; i < PW * PH; i += LT_THREADS) {
-        const int ly = i / PW, lx = i - ly * PW;
-        int gy = reflect(min(max(ty0 + ly - 2, -1), H), H);
-        int gx = reflect(min(max(tx0 + lx - 2, -1), W), W);
-        gy = min(max(gy, 0), H - 1);
-        gx = min(max(gx, 0), W - 1);
-        const int64_t o = (int64_t)gy * W + gx;
-        const float m = HASMASK ? __ldg(p.in.mask_novel + (int64_t)b * p.hw + o) : 1.0f;
+    {
+        constexpr int NL = (PW * PH + LT_THREADS - 1) / LT_THREADS;  // positions per thread: all loads are issued before
+        float vt[NL][3], vr[NL][3], vs[NL][3], vm[NL];                // the first store so that they overlap
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const int64_t oc = ((int64_t)b * 3 + c) * p.hw + o;
-            const float t = __ldg(p.in.tgt + oc), r = __ldg(p.in.rgb_rec + oc);
-            sT[c * PW * PH + i] = t;
-            sP[c * PW * PH + i] = HASMASK ? blend_pred(r, t, m) : r;
-            if (AUTO) sS[c * PW * PH + i] = __ldg(p.in.src + oc);
+        for (int q = 0; q < NL; ++q) {
+            const int i = threadIdx.x + q * LT_THREADS;
+            const int ic = min(i, PW * PH - 1);
+            const int ly = ic / PW, lx = ic - ly * PW;
+            int gy = reflect(min(max(ty0 + ly - 2, -1), H), H);
+            int gx = reflect(min(max(tx0 + lx - 2, -1), W), W);
+            gy = min(max(gy, 0), H - 1);
+            gx = min(max(gx, 0), W - 1);
+            const int64_t o = (int64_t)gy * W + gx;
+            vm[q] = HASMASK ? __ldg(p.in.mask_novel + (int64_t)b * p.hw + o) : 1.0f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int64_t oc = ((int64_t)b * 3 + c) * p.hw + o;
+                vt[q][c] = __ldg(p.in.tgt + oc);
+                vr[q][c] = __ldg(p.in.rgb_rec + oc);
+                vs[q][c] = AUTO ? __ldg(p.in.src + oc) : 0.0f;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NL; ++q) {
+            const int i = threadIdx.x + q * LT_THREADS;
+            if (i < PW * PH) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    sT[c * PW * PH + i] = vt[q][c];
+                    sP[c * PW * PH + i] = HASMASK ? blend_pred(vr[q][c], vt[q][c], vm[q]) : vr[q][c];
+                    if (AUTO) sS[c * PW * PH + i] = vs[q][c];
+                }
+            }
         }
     }
     __syncthreads();
 
-    // ---- stage 2: window centres of the tile and of the ring around it
+    // ---- stage 2: window centres of the tile and of the ring around it.  One thread walks a column of 5 centres
+    // (half of the 10 centre rows) with rolling row sums: 6 shared loads per window row instead of 18 per window.
     float ph_acc = 0.0f;
-    for (int i = threadIdx.x; i < CW * CH; i += LT_THREADS) {
-        const int cyl = i / CW, cxl = i - cyl * CW;
-        const int qy = ty0 + cyl - 1, qx = tx0 + cxl - 1;
-        const bool inside = (qy >= 0) && (qy < H) && (qx >= 0) && (qx < W);
-        float a[3] = {0, 0, 0}, bb[3] = {0, 0, 0}, cc[3] = {0, 0, 0};
-        float g = 0.0f;
-        if (inside) {
-            const int cy = cyl + 1, cx = cxl + 1;  // position in the padded tile
-            float l1 = 0, l1a = 0, ss = 0, ssa = 0;
+    if (threadIdx.x < 2 * CW) {
+        constexpr int NJ = CH / 2;  // centres per thread
+        const int half = threadIdx.x / CW, cxl = threadIdx.x - half * CW;
+        const int idx0 = half * NJ;  // first centre row of this thread; its window starts at padded row idx0
+        const int qx = tx0 + cxl - 1;
+        const bool in_x = (qx >= 0) && (qx < W);
+        float ss[NJ], l1[NJ], ssa[NJ], l1a[NJ];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float* X = sP + c * PW * PH;
-                const float* Y = sT + c * PW * PH;
-                const WinStats w = win_stats(X, Y, cy, cx, PW);
-                float n, d;
-                const float v = ssim_val(w, n, d);
-                ss += fminf(fmaxf(v, 0.0f), 1.0f);
-                l1 += fabsf(X[cy * PW + cx] - Y[cy * PW + cx]);
-                if (WANT_G && v >= 0.0f && v <= 1.0f) {  // clamp backward
-                    const float a1 = 2.0f * w.mx * w.my + kC1, a2 = 2.0f * w.sxy + kC2;
-                    const float b1 = w.mx * w.mx + w.my * w.my + kC1, b2 = w.sx + w.sy + kC2;
-                    const float id = 1.0f / d, nd2 = n * id * id;
-                    const float k9 = 1.0f / 9.0f;
-                    bb[c] = nd2 * b1 * k9;
-                    cc[c] = -a1 * id * k9;
-                    a[c] = k9 * ((a1 - a2) * w.my * id + nd2 * (b2 - b1) * w.mx);
-                }
+        for (int j = 0; j < NJ; ++j) ss[j] = l1[j] = ssa[j] = l1a[j] = 0.0f;
+        const float k9 = 1.0f / 9.0f, ks = 0.85f * k3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* X = sP + c * PW * PH + cxl;
+            const float* Y = sT + c * PW * PH + cxl;
+            const float* S = sS + (AUTO ? c * PW * PH + cxl : 0);
+            // row sums of the two previous padded rows: {sum x, sum y, sum xx, sum yy, sum xy, sum s, sum ss, sum sy}
+            float r0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, r1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            float pa = 0, pb = 0, ps = 0;  // centre-column values of the previous row
+#pragma unroll
+            for (int k = 0; k < NJ + 2; ++k) {
+                const int ly = idx0 + k;
+                const float a0 = X[ly * PW], a1 = X[ly * PW + 1], a2 = X[ly * PW + 2];
+                const float b0 = Y[ly * PW], b1 = Y[ly * PW + 1], b2 = Y[ly * PW + 2];
+                float rs[8];
+                rs[0] = a0 + a1 + a2, rs[1] = b0 + b1 + b2;
+                rs[2] = fmaf(a0, a0, fmaf(a1, a1, a2 * a2)), rs[3] = fmaf(b0, b0, fmaf(b1, b1, b2 * b2));
+                rs[4] = fmaf(a0, b0, fmaf(a1, b1, a2 * b2));
+                float s1 = 0;
                 if (AUTO) {
-                    const float* S = sS + c * PW * PH;
-                    float na, da;
-                    const float va = ssim_val(win_stats(S, Y, cy, cx, PW), na, da);
-                    ssa += fminf(fmaxf(va, 0.0f), 1.0f);
-                    l1a += fabsf(S[cy * PW + cx] - Y[cy * PW + cx]);
+                    const float s0 = S[ly * PW], s2 = S[ly * PW + 2];
+                    s1 = S[ly * PW + 1];
+                    rs[5] = s0 + s1 + s2, rs[6] = fmaf(s0, s0, fmaf(s1, s1, s2 * s2)), rs[7] = fmaf(s0, b0, fmaf(s1, b1, s2 * b2));
                 }
+                if (k >= 2) {
+                    const int j = k - 2, ci = (idx0 + j) * CW + cxl;
+                    const int qy = ty0 + idx0 + j - 1;
+                    const bool inside = in_x && (qy >= 0) && (qy < H);
+                    WinStats w;
+                    w.mx = (r0[0] + r1[0] + rs[0]) * k9, w.my = (r0[1] + r1[1] + rs[1]) * k9;
+                    w.sx = (r0[2] + r1[2] + rs[2]) * k9 - w.mx * w.mx;
+                    w.sy = (r0[3] + r1[3] + rs[3]) * k9 - w.my * w.my;
+                    w.sxy = (r0[4] + r1[4] + rs[4]) * k9 - w.mx * w.my;
+                    float n, d;
+                    const float v = ssim_val(w, n, d);
+                    ss[j] += fminf(fmaxf(v, 0.0f), 1.0f);
+                    l1[j] += fabsf(pa - pb);
+                    if (WANT_G) {
+                        float ca = 0, cb = 0, cc = 0;
+                        if (inside && v >= 0.0f && v <= 1.0f) {  // clamp backward
+                            const float a1c = 2.0f * w.mx * w.my + kC1, a2c = 2.0f * w.sxy + kC2;
+                            const float b1c = w.mx * w.mx + w.my * w.my + kC1, b2c = w.sx + w.sy + kC2;
+                            const float id = 1.0f / d, nd2 = n * id * id;
+                            cb = nd2 * b1c * (k9 * ks);
+                            cc = -a1c * id * (k9 * ks);
+                            ca = (k9 * ks) * ((a1c - a2c) * w.my * id + nd2 * (b2c - b1c) * w.mx);
+                        }
+                        cA[c * CW * CH + ci] = ca, cB[c * CW * CH + ci] = cb, cC[c * CW * CH + ci] = cc;
+                    }
+                    if (AUTO) {
+                        WinStats u;
+                        u.mx = (r0[5] + r1[5] + rs[5]) * k9, u.my = w.my;
+                        u.sx = (r0[6] + r1[6] + rs[6]) * k9 - u.mx * u.mx;
+                        u.sy = w.sy;
+                        u.sxy = (r0[7] + r1[7] + rs[7]) * k9 - u.mx * u.my;
+                        float na, da;
+                        ssa[j] += fminf(fmaxf(ssim_val(u, na, da), 0.0f), 1.0f);
+                        l1a[j] += fabsf(ps - pb);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) r0[q] = r1[q], r1[q] = rs[q];
+                pa = a1, pb = b1, ps = s1;
             }
-            float ph = 0.85f * (ss * k3) + 0.15f * (l1 * k3);
-            g = 1.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int cyl = idx0 + j, ci = cyl * CW + cxl;
+            const int qy = ty0 + cyl - 1;
+            const bool inside = in_x && (qy >= 0) && (qy < H);
+            float ph = 0.85f * (ss[j] * k3) + 0.15f * (l1[j] * k3);
+            float g = inside ? 1.0f : 0.0f;
             if (AUTO) {
-                const float pa = 0.85f * (ssa * k3) + 0.15f * (l1a * k3);
-                if (!(ph <= pa)) g = 0.0f;  // min() routes the gradient to the first minimum
-                ph = fminf(ph, pa);
+                const float pa2 = 0.85f * (ssa[j] * k3) + 0.15f * (l1a[j] * k3);
+                if (!(ph <= pa2)) g = 0.0f;  // min() routes the gradient to the first minimum
+                ph = fminf(ph, pa2);
             }
-            if (cyl >= 1 && cyl <= LT_H && cxl >= 1 && cxl <= LT_W) {  // a pixel of this tile
+            if (inside && cyl >= 1 && cyl <= LT_H && cxl >= 1 && cxl <= LT_W) {  // a pixel of this tile
                 ph_acc += ph;
                 if (p.out.ph_map) p.out.ph_map[(int64_t)b * p.hw + (int64_t)qy * W + qx] = ph;
             }
-        }
-        if (WANT_G) {
-            gate[i] = g;
-            const float ks = g * 0.85f * k3;
+            if (WANT_G) {
+                gate[ci] = g;
+                if (AUTO && g == 0.0f) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                cA[c * CW * CH + i] = a[c] * ks;
-                cB[c * CW * CH + i] = bb[c] * ks;
-                cC[c * CW * CH + i] = cc[c] * ks;
+                    for (int c = 0; c < 3; ++c) cA[c * CW * CH + ci] = cB[c * CW * CH + ci] = cC[c * CW * CH + ci] = 0.0f;
+                }
             }
         }
     }

@@ -49,13 +49,13 @@ def launches(tag):
             f.write('%s,"%s","%s","%s",%s\n' % (r["ID"], short(r["Kernel Name"]), r["Grid Size"], r["Block Size"], r["Metric Value"]))
     # share of one step: take the LAST occurrence of each of our kernels plus everything between the last
     # forward warp launch and the last backward warp launch
-    ours = [i for i, r in enumerate(rows) if "pd::" in r["Kernel Name"] or "warp_composite" in r["Kernel Name"]]
+    ours = [i for i, r in enumerate(rows) if "pd::" in r["Kernel Name"]]
     with open(os.path.join(ROOT, "profiles", tag + "_launch_shares.txt"), "w") as f:
         if not ours:
             f.write("no library kernels in the launch list\n")
             return
-        fwd = [i for i in ours if "warp_composite_fwd" in rows[i]["Kernel Name"]]
-        bwd = [i for i in ours if "warp_composite_bwd" in rows[i]["Kernel Name"]]
+        fwd = [i for i in ours if "warp_composite_fwd" in rows[i]["Kernel Name"] or "rows_fwd" in rows[i]["Kernel Name"]]
+        bwd = [i for i in ours if "warp_composite_bwd" in rows[i]["Kernel Name"] or "rows_bwd" in rows[i]["Kernel Name"]]
         a, b = fwd[-1], bwd[-1]
         step = rows[a:b + 1]
         tot = sum(float(r["Metric Value"]) for r in step)
@@ -85,10 +85,10 @@ def full(tag):
                     vals[k] = r[i]
                     f.write("  %-75s %s %s\n" % (k, r[i], units[i]))
             try:
-                rd, wr = float(vals["dram__bytes_read.sum"]), float(vals["dram__bytes_write.sum"])
-                u = units[hdr.index("dram__bytes_read.sum")]
-                scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-                f.write("  %-75s %.1f MB\n" % ("traffic = dram read + write per launch", (rd + wr) * scale / 1e6))
+                sc = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                rd = float(vals["dram__bytes_read.sum"]) * sc.get(units[hdr.index("dram__bytes_read.sum")], 1)
+                wr = float(vals["dram__bytes_write.sum"]) * sc.get(units[hdr.index("dram__bytes_write.sum")], 1)
+                f.write("  %-75s %.1f MB\n" % ("traffic = dram read + write per launch", (rd + wr) / 1e6))
             except Exception:
                 pass
 
