@@ -261,6 +261,10 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if ws > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION/INFO
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("PD_BENCH_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = _lib.lib()
     B, H, W, over, photometric, desc = CONFIGS[args.config]
