@@ -399,7 +399,8 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(args.config, {}).get(dom)
+            tj = json.load(open(tp))
+            traffic = tj.get(args.config + ("_compact" if args.layout == "compact" else ""), {}).get(dom)
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

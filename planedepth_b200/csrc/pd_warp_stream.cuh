@@ -648,18 +648,22 @@ __device__ __forceinline__ float bwd_plane(uint32_t srow, uint32_t lrow, uint32_
             if (PERPIX) sraw *= mm[i];
             const float sg = fminf(fmaxf(sraw, 0.01f), 1.0f);
             const float inv = fast_rcp(sg);
+            // with a = 1/sigma, w = pi a / Z (compositing weight), q = gD pi lap (the plane's share of dL/dD):
+            //   dL/dlogit = w dG + q - pi gDD,  dL/dsigma = a (q a (err - sigma) - w dG),  dL/dcolour = w g -+ q a / 3
             const float w = pi[i] * inv * c.Zinv[i];
+            const float dG = Gn[i] - c.Gbar[i];
             const float err = (fabsf(cr[i] - c.tr[i]) + fabsf(cg[i] - c.tg[i]) + fabsf(cb[i] - c.tb[i])) * (1.0f / 3.0f);
-            const float lap = 0.5f * fast_exp2(-err * inv * kLog2e) * inv;
-            const float P = (Gn[i] - c.Gbar[i]) * inv * c.Zinv[i] + c.gD[i] * lap;
-            dl[i] = pi[i] * (P - c.gDD[i]);
-            const float dsgt = -(Gn[i] - c.Gbar[i]) * w * inv + c.gD[i] * pi[i] * lap * (err - sg) * inv * inv;
+            const float ea = err * inv;
+            const float q = c.gD[i] * pi[i] * (0.5f * inv) * fast_exp2(-ea * kLog2e);
+            const float wdG = w * dG;
+            dl[i] = fmaf(-pi[i], c.gDD[i], wdG + q);
+            const float dsgt = inv * fmaf(q, ea - 1.0f, -wdG);  // q a (err - sigma) = q (err a - 1)
             ds[i] = (sraw >= 0.01f && sraw <= 1.0f) ? dsgt : 0.0f;  // clamp backward
             if (WANT_DISP) {
-                const float ce = -c.gD[i] * pi[i] * lap * inv * (1.0f / 3.0f);
-                const float dcr = w * c.g0[i] + ce * sgn(cr[i], c.tr[i]);
-                const float dcg = w * c.g1[i] + ce * sgn(cg[i], c.tg[i]);
-                const float dcb = w * c.g2[i] + ce * sgn(cb[i], c.tb[i]);
+                const float ce = -q * inv * (1.0f / 3.0f);
+                const float dcr = fmaf(w, c.g0[i], ce * sgn(cr[i], c.tr[i]));
+                const float dcg = fmaf(w, c.g1[i], ce * sgn(cg[i], c.tg[i]));
+                const float dcb = fmaf(w, c.g2[i], ce * sgn(cb[i], c.tb[i]));
                 gx[i] = dcr * dr[i] + dcg * dg[i] + dcb * db[i] + dl[i] * dlu[i] + ds[i] * (v[R + i + 1] - v[R + i]);
             }
         }
@@ -1008,7 +1012,7 @@ inline bool launch_fwd_stream_m(const WarpParams& p, cudaStream_t st) {
     const int W = p.d.W;
     if (W % 8 == 0 && W / 8 <= 160 && stream_env_int("PD_STREAM_PX8", 0)) return launch_fwd_stream_t<MIX, MASKMODE, 8, 192, 2>(p, st);
     if (W / 4 <= 160) return launch_fwd_stream_t<MIX, MASKMODE, 4, 192, MIX ? 2 : 4>(p, st);
-    if (W / 4 <= 320) return launch_fwd_stream_t<MIX, MASKMODE, 4, 352, 1>(p, st);
+    if (W / 4 <= 320) return launch_fwd_stream_t<MIX, MASKMODE, 4, 352, MIX ? 2 : 2>(p, st);
     return false;
 }
 
