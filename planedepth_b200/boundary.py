@@ -195,29 +195,40 @@ class HotPathMixin:
         if mode == L.PD_LOSS_MIXTURE and not _flag(opt, "use_mixture_loss", False):
             raise ValueError("photometric='mixture' needs opt.use_mixture_loss (sigma channel)")
         pc_net = getattr(self, "pc_net", None)
-        losses = {"loss/ph_loss": 0, "loss/pc_loss": 0, "loss/total_loss": 0}
+        # trainer.py:717-766 accumulates into zero-initialised entries and divides every entry by len(target_sides)
+        # in place; the same values are formed here without the no-op kernels (0 + x, x / 1): at B200 speeds each
+        # tiny elementwise launch costs as much as 1 % of the whole step
+        acc: Dict[str, Optional[torch.Tensor]] = {"loss/ph_loss": None, "loss/pc_loss": None, "loss/total_loss": None}
+
+        def add(key, val):
+            acc[key] = val if acc[key] is None else acc[key] + val
+
         src = inputs[(color, "l")]
         mask_novel = outputs.get("mask_novel")
+        inv_count = 1.0 / float(B * H * W)
         for side in self.target_sides:
             target = inputs[(color, side)]
             ph_sum, pred, _ = photometric_loss(
                 mode, automask, outputs[("rgb_rec", side)], target, src, mask_novel,
                 outputs.get(("nll_rec", side)), outputs.get(("nll_auto_rec", side)))
-            ph_loss = ph_sum / float(B * H * W)
-            losses["loss/ph_loss"] = losses["loss/ph_loss"] + ph_loss
+            ph_loss = ph_sum * inv_count  # ph_loss.mean(), trainer.py:742
+            add("loss/ph_loss", ph_loss)
             total = ph_loss
             if pc_net is not None:
                 pc = self.perceptual_loss(pred, target, src if automask else None)
-                losses["loss/pc_loss"] = losses["loss/pc_loss"] + pc
+                add("loss/pc_loss", pc)
                 total = total + _flag(opt, "alpha_pc", 0.1) * pc
             if _flag(opt, "self_distillation", 0.0) > 0:
                 dl = torch.abs(outputs["disp"] - outputs["disp_pp"]).mean()
-                losses["loss/disp_loss"] = dl
+                acc["loss/disp_loss"] = dl
                 total = total + opt.self_distillation * dl
-            losses["loss/total_loss"] = losses["loss/total_loss"] + total
+            add("loss/total_loss", total)
         n_t = len(self.target_sides)
-        for k in list(losses.keys()):  # trainer.py:765-766
-            losses[k] = losses[k] / n_t
+        losses = {}
+        for k, v in acc.items():  # trainer.py:765-766
+            if v is None:
+                v = torch.zeros((), device=src.device)
+            losses[k] = v / n_t if n_t != 1 else v
         if "disp" in outputs:
             x0 = int(0.2 * W)
             sm = smooth_loss_disp(outputs["disp"][..., x0:], inputs[("color", "l")][..., x0:], _flag(opt, "gamma_smooth", 2))
