@@ -63,28 +63,83 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed regions: an NVML polling thread (the timed regions last
+    milliseconds, far below nvidia-smi's start-up time) plus inline samples taken by the main thread while it waits for
+    the queued steps to drain.  Falls back to `nvidia-smi -lms` when NVML cannot be loaded."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.sm, self.bits, self.smax, self.h, self.nv = [], 0, None, None, None
+        self.running = False
 
     def start(self):
         try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except Exception:
+                    idx = self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.smax = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.running = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.h = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
+
+    def sample(self):
+        """One NVML sample (callable from the main thread while the GPU works)."""
+        if self.h is None:
+            return
+        try:
+            self.sm.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            try:
+                self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+
+    def sample_until(self, event):
+        """Sample while `event` (recorded after the queued steps) has not completed."""
+        while not event.query():
+            self.sample()
+
+    def _poll(self):
+        while self.running:
+            self.sample()
+            time.sleep(0.001)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.h is not None:
+            self.running = False
+            self.thread.join(timeout=1)
+            sm = sorted(self.sm)
+            reasons = [n for n, bit in self.REASONS.items() if self.bits & bit]
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax, "reasons": reasons, "samples": len(sm),
+                    "source": "nvml, polled during the timed regions"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -97,7 +152,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
 def algorithmic_bytes(B, N, H, W, mixture):
@@ -232,7 +287,9 @@ def run_reference(args):
     if rank != 0:
         return
     B, H, W, over, photometric, desc = CONFIGS[args.config]
-    B_sample = min(B, 4)
+    # each step is a bounded sample of the workload (images of the configured shape), sized so that K steps of the
+    # CPU path (about 0.1 s per image on 16 host threads at cfg2) end within a few minutes
+    B_sample = min(B, 4 if args.steps <= 30 else (2 if args.steps <= 100 else 1))
     cb, dt = time_cpu(args.config, B_sample, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -305,18 +362,20 @@ def run_ours(args):
         graphed.replay()
     clocks = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        clocks.start()
     lib.pd_reset_launch_count()
     probe = step()  # one eager step to count the library launches a step performs
     launches_per_step = lib.pd_launch_count()
     del probe
     barrier()
+    if rank == 0:
+        clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
         graphed.replay()
     ev1.record()
+    if rank == 0:
+        clocks.sample_until(ev1)  # the queued steps are still running: these samples are under load
     barrier()
     ms_step = D.max_over_ranks(ev0.elapsed_time(ev1), ws, dev) / args.steps
     loss_val = float(graphed.result["loss"].item())
@@ -441,8 +500,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--layout", default="reference", choices=["reference", "compact"])

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PD_ABI_VERSION 3
+#define PD_ABI_VERSION 4
 
 typedef void* pd_stream_t; /* a cudaStream_t */
 
@@ -98,15 +98,17 @@ typedef struct pd_warp_in {
                             (K·T)[:3,:] row-major (12)  (layers.py:152,172) */
 } pd_warp_in;
 
-/* Number of per-pixel fp32 statistics saved for the backward pass: [B,PD_STATS(mixture),H,W].
- * non-mixture: {reference logit * log2(e), sum exp(l - ref)}.  mixture: additionally {sum exp/sigma, mixture
- * density sum pi*lap + 1e-7}.  Opaque to callers: only pd_warp_composite_bwd reads it. */
+/* Statistics saved for the backward pass: an opaque buffer of pd_warp_composite_stats_bytes(desc) bytes that only
+ * pd_warp_composite_bwd reads.  It holds [B,PD_STATS(mixture),H,W] fp32 per-pixel values — non-mixture: {reference
+ * logit * log2(e), sum exp(l - ref)}; mixture: additionally {sum exp/sigma, mixture density sum pi*lap + 1e-7} —
+ * followed by a row summary of a dense padding_mask (which 128-pixel row segments are all ones / all zeros) that
+ * lets the backward pass leave those mask rows in HBM. */
 #define PD_STATS_PLAIN 2
 #define PD_STATS_MIXTURE 4
 
 typedef struct pd_warp_out {
     float* rgb_rec;  /* [B,3,H,W]   outputs[("rgb_rec", s)]                       trainer.py:603 */
-    float* stats;    /* [B,PD_STATS,H,W] saved for pd_warp_composite_bwd */
+    float* stats;    /* pd_warp_composite_stats_bytes(desc) bytes, 16-byte aligned, saved for pd_warp_composite_bwd */
     float* nll;      /* [B,1,H,W] mixture: -log(sum pi*lap + 1e-7)                trainer.py:730 */
     float* nll_auto; /* [B,1,H,W] mixture+automask: same with err = |src - tgt|   trainer.py:732-733 */
     /* optional (NULL = not materialised; tests and tensorboard-style consumers only) */
@@ -136,6 +138,7 @@ int pd_version(void);
 const char* pd_last_error(void);
 
 size_t pd_warp_composite_workspace_bytes(const pd_warp_desc* desc);
+size_t pd_warp_composite_stats_bytes(const pd_warp_desc* desc);
 
 int pd_warp_composite_fwd(const pd_warp_desc* desc, const pd_warp_in* in, pd_warp_out* out,
                           void* workspace, pd_stream_t stream);

@@ -23,12 +23,12 @@ PD_WARP_DISP, PD_WARP_HOMOGRAPHY, PD_WARP_DEPTH = 0, 1, 2
 PD_LOSS_L1, PD_LOSS_MIXTURE, PD_LOSS_SSIM_L1 = 0, 1, 2
 PD_MASK_NONE, PD_MASK_F32, PD_MASK_U8 = 0, 1, 2
 PD_FLAG_EXACT_COORDS = 1
-ABI_VERSION = 3  # PD_ABI_VERSION in include/planedepth_b200.h
+ABI_VERSION = 4  # PD_ABI_VERSION in include/planedepth_b200.h
 PD_STATS_PLAIN, PD_STATS_MIXTURE = 2, 4
 
 EXPORTS = [
     "pd_version", "pd_last_error", "pd_launch_count", "pd_reset_launch_count",
-    "pd_warp_composite_workspace_bytes", "pd_warp_composite_fwd", "pd_warp_composite_bwd",
+    "pd_warp_composite_workspace_bytes", "pd_warp_composite_stats_bytes", "pd_warp_composite_fwd", "pd_warp_composite_bwd",
     "pd_photometric_workspace_bytes", "pd_photometric_fwd", "pd_photometric_bwd", "pd_debug_roundtrip",
 ]
 
@@ -139,6 +139,8 @@ def lib() -> C.CDLL:
     L.pd_reset_launch_count.restype = None
     L.pd_warp_composite_workspace_bytes.restype = C.c_size_t
     L.pd_warp_composite_workspace_bytes.argtypes = [C.POINTER(WarpDesc)]
+    L.pd_warp_composite_stats_bytes.restype = C.c_size_t
+    L.pd_warp_composite_stats_bytes.argtypes = [C.POINTER(WarpDesc)]
     L.pd_warp_composite_fwd.restype = C.c_int
     L.pd_warp_composite_fwd.argtypes = [C.POINTER(WarpDesc), C.POINTER(WarpIn), C.POINTER(WarpOut), C.c_void_p, C.c_void_p]
     L.pd_warp_composite_bwd.restype = C.c_int

@@ -82,6 +82,20 @@ pd::WarpParams make_params(const pd_warp_desc* d, const pd_warp_in* in) {
     return p;
 }
 
+// Dense-mask row summary behind the saved statistics (WarpParams::mask_rows): kept when the streamed kernels would
+// run with a dense fp32 mask and a warp covers exactly one 128-pixel segment of one row (4-pixel threads).
+size_t stats_floats(const pd_warp_desc* d) { return (size_t)d->B * (d->mixture ? PD_STATS_MIXTURE : PD_STATS_PLAIN) * d->H * d->W; }
+size_t mask_summary_bytes(const pd_warp_desc* d) { return (size_t)d->B * d->H * ((d->W + 127) / 128) * 2 * sizeof(unsigned long long); }
+
+void attach_mask_summary(pd::WarpParams& p, const float* stats) {
+    const pd_warp_desc& d = p.d;
+    p.mask_rows = nullptr;
+    p.mask_segs = d.W / 128;
+    const bool keep = d.warp_type == PD_WARP_DISP && p.in.mask && d.mask_dtype == PD_MASK_F32 && d.mask_stride.x == 1 && d.N <= 64 &&
+                      d.W % 128 == 0 && d.W / 4 <= 320 && !pd::ts::stream_env_int("PD_STREAM_PX8", 0) && !getenv("PD_NO_MASK_SUMMARY");
+    if (keep) p.mask_rows = reinterpret_cast<unsigned long long*>(const_cast<float*>(stats) + stats_floats(&d));
+}
+
 int64_t strided_extent(const pd_strides4& s, int B, int N, int H, int W) {
     return (int64_t)(B - 1) * s.b + (int64_t)(N - 1) * s.n + (int64_t)(H - 1) * s.y + (int64_t)(W - 1) * s.x + 1;
 }
@@ -182,6 +196,11 @@ size_t pd_warp_composite_workspace_bytes(const pd_warp_desc* desc) {
     return 0;
 }
 
+size_t pd_warp_composite_stats_bytes(const pd_warp_desc* d) {
+    if (!d || d->B < 1 || d->H < 1 || d->W < 1) return 0;
+    return stats_floats(d) * sizeof(float) + mask_summary_bytes(d);
+}
+
 int pd_warp_composite_fwd(const pd_warp_desc* d, const pd_warp_in* in, pd_warp_out* out, void* workspace, pd_stream_t stream) {
     (void)workspace;
     int rc = validate_warp(d, in);
@@ -192,9 +211,14 @@ int pd_warp_composite_fwd(const pd_warp_desc* d, const pd_warp_in* in, pd_warp_o
     cudaStream_t st = (cudaStream_t)stream;
     pd::WarpParams p = make_params(d, in);
     p.out = *out;
+    attach_mask_summary(p, out->stats);
     const bool debug = out->rgb_rec_layered || out->logit_rec || out->probability_rec || out->sigma_rec || out->pi_rec;
     if (!debug && !exact_coords(d) && pd::ts::stream_path_supported(p) && pd::ts::launch_fwd_stream(p, st))
         return check_launch("rows_fwd_stream");
+    if (p.mask_rows) {  // the other forward kernels keep no summary: all-clear sets mean "read the mask"
+        cudaError_t e = cudaMemsetAsync(p.mask_rows, 0, mask_summary_bytes(d), st);
+        if (e != cudaSuccess) return fail(PD_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    }
     if (!debug && pd::rows_path_supported(p)) {
         pd::launch_fwd_rows(p, st);
         return check_launch("warp_composite_fwd_rows");
@@ -220,6 +244,7 @@ int pd_warp_composite_bwd(const pd_warp_desc* d, const pd_warp_in* in, const pd_
     cudaStream_t st = (cudaStream_t)stream;
     pd::WarpParams p = make_params(d, in);
     p.out = *saved;
+    attach_mask_summary(p, saved->stats);
     p.gout = *gout;
     p.gin = *gin;
     if (!d->mixture) p.gin.g_sigma = nullptr;

@@ -41,7 +41,8 @@ struct __align__(16) PlaneCoef {
     float wl1;       // wc1 * log2(e)
     float m;         // row mask value (1 when the mask is dense or absent)
     int k4;          // k0 * 4: the shift in bytes
-    float pad1;
+    float skip;      // dense mask, backward: != 0 when the row summary says the mask row is all ones (m = 1) or all
+                     // zeros (m = 0), so the row is neither copied nor read
 };
 
 struct StreamCfg {
@@ -232,14 +233,14 @@ __device__ __forceinline__ void zero_pads(const Smem& s, const StreamCfg& c, int
 }
 
 // per-(row, plane) coefficients of row group g (executed by the 32 lanes of the producer warp)
-template <int MASKMODE>
+template <int MASKMODE, bool SUMMARY>
 __device__ __forceinline__ void stage_coef(const WarpParams& p, const StreamCfg& c, PlaneCoef* coef, int g, int rows_total) {
     const int N = p.d.N, H = p.d.H, W = p.d.W;
     for (int idx = threadIdx.x & 31; idx < c.rpc * N; idx += 32) {
         const int r = idx / N, n = idx - r * N;
         const int row = g * c.rpc + r;
         PlaneCoef k;
-        k.k0 = W + 16, k.wc0 = k.wc1 = k.wl0 = k.wl1 = 0.0f, k.m = 0.0f, k.pad1 = 0.0f;
+        k.k0 = W + 16, k.wc0 = k.wc1 = k.wl0 = k.wl1 = 0.0f, k.m = 0.0f, k.skip = 0.0f;
         if (row < rows_total) {
             const int b = row / H, y = row - b * H;
             const float d = __ldg(p.in.disp + soff(p.d.disp_stride, b, n, y, 0));
@@ -247,7 +248,14 @@ __device__ __forceinline__ void stage_coef(const WarpParams& p, const StreamCfg&
             const float kf = floorf(sd);
             const bool sane = fabsf(sd) < (float)(W + 8);  // otherwise every tap is out of range
             const float w1 = sane ? sd - kf : 0.0f;
-            const float m = (MASKMODE == SMASK_ROW) ? load_mask(p.in.mask, p.d.mask_dtype, soff(p.d.mask_stride, b, n, y, 0)) : 1.0f;
+            float m = (MASKMODE == SMASK_ROW) ? load_mask(p.in.mask, p.d.mask_dtype, soff(p.d.mask_stride, b, n, y, 0)) : 1.0f;
+            if (SUMMARY && MASKMODE == SMASK_DENSE && p.mask_rows) {
+                const unsigned long long* mr = p.mask_rows + (size_t)row * p.mask_segs * 2;
+                unsigned long long ones = ~0ull, zeros = ~0ull;
+                for (int sgm = 0; sgm < p.mask_segs; ++sgm) ones &= __ldg(mr + 2 * sgm), zeros &= __ldg(mr + 2 * sgm + 1);
+                if ((zeros >> n) & 1ull) m = 0.0f, k.skip = 1.0f;
+                else if ((ones >> n) & 1ull) k.skip = 1.0f;
+            }
             k.k0 = sane ? (int)kf : W + 16;
             k.m = m;
             k.wc1 = w1 * m;
@@ -265,7 +273,7 @@ __device__ __forceinline__ void stage_coef(const WarpParams& p, const StreamCfg&
 // arms the stage's full barrier with the byte count and issues one bulk copy per (plane, row, stream).
 // Releases that make reuse safe: the stage's empty barrier is armed by the consumers after their last read
 // of block jb - nst; with nst <= nblk that also covers the coefficient / source-row buffers of group it - 2.
-template <bool MIX, int MASKMODE>
+template <bool MIX, int MASKMODE, bool SUMMARY>
 __device__ __forceinline__ void producer_loop(const WarpParams& p, const StreamCfg& c, const Smem& s, int nit) {
     constexpr bool DENSE = (MASKMODE == SMASK_DENSE);
     const int lane = threadIdx.x & 31;
@@ -280,7 +288,7 @@ __device__ __forceinline__ void producer_loop(const WarpParams& p, const StreamC
         for (int j = 0; j < c.nblk; ++j) {
             if (use > 0) mbar_wait(s.bars + BAR_EMPTY + stage, (use - 1) & 1);
             if (j == 0) {
-                stage_coef<MASKMODE>(p, c, s.coef + (size_t)(it & 1) * c.rpc * N, g, rows_total);
+                stage_coef<MASKMODE, SUMMARY>(p, c, s.coef + (size_t)(it & 1) * c.rpc * N, g, rows_total);
                 __syncwarp();
                 if (lane == 0) {
                     uint64_t* bar = s.bars + BAR_SRC + (it & 1);
@@ -296,7 +304,13 @@ __device__ __forceinline__ void producer_loop(const WarpParams& p, const StreamC
             if (lane == 0) {
                 uint64_t* bar = s.bars + BAR_FULL + stage;
                 const int n0 = j * c.hs, n1 = min(N, n0 + c.hs);
-                mbar_expect_tx(bar, (uint32_t)((n1 - n0) * nrows * streams) * rowbytes);
+                const bool summary = SUMMARY && DENSE && p.mask_rows;
+                const PlaneCoef* cf = s.coef + (size_t)(it & 1) * c.rpc * N;
+                int copies = (n1 - n0) * nrows * streams;
+                if (summary)  // mask rows the summary describes stay in HBM
+                    for (int r = 0; r < nrows; ++r)
+                        for (int n = n0; n < n1; ++n) copies -= (cf[r * N + n].skip != 0.0f);
+                mbar_expect_tx(bar, (uint32_t)copies * rowbytes);
                 for (int r = 0; r < nrows; ++r) {
                     const int row = row0 + r, b = row / H, y = row - b * H;
                     int64_t off = (((int64_t)b * N + n0) * H + y) * W;
@@ -304,7 +318,8 @@ __device__ __forceinline__ void producer_loop(const WarpParams& p, const StreamC
                     for (int n = n0; n < n1; ++n) {
                         tma_row(s.lring + slot, p.in.logits + off, rowbytes, bar);
                         if (MIX) tma_row(s.sring + slot, p.in.sigma + off, rowbytes, bar);
-                        if (DENSE) tma_row(s.mring + slot, reinterpret_cast<const float*>(p.in.mask) + soff(p.d.mask_stride, b, n, y, 0), rowbytes, bar);
+                        if (DENSE && !(summary && cf[r * N + n].skip != 0.0f))
+                            tma_row(s.mring + slot, reinterpret_cast<const float*>(p.in.mask) + soff(p.d.mask_stride, b, n, y, 0), rowbytes, bar);
                         off += p.hw;
                         slot += (size_t)c.rpc * c.pitch;
                     }
@@ -319,7 +334,7 @@ __device__ __forceinline__ PlaneCoef load_coef(uint32_t a32) {
     const float4 a = lds128(a32);
     const float4 b = lds128(a32 + 16);
     PlaneCoef k;
-    k.k0 = __float_as_int(a.x), k.wc0 = a.y, k.wc1 = a.z, k.wl0 = a.w, k.wl1 = b.x, k.m = b.y, k.k4 = __float_as_int(b.z);
+    k.k0 = __float_as_int(a.x), k.wc0 = a.y, k.wc1 = a.z, k.wl0 = a.w, k.wl1 = b.x, k.m = b.y, k.k4 = __float_as_int(b.z), k.skip = b.w;
     return k;
 }
 
@@ -333,6 +348,14 @@ __device__ __forceinline__ bool all_ones(const float (&m)[PX]) {
 #pragma unroll
     for (int i = 0; i < PX; ++i) acc &= __float_as_uint(m[i]), orr |= __float_as_uint(m[i]);
     return acc == 0x3f800000u && orr == 0x3f800000u;
+}
+
+template <int PX>
+__device__ __forceinline__ bool all_zeros(const float (&m)[PX]) {
+    unsigned orr = 0u;
+#pragma unroll
+    for (int i = 0; i < PX; ++i) orr |= __float_as_uint(m[i]);
+    return orr == 0u;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -479,12 +502,14 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
     __syncthreads();
     const int nit = (cfg.ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if ((int)threadIdx.x >= cfg.nc) {
-        producer_loop<MIX, MASKMODE>(p, cfg, s, nit);
+        producer_loop<MIX, MASKMODE, false>(p, cfg, s, nit);
         return;
     }
     const int lane = threadIdx.x & 31;
     const int r = threadIdx.x / cfg.tpr;
     const int x0 = (threadIdx.x - r * cfg.tpr) * PX;
+    // dense-mask row summary (host enables it only when a warp covers one 128-pixel segment of one row)
+    const bool track = DENSE && p.mask_rows != nullptr;
     // 32-bit shared-window addresses of the row interiors (byte units from here on)
     const uint32_t bars = smem_u32(s.bars), coef0 = smem_u32(s.coef), src0 = smem_u32(s.src + PAD), lring0 = smem_u32(s.lring + PAD);
     const uint32_t pitch4 = (uint32_t)pitch * 4u, rowpitch4 = (uint32_t)rpc * pitch4;
@@ -524,6 +549,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
         uint32_t coef_a = coef0 + (uint32_t)(((it & 1) * rpc + r) * N) * (uint32_t)sizeof(PlaneCoef);
         const uint32_t srow = src0 + (uint32_t)(((it & 1) * rpc + r) * 3) * pitch4;
         mbar_wait(bars + 8 * (BAR_SRC + (it & 1)), (it >> 1) & 1);
+        unsigned long long seg_ones = ~0ull, seg_zeros = ~0ull;
 
         for (int j = 0; j < NB; ++j) {
             // every consumer thread waits (also idle ones: a warp must not run ahead of the ring and arrive twice
@@ -539,6 +565,11 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
                     if (DENSE) {
                         load_window<PX>(lrow + mdelta + x04, mm);
                         perpix = !all_ones<PX>(mm);
+                        if (track) {
+                            const unsigned long long bit = 1ull << (j * hs + q);
+                            if (!__all_sync(0xffffffffu, !perpix)) seg_ones &= ~bit;
+                            if (!__all_sync(0xffffffffu, all_zeros<PX>(mm))) seg_zeros &= ~bit;
+                        }
                     }
                     if (DENSE && perpix) fwd_plane_any<MIX, PX, true>(srow, lrow, lrow + sdelta, pitch4, x04 + k.k4, W4, k, mm, acc);
                     else fwd_plane_any<MIX, PX, false>(srow, lrow, lrow + sdelta, pitch4, x04 + k.k4, W4, k, mm, acc);
@@ -549,6 +580,10 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
             if (++stage == cfg.nst) stage = 0, fphase ^= 1;
         }
         if (!active) continue;
+        if (track && lane == 0) {
+            unsigned long long* mr = p.mask_rows + ((size_t)row * p.mask_segs + (x0 >> 7)) * 2;
+            mr[0] = seg_ones, mr[1] = seg_zeros;
+        }
         float o0[PX], o1[PX], o2[PX];
 #pragma unroll
         for (int i = 0; i < PX; ++i) {
@@ -746,7 +781,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
     __syncthreads();
     const int nit = (cfg.ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if ((int)threadIdx.x >= cfg.nc) {
-        producer_loop<MIX, MASKMODE>(p, cfg, s, nit);
+        producer_loop<MIX, MASKMODE, true>(p, cfg, s, nit);
         return;
     }
     const int lane = threadIdx.x & 31;
@@ -830,7 +865,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
                         const PlaneCoef k = load_coef(coef_a);
                         float mm[PX] = {};
                         bool perpix = false;
-                        if (DENSE) {
+                        if (DENSE && k.skip == 0.0f) {
                             load_window<PX>(lrow + mdelta + x04, mm);
                             perpix = !all_ones<PX>(mm);
                         }

@@ -95,9 +95,8 @@ class _WarpComposite(torch.autograd.Function):
             desc.mask_dtype = L.PD_MASK_F32 if mask.dtype == torch.float32 else L.PD_MASK_U8
         tin = L.WarpIn(src=_ptr(src), tgt=_ptr(tgt), logits=_ptr(logits), sigma=_ptr(sigma), disp=_ptr(disp), mask=_ptr(mask),
                        hmat=_ptr(hmat), cam=_ptr(cam))
-        ns = L.PD_STATS_MIXTURE if cfg.mixture else L.PD_STATS_PLAIN
         rgb_rec = torch.empty(B, 3, H, W, device=dev, dtype=torch.float32)
-        stats = torch.empty(B, ns, H, W, device=dev, dtype=torch.float32)
+        stats = torch.empty((lib.pd_warp_composite_stats_bytes(C.byref(desc)) + 3) // 4, device=dev, dtype=torch.float32)
         nll = torch.empty(B, 1, H, W, device=dev, dtype=torch.float32) if cfg.mixture else None
         nll_auto = torch.empty(B, 1, H, W, device=dev, dtype=torch.float32) if (cfg.mixture and cfg.automask) else None
         out = L.WarpOut(rgb_rec=_ptr(rgb_rec), stats=_ptr(stats), nll=_ptr(nll), nll_auto=_ptr(nll_auto))

@@ -77,7 +77,7 @@ def test_cuda_matches_reference_golden(name, mode):
             check(g, want, grad_tol(k[5:]) * scale, k, allow_frac=2e-3)
 
 
-def synth_case(B, N, H, W, warp, mixture, automask, frames, mask_novel, seed, dense=False, n_xz=0, u8mask=False, compact=False):
+def synth_case(B, N, H, W, warp, mixture, automask, frames, mask_novel, seed, dense=False, n_xz=0, u8mask=False, compact=False, holes=False):
     """Fresh seeded inputs in the reference's dict layout (CPU tensors)."""
     from types import SimpleNamespace
 
@@ -117,6 +117,10 @@ def synth_case(B, N, H, W, warp, mixture, automask, frames, mask_novel, seed, de
         disp_layered = disp_layered + bump
     if u8mask:
         padding_mask = (rnd(B, N, H, W) > 0.1)
+    if holes:  # dense fp32 mask with all-one rows, all-zero rows and rows with scattered zeros (row summary of the streamed kernels)
+        padding_mask = torch.ones(B, N, H, W)
+        padding_mask[:, 1::3, ::2] = 0.0
+        padding_mask[:, ::4] *= (rnd(B, (N + 3) // 4, H, W) > 0.2).float()
     if compact:  # row-constant mask stored with a zero x stride (what a fused decoder tail would hand over)
         padding_mask = padding_mask[..., :1].contiguous().expand(-1, -1, -1, W)
     logits = (1.5 * torch.randn(B, N, H, W, generator=g)).requires_grad_(True)
@@ -157,6 +161,8 @@ CONFIGS = [
     (3, 11, 10, 200, "disp_warp", False, True, [], True, dict(n_xz=3)),          # rows of several images share a CTA
     (2, 9, 12, 72, "disp_warp", True, True, [], False, dict(n_xz=3, compact=True)),  # zero-stride row mask
     (2, 9, 12, 72, "disp_warp", False, False, [], False, dict(n_xz=3, compact=True)),
+    (2, 9, 6, 256, "disp_warp", False, False, [], False, dict(holes=True)),      # dense mask, 128-pixel segments: row summary
+    (1, 7, 5, 128, "disp_warp", True, True, [], True, dict(holes=True)),
 ]
 
 
@@ -230,7 +236,7 @@ def test_cuda_matches_oracle(idx, photometric, mode):
 
 
 @pytest.mark.parametrize("mode", ["fused", "fused_exact"])
-@pytest.mark.parametrize("idx", [2, 8, 11])
+@pytest.mark.parametrize("idx", [2, 8, 10, 11])
 def test_rowwise_promise_on_dense_cat_layout(idx, mode):
     """49+14-style plane sets arrive as a dense [B,N,H,W] cat (depth_decoder.py:181): with the integrator's
     promise ``disp_rowwise`` the fast path reads column 0 and hands the gradient back spread over x."""
