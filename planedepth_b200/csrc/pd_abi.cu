@@ -82,18 +82,15 @@ pd::WarpParams make_params(const pd_warp_desc* d, const pd_warp_in* in) {
     return p;
 }
 
-// Dense-mask row summary behind the saved statistics (WarpParams::mask_rows): kept when the streamed kernels would
-// run with a dense fp32 mask and a warp covers exactly one 128-pixel segment of one row (4-pixel threads).
+// Dense-mask row summary behind the saved statistics (WarpParams::mask_rows): per image row two 64-bit sets over planes.
 size_t stats_floats(const pd_warp_desc* d) { return (size_t)d->B * (d->mixture ? PD_STATS_MIXTURE : PD_STATS_PLAIN) * d->H * d->W; }
-size_t mask_summary_bytes(const pd_warp_desc* d) { return (size_t)d->B * d->H * ((d->W + 127) / 128) * 2 * sizeof(unsigned long long); }
+size_t mask_summary_bytes(const pd_warp_desc* d) { return (size_t)d->B * d->H * 2 * sizeof(unsigned long long); }
 
 void attach_mask_summary(pd::WarpParams& p, const float* stats) {
     const pd_warp_desc& d = p.d;
-    p.mask_rows = nullptr;
-    p.mask_segs = d.W / 128;
     const bool keep = d.warp_type == PD_WARP_DISP && p.in.mask && d.mask_dtype == PD_MASK_F32 && d.mask_stride.x == 1 && d.N <= 64 &&
-                      d.W % 128 == 0 && d.W / 4 <= 320 && !pd::ts::stream_env_int("PD_STREAM_PX8", 0) && !getenv("PD_NO_MASK_SUMMARY");
-    if (keep) p.mask_rows = reinterpret_cast<unsigned long long*>(const_cast<float*>(stats) + stats_floats(&d));
+                      (stats_floats(&d) % 2 == 0) && !getenv("PD_NO_MASK_SUMMARY");
+    p.mask_rows = keep ? reinterpret_cast<unsigned long long*>(const_cast<float*>(stats) + stats_floats(&d)) : nullptr;
 }
 
 int64_t strided_extent(const pd_strides4& s, int B, int N, int H, int W) {

@@ -57,9 +57,14 @@ struct StreamCfg {
 };
 
 constexpr int MAX_STAGES = 8;
-constexpr int BAR_FULL = 0, BAR_EMPTY = MAX_STAGES, BAR_SRC = 2 * MAX_STAGES, BAR_BYTES = 256;
+constexpr int BAR_FULL = 0, BAR_EMPTY = MAX_STAGES, BAR_SRC = 2 * MAX_STAGES, BAR_SUMM = 2 * MAX_STAGES + 2, BAR_BYTES = 384;
+constexpr int MAX_RPC = 8;  // rows per CTA iteration; BAR_SUMM holds 2 * MAX_RPC 64-bit plane sets of the row summary
 
-enum { SMASK_ROW = 0, SMASK_DENSE = 1 };
+// SMASK_ROW: no mask or one value per (row, plane), folded into the coefficients.  SMASK_DENSE: fp32 mask rows travel
+// through the TMA ring next to the logits.  SMASK_SUMMARY (backward only): dense mask whose rows the forward pass has
+// summarised (WarpParams::mask_rows): all-ones / all-zero rows are folded into the coefficients like SMASK_ROW, the
+// remaining rows are read from global memory by the consumers; no mask ring.
+enum { SMASK_ROW = 0, SMASK_DENSE = 1, SMASK_SUMMARY = 2 };
 
 // ------------------------------------------------------------------------------------------------
 // mbarrier / TMA primitives (PTX; SASS: SYNCS / UBLKCP)
@@ -233,7 +238,7 @@ __device__ __forceinline__ void zero_pads(const Smem& s, const StreamCfg& c, int
 }
 
 // per-(row, plane) coefficients of row group g (executed by the 32 lanes of the producer warp)
-template <int MASKMODE, bool SUMMARY>
+template <int MASKMODE>
 __device__ __forceinline__ void stage_coef(const WarpParams& p, const StreamCfg& c, PlaneCoef* coef, int g, int rows_total) {
     const int N = p.d.N, H = p.d.H, W = p.d.W;
     for (int idx = threadIdx.x & 31; idx < c.rpc * N; idx += 32) {
@@ -249,10 +254,8 @@ __device__ __forceinline__ void stage_coef(const WarpParams& p, const StreamCfg&
             const bool sane = fabsf(sd) < (float)(W + 8);  // otherwise every tap is out of range
             const float w1 = sane ? sd - kf : 0.0f;
             float m = (MASKMODE == SMASK_ROW) ? load_mask(p.in.mask, p.d.mask_dtype, soff(p.d.mask_stride, b, n, y, 0)) : 1.0f;
-            if (SUMMARY && MASKMODE == SMASK_DENSE && p.mask_rows) {
-                const unsigned long long* mr = p.mask_rows + (size_t)row * p.mask_segs * 2;
-                unsigned long long ones = ~0ull, zeros = ~0ull;
-                for (int sgm = 0; sgm < p.mask_segs; ++sgm) ones &= __ldg(mr + 2 * sgm), zeros &= __ldg(mr + 2 * sgm + 1);
+            if (MASKMODE == SMASK_SUMMARY) {
+                const unsigned long long ones = __ldg(p.mask_rows + 2 * (size_t)row), zeros = __ldg(p.mask_rows + 2 * (size_t)row + 1);
                 if ((zeros >> n) & 1ull) m = 0.0f, k.skip = 1.0f;
                 else if ((ones >> n) & 1ull) k.skip = 1.0f;
             }
@@ -273,22 +276,64 @@ __device__ __forceinline__ void stage_coef(const WarpParams& p, const StreamCfg&
 // arms the stage's full barrier with the byte count and issues one bulk copy per (plane, row, stream).
 // Releases that make reuse safe: the stage's empty barrier is armed by the consumers after their last read
 // of block jb - nst; with nst <= nblk that also covers the coefficient / source-row buffers of group it - 2.
-template <bool MIX, int MASKMODE, bool SUMMARY>
+//
+// SCAN (forward, dense mask): between two issues the otherwise idle producer warp reads the mask rows of the
+// previous block out of the ring and records, per image row, which planes' mask rows are all ones / all zeros
+// (WarpParams::mask_rows); it then counts as one more reader of the stage (the empty barriers expect it).
+struct ScanBlock {
+    int stage, phase, row0, nrows, n0, n1, last;
+};
+
+__device__ __forceinline__ void scan_mask_block(const WarpParams& p, const StreamCfg& c, const Smem& s, const ScanBlock& k) {
+    const int lane = threadIdx.x & 31, W4 = p.d.W / 4;
+    unsigned long long* sets = reinterpret_cast<unsigned long long*>(s.bars + BAR_SUMM);  // [rpc][2], lane 0 only
+    mbar_wait(s.bars + BAR_FULL + k.stage, (uint32_t)k.phase);
+    for (int r = 0; r < k.nrows; ++r) {
+        unsigned long long ones = 0ull, zeros = 0ull;
+        if (k.n0 != 0) ones = sets[2 * r], zeros = sets[2 * r + 1];
+        for (int n = k.n0; n < k.n1; ++n) {
+            const float* row = s.mring + ((size_t)(k.stage * c.hs + (n - k.n0)) * c.rpc + r) * c.pitch + PAD;
+            unsigned band = 0xffffffffu, bor = 0u;
+            for (int i = lane; i < W4; i += 32) {
+                const float4 v = lds128(row + 4 * i);
+                band &= __float_as_uint(v.x) & __float_as_uint(v.y) & __float_as_uint(v.z) & __float_as_uint(v.w);
+                bor |= __float_as_uint(v.x) | __float_as_uint(v.y) | __float_as_uint(v.z) | __float_as_uint(v.w);
+            }
+            band = __reduce_and_sync(0xffffffffu, band);
+            bor = __reduce_or_sync(0xffffffffu, bor);
+            if (band == 0x3f800000u && bor == 0x3f800000u) ones |= 1ull << n;
+            if (bor == 0u) zeros |= 1ull << n;
+        }
+        if (lane == 0) {
+            if (k.last) p.mask_rows[2 * (size_t)(k.row0 + r)] = ones, p.mask_rows[2 * (size_t)(k.row0 + r) + 1] = zeros;
+            else sets[2 * r] = ones, sets[2 * r + 1] = zeros;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(s.bars + BAR_EMPTY + k.stage);
+}
+
+template <bool MIX, int MASKMODE, bool SCAN>
 __device__ __forceinline__ void producer_loop(const WarpParams& p, const StreamCfg& c, const Smem& s, int nit) {
     constexpr bool DENSE = (MASKMODE == SMASK_DENSE);
     const int lane = threadIdx.x & 31;
     const int W = p.d.W, H = p.d.H, N = p.d.N, rows_total = p.d.B * H;
     const uint32_t rowbytes = (uint32_t)(W * sizeof(float));
     const int streams = 1 + (MIX ? 1 : 0) + (DENSE ? 1 : 0);
+    const bool scan = SCAN && DENSE && p.mask_rows != nullptr;
+    ScanBlock prev;
+    prev.stage = -1;
     int stage = 0, use = 0;  // use = how many times the ring wrapped
     for (int it = 0; it < nit; ++it) {
         const int g = blockIdx.x + it * gridDim.x;
         const int row0 = g * c.rpc;
         const int nrows = min(c.rpc, rows_total - row0);
         for (int j = 0; j < c.nblk; ++j) {
+            // with a single stage the previous block must be scanned (and released) before its stage can be reused
+            if (scan && c.nst == 1 && prev.stage >= 0) scan_mask_block(p, c, s, prev), prev.stage = -1;
             if (use > 0) mbar_wait(s.bars + BAR_EMPTY + stage, (use - 1) & 1);
             if (j == 0) {
-                stage_coef<MASKMODE, SUMMARY>(p, c, s.coef + (size_t)(it & 1) * c.rpc * N, g, rows_total);
+                stage_coef<MASKMODE>(p, c, s.coef + (size_t)(it & 1) * c.rpc * N, g, rows_total);
                 __syncwarp();
                 if (lane == 0) {
                     uint64_t* bar = s.bars + BAR_SRC + (it & 1);
@@ -301,16 +346,10 @@ __device__ __forceinline__ void producer_loop(const WarpParams& p, const StreamC
                     }
                 }
             }
+            const int n0 = j * c.hs, n1 = min(N, n0 + c.hs);
             if (lane == 0) {
                 uint64_t* bar = s.bars + BAR_FULL + stage;
-                const int n0 = j * c.hs, n1 = min(N, n0 + c.hs);
-                const bool summary = SUMMARY && DENSE && p.mask_rows;
-                const PlaneCoef* cf = s.coef + (size_t)(it & 1) * c.rpc * N;
-                int copies = (n1 - n0) * nrows * streams;
-                if (summary)  // mask rows the summary describes stay in HBM
-                    for (int r = 0; r < nrows; ++r)
-                        for (int n = n0; n < n1; ++n) copies -= (cf[r * N + n].skip != 0.0f);
-                mbar_expect_tx(bar, (uint32_t)copies * rowbytes);
+                mbar_expect_tx(bar, (uint32_t)((n1 - n0) * nrows * streams) * rowbytes);
                 for (int r = 0; r < nrows; ++r) {
                     const int row = row0 + r, b = row / H, y = row - b * H;
                     int64_t off = (((int64_t)b * N + n0) * H + y) * W;
@@ -318,16 +357,20 @@ __device__ __forceinline__ void producer_loop(const WarpParams& p, const StreamC
                     for (int n = n0; n < n1; ++n) {
                         tma_row(s.lring + slot, p.in.logits + off, rowbytes, bar);
                         if (MIX) tma_row(s.sring + slot, p.in.sigma + off, rowbytes, bar);
-                        if (DENSE && !(summary && cf[r * N + n].skip != 0.0f))
-                            tma_row(s.mring + slot, reinterpret_cast<const float*>(p.in.mask) + soff(p.d.mask_stride, b, n, y, 0), rowbytes, bar);
+                        if (DENSE) tma_row(s.mring + slot, reinterpret_cast<const float*>(p.in.mask) + soff(p.d.mask_stride, b, n, y, 0), rowbytes, bar);
                         off += p.hw;
                         slot += (size_t)c.rpc * c.pitch;
                     }
                 }
             }
+            if (scan) {
+                if (prev.stage >= 0) scan_mask_block(p, c, s, prev);
+                prev.stage = stage, prev.phase = use & 1, prev.row0 = row0, prev.nrows = nrows, prev.n0 = n0, prev.n1 = n1, prev.last = (j == c.nblk - 1);
+            }
             if (++stage == c.nst) stage = 0, ++use;
         }
     }
+    if (scan && prev.stage >= 0) scan_mask_block(p, c, s, prev);
 }
 
 __device__ __forceinline__ PlaneCoef load_coef(uint32_t a32) {
@@ -348,14 +391,6 @@ __device__ __forceinline__ bool all_ones(const float (&m)[PX]) {
 #pragma unroll
     for (int i = 0; i < PX; ++i) acc &= __float_as_uint(m[i]), orr |= __float_as_uint(m[i]);
     return acc == 0x3f800000u && orr == 0x3f800000u;
-}
-
-template <int PX>
-__device__ __forceinline__ bool all_zeros(const float (&m)[PX]) {
-    unsigned orr = 0u;
-#pragma unroll
-    for (int i = 0; i < PX; ++i) orr |= __float_as_uint(m[i]);
-    return orr == 0u;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -491,9 +526,10 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
     const Smem s = carve(smem_raw, cfg, N, MIX, DENSE, 0, false);
     zero_pads(s, cfg, W);
     if (threadIdx.x == 0) {
+        const uint32_t readers = (uint32_t)(cfg.nc / 32) + ((DENSE && p.mask_rows) ? 1u : 0u);  // + the scanning producer warp
         for (int i = 0; i < cfg.nst; ++i) {
             mbar_init(s.bars + BAR_FULL + i, 1);
-            mbar_init(s.bars + BAR_EMPTY + i, (uint32_t)(cfg.nc / 32));
+            mbar_init(s.bars + BAR_EMPTY + i, readers);
         }
         mbar_init(s.bars + BAR_SRC, 1);
         mbar_init(s.bars + BAR_SRC + 1, 1);
@@ -502,14 +538,12 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
     __syncthreads();
     const int nit = (cfg.ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if ((int)threadIdx.x >= cfg.nc) {
-        producer_loop<MIX, MASKMODE, false>(p, cfg, s, nit);
+        producer_loop<MIX, MASKMODE, true>(p, cfg, s, nit);
         return;
     }
     const int lane = threadIdx.x & 31;
     const int r = threadIdx.x / cfg.tpr;
     const int x0 = (threadIdx.x - r * cfg.tpr) * PX;
-    // dense-mask row summary (host enables it only when a warp covers one 128-pixel segment of one row)
-    const bool track = DENSE && p.mask_rows != nullptr;
     // 32-bit shared-window addresses of the row interiors (byte units from here on)
     const uint32_t bars = smem_u32(s.bars), coef0 = smem_u32(s.coef), src0 = smem_u32(s.src + PAD), lring0 = smem_u32(s.lring + PAD);
     const uint32_t pitch4 = (uint32_t)pitch * 4u, rowpitch4 = (uint32_t)rpc * pitch4;
@@ -549,7 +583,6 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
         uint32_t coef_a = coef0 + (uint32_t)(((it & 1) * rpc + r) * N) * (uint32_t)sizeof(PlaneCoef);
         const uint32_t srow = src0 + (uint32_t)(((it & 1) * rpc + r) * 3) * pitch4;
         mbar_wait(bars + 8 * (BAR_SRC + (it & 1)), (it >> 1) & 1);
-        unsigned long long seg_ones = ~0ull, seg_zeros = ~0ull;
 
         for (int j = 0; j < NB; ++j) {
             // every consumer thread waits (also idle ones: a warp must not run ahead of the ring and arrive twice
@@ -565,11 +598,6 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
                     if (DENSE) {
                         load_window<PX>(lrow + mdelta + x04, mm);
                         perpix = !all_ones<PX>(mm);
-                        if (track) {
-                            const unsigned long long bit = 1ull << (j * hs + q);
-                            if (!__all_sync(0xffffffffu, !perpix)) seg_ones &= ~bit;
-                            if (!__all_sync(0xffffffffu, all_zeros<PX>(mm))) seg_zeros &= ~bit;
-                        }
                     }
                     if (DENSE && perpix) fwd_plane_any<MIX, PX, true>(srow, lrow, lrow + sdelta, pitch4, x04 + k.k4, W4, k, mm, acc);
                     else fwd_plane_any<MIX, PX, false>(srow, lrow, lrow + sdelta, pitch4, x04 + k.k4, W4, k, mm, acc);
@@ -580,10 +608,6 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
             if (++stage == cfg.nst) stage = 0, fphase ^= 1;
         }
         if (!active) continue;
-        if (track && lane == 0) {
-            unsigned long long* mr = p.mask_rows + ((size_t)row * p.mask_segs + (x0 >> 7)) * 2;
-            mr[0] = seg_ones, mr[1] = seg_zeros;
-        }
         float o0[PX], o1[PX], o2[PX];
 #pragma unroll
         for (int i = 0; i < PX; ++i) {
@@ -763,7 +787,7 @@ __device__ __forceinline__ void gather_any(uint32_t drow, int at4, int W4, float
 template <bool MIX, int MASKMODE, bool WANT_DISP, int PX, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParams p, const StreamCfg cfg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr bool DENSE = (MASKMODE == SMASK_DENSE);
+    constexpr bool DENSE = (MASKMODE == SMASK_DENSE), SUMM = (MASKMODE == SMASK_SUMMARY);
     constexpr int NE = MIX ? 2 : 1;
     const int W = p.d.W, H = p.d.H, N = p.d.N, pitch = cfg.pitch, rpc = cfg.rpc, hs = cfg.hs, NB = cfg.nblk;
     const int rows_total = p.d.B * H;
@@ -781,7 +805,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
     __syncthreads();
     const int nit = (cfg.ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if ((int)threadIdx.x >= cfg.nc) {
-        producer_loop<MIX, MASKMODE, true>(p, cfg, s, nit);
+        producer_loop<MIX, MASKMODE, false>(p, cfg, s, nit);
         return;
     }
     const int lane = threadIdx.x & 31;
@@ -865,11 +889,14 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
                         const PlaneCoef k = load_coef(coef_a);
                         float mm[PX] = {};
                         bool perpix = false;
-                        if (DENSE && k.skip == 0.0f) {
+                        if (DENSE) {
                             load_window<PX>(lrow + mdelta + x04, mm);
                             perpix = !all_ones<PX>(mm);
+                        } else if (SUMM && k.skip == 0.0f) {  // a row the summary could not fold away: straight from global memory
+                            load_px_global<PX>(reinterpret_cast<const float*>(p.in.mask) + soff(p.d.mask_stride, b, n0 + q, y, x0), mm);
+                            perpix = !all_ones<PX>(mm);
                         }
-                        if (DENSE && perpix)
+                        if ((DENSE || SUMM) && perpix)
                             gsum = bwd_plane_any<MIX, WANT_DISP, PX, true>(srow, lrow, lrow + sdelta, pitch4, x04 + k.k4, W4, k, mm, c, drow + x04, rowpitch4);
                         else
                             gsum = bwd_plane_any<MIX, WANT_DISP, PX, false>(srow, lrow, lrow + sdelta, pitch4, x04 + k.k4, W4, k, mm, c, drow + x04, rowpitch4);
@@ -1079,8 +1106,13 @@ inline bool launch_bwd_stream_m(const WarpParams& p, cudaStream_t st) {
 }
 
 inline bool launch_bwd_stream(const WarpParams& p, cudaStream_t st) {
-    const int mm = stream_mask_mode(p);
-    if (p.d.mixture) return mm == SMASK_ROW ? launch_bwd_stream_m<true, SMASK_ROW>(p, st) : launch_bwd_stream_m<true, SMASK_DENSE>(p, st);
+    int mm = stream_mask_mode(p);
+    if (mm == SMASK_DENSE && p.mask_rows) mm = SMASK_SUMMARY;  // the forward pass left a row summary of the mask
+    if (p.d.mixture) {
+        if (mm == SMASK_SUMMARY) return launch_bwd_stream_m<true, SMASK_SUMMARY>(p, st);
+        return mm == SMASK_ROW ? launch_bwd_stream_m<true, SMASK_ROW>(p, st) : launch_bwd_stream_m<true, SMASK_DENSE>(p, st);
+    }
+    if (mm == SMASK_SUMMARY) return launch_bwd_stream_m<false, SMASK_SUMMARY>(p, st);
     return mm == SMASK_ROW ? launch_bwd_stream_m<false, SMASK_ROW>(p, st) : launch_bwd_stream_m<false, SMASK_DENSE>(p, st);
 }
 

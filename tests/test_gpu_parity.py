@@ -163,6 +163,7 @@ CONFIGS = [
     (2, 9, 12, 72, "disp_warp", False, False, [], False, dict(n_xz=3, compact=True)),
     (2, 9, 6, 256, "disp_warp", False, False, [], False, dict(holes=True)),      # dense mask, 128-pixel segments: row summary
     (1, 7, 5, 128, "disp_warp", True, True, [], True, dict(holes=True)),
+    (2, 8, 8, 256, "disp_warp", False, True, [], True, dict(n_xz=3)),            # xz masks: all-zero rows above the horizon
 ]
 
 
@@ -236,7 +237,7 @@ def test_cuda_matches_oracle(idx, photometric, mode):
 
 
 @pytest.mark.parametrize("mode", ["fused", "fused_exact"])
-@pytest.mark.parametrize("idx", [2, 8, 10, 11])
+@pytest.mark.parametrize("idx", [2, 8, 11, 16])
 def test_rowwise_promise_on_dense_cat_layout(idx, mode):
     """49+14-style plane sets arrive as a dense [B,N,H,W] cat (depth_decoder.py:181): with the integrator's
     promise ``disp_rowwise`` the fast path reads column 0 and hands the gradient back spread over x."""
