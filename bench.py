@@ -339,7 +339,7 @@ def run_ours(args):
     inputs = batch_gpu.inputs
     leaves = list(leaves_map.values())
     # the integration patch promises x-constant disparities whenever the decoder has no yz planes
-    hp = HotPath(opt, batch.target_sides, pc_net=None, photometric=photometric, disp_rowwise=(getattr(opt, "yz_levels", 0) == 0))
+    hp = HotPath(opt, batch.target_sides, pc_net=None, photometric=photometric, disp_rowwise=(getattr(opt, "yz_levels", 0) == 0) and not args.no_rowwise)
     step = make_step(hp, inputs, outputs, leaves, batch_gpu.attach)
     if args.no_graph:
         class _Eager:
@@ -481,6 +481,7 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * ws, "planes": N, "height": H, "width": W,
                    "photometric": photometric or ("mixture" if opt.use_mixture_loss else "l1"), "layout": args.layout,
+                   "rowwise_promise": bool((getattr(opt, "yz_levels", 0) == 0) and not args.no_rowwise),
                    "parallelism": "dp%d (independent shards, no data-path collective)" % ws, "launch": "eager" if args.no_graph else "cuda_graph replay",
                    "l2": "no flush: per-step working set (logits %.0f MB + grads %.0f MB) exceeds the 126 MB L2" % (
                        B * N * H * W * 4 / 1e6, B * N * H * W * 4 / 1e6),
@@ -505,6 +506,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--layout", default="reference", choices=["reference", "compact"])
+    ap.add_argument("--no-rowwise", action="store_true",
+                    help="withhold the integrator's promise that plane geometry is x-constant (yz_levels == 0): dense masks are streamed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -101,7 +101,7 @@ typedef struct pd_warp_in {
 /* Statistics saved for the backward pass: an opaque buffer of pd_warp_composite_stats_bytes(desc) bytes that only
  * pd_warp_composite_bwd reads.  It holds [B,PD_STATS(mixture),H,W] fp32 per-pixel values — non-mixture: {reference
  * logit * log2(e), sum exp(l - ref)}; mixture: additionally {sum exp/sigma, mixture density sum pi*lap + 1e-7} —
- * followed by a row summary of a dense padding_mask (which rows of which planes are all ones / all zeros) that lets
+ * followed by a row summary of a dense padding_mask (which rows of which planes are all ones) that lets
  * the backward pass leave those mask rows in HBM. */
 #define PD_STATS_PLAIN 2
 #define PD_STATS_MIXTURE 4

@@ -110,12 +110,14 @@ class HotPathMixin:
     #: reproduce the fp32 rounding of the reference's coordinate normalise / un-normalise round trip bit for bit
     #: (PD_FLAG_EXACT_COORDS); the default stereo fast path samples at the exact positions instead
     exact_coords: bool = False
-    #: Promise that ``outputs["disp_layered"]`` does not vary along x even though it is stored densely.  PlaneDepth's
-    #: DepthDecoder emits one disparity per (image, plane) for vertical planes and one per row for xz ground planes
-    #: (depth_decoder.py:153-183) but hands the 49+14 set over as a dense [B,N,H,W] ``cat``; only yz planes
-    #: (--yz_levels > 0, :209-236) vary with x.  An integrator sets this to ``opt.yz_levels == 0``;
-    #: the stereo fast path then reads column 0 only.  Left False, x-constancy is only used when the strides prove it
-    #: (the stride-0 expand of depth_decoder.py:156), and dense tensors take the per-pixel kernels.
+    #: Promise that the plane geometry — ``outputs["disp_layered"]`` and ``outputs["padding_mask"]`` — does not vary along
+    #: x even though it is stored densely.  PlaneDepth's DepthDecoder emits one disparity per (image, plane) for vertical
+    #: planes (mask: ones, depth_decoder.py:157) and one per row for xz ground planes (mask: ``y_grids >= 1e-7``, :168)
+    #: but hands the 49+14 set over as dense [B,N,H,W] ``cat`` s (:181-182); only yz planes (--yz_levels > 0, :209-236)
+    #: vary with x.  An integrator sets this to ``opt.yz_levels == 0``; the stereo fast path then reads
+    #: column 0 of both tensors only.  Left False, x-constancy is only used when the strides prove it (the stride-0
+    #: expand of depth_decoder.py:156): a dense disparity takes the per-pixel kernels, a dense mask is streamed next to
+    #: the logits (the forward pass keeps a row summary so that the backward pass can leave all-ones rows in HBM).
     disp_rowwise: bool = False
     #: photometric term: None = reference behaviour (mixture NLL if opt.use_mixture_loss else L1);
     #: "ssim_l1" = 0.85*SSIM + 0.15*L1 (compute_reprojection_loss, trainer.py:687-699) on the novel view
@@ -143,6 +145,8 @@ class HotPathMixin:
                 sign = 1.0 if side == "r" else (-1.0 if side == "l" else 0.0)
                 if self.disp_rowwise and disp.dim() == 4 and disp.stride(3) != 0 and disp.shape[3] > 1:
                     disp = rowwise_view(disp)
+                if self.disp_rowwise and torch.is_tensor(mask) and mask.dim() == 4 and mask.stride(3) != 0 and mask.shape[3] > 1:
+                    mask = mask.detach()[..., :1].expand(-1, -1, -1, mask.shape[3])  # zero x stride: one value per row
             elif wt == "homography_warp":
                 hmat, cam = homography_params(outputs["distance"], outputs["norm"], outputs[("Rt", side)], inputs["K"], inputs["inv_K"])
             else:

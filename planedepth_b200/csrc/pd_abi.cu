@@ -82,9 +82,9 @@ pd::WarpParams make_params(const pd_warp_desc* d, const pd_warp_in* in) {
     return p;
 }
 
-// Dense-mask row summary behind the saved statistics (WarpParams::mask_rows): per image row two 64-bit sets over planes.
+// Dense-mask row summary behind the saved statistics (WarpParams::mask_rows): per image row one 64-bit set over planes.
 size_t stats_floats(const pd_warp_desc* d) { return (size_t)d->B * (d->mixture ? PD_STATS_MIXTURE : PD_STATS_PLAIN) * d->H * d->W; }
-size_t mask_summary_bytes(const pd_warp_desc* d) { return (size_t)d->B * d->H * 2 * sizeof(unsigned long long); }
+size_t mask_summary_bytes(const pd_warp_desc* d) { return (size_t)d->B * d->H * sizeof(unsigned long long); }
 
 void attach_mask_summary(pd::WarpParams& p, const float* stats) {
     const pd_warp_desc& d = p.d;
@@ -166,6 +166,11 @@ void launch_ssim(const pd::LossParams& p, dim3 g, cudaStream_t st) {
     kern<<<g, pd::LT_THREADS, smem, st>>>(p);
 }
 
+template <bool AUTO, bool HASMASK, bool WANT_G>
+void launch_ssim_stream(const pd::LossParams& p, int strips, int segs, int rs, unsigned grid, cudaStream_t st) {
+    pd::ssim_l1_stream_kernel<AUTO, HASMASK, WANT_G><<<grid, pd::SW_THREADS, 0, st>>>(p, strips, segs, rs);
+}
+
 template <int MODE, bool AUTO, bool HASMASK>
 void launch_ew(const pd::LossParams& p, unsigned g, bool want_g, cudaStream_t st) {
     if (want_g) pd::elementwise_fwd_kernel<MODE, AUTO, HASMASK, true><<<g, pd::EW_THREADS, 0, st>>>(p);
@@ -210,10 +215,16 @@ int pd_warp_composite_fwd(const pd_warp_desc* d, const pd_warp_in* in, pd_warp_o
     p.out = *out;
     attach_mask_summary(p, out->stats);
     const bool debug = out->rgb_rec_layered || out->logit_rec || out->probability_rec || out->sigma_rec || out->pi_rec;
-    if (!debug && !exact_coords(d) && pd::ts::stream_path_supported(p) && pd::ts::launch_fwd_stream(p, st))
-        return check_launch("rows_fwd_stream");
-    if (p.mask_rows) {  // the other forward kernels keep no summary: all-clear sets mean "read the mask"
-        cudaError_t e = cudaMemsetAsync(p.mask_rows, 0, mask_summary_bytes(d), st);
+    const bool streamed = !debug && !exact_coords(d) && pd::ts::stream_path_supported(p);
+    if (p.mask_rows) {
+        // bit n of a row = "plane n's mask row is not all ones".  The streamed forward ORs bits into a cleared summary;
+        // the other forward kernels keep none: all bits set means "read the mask"
+        cudaError_t e = cudaMemsetAsync(p.mask_rows, streamed ? 0 : 0xff, mask_summary_bytes(d), st);
+        if (e != cudaSuccess) return fail(PD_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    }
+    if (streamed && pd::ts::launch_fwd_stream(p, st)) return check_launch("rows_fwd_stream");
+    if (streamed && p.mask_rows) {  // no launch configuration after all
+        cudaError_t e = cudaMemsetAsync(p.mask_rows, 0xff, mask_summary_bytes(d), st);
         if (e != cudaSuccess) return fail(PD_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
     }
     if (!debug && pd::rows_path_supported(p)) {
@@ -291,8 +302,13 @@ int pd_debug_roundtrip(const float* u, int64_t n, int32_t size, float* out_exact
 size_t pd_photometric_workspace_bytes(const pd_loss_desc* d) {
     if (!d) return 0;
     dim3 g = loss_grid(d);
+    // one partial per CTA of whichever forward kernel runs: SSIM tiles / streamed SSIM warps (<= one CTA per 8 warps
+    // of at least 8 rows x 28 columns, fewer than the 8x64 tiles) / persistent elementwise grid
     const size_t tiles = (size_t)g.x * g.y * g.z, ew = 148 * 8;
-    return (tiles > ew ? tiles : ew) * sizeof(float);
+    const size_t stream = ((size_t)d->B * ((d->W + pd::SW_COLS - 1) / pd::SW_COLS) * ((d->H + 7) / 8) + pd::SW_WARPS - 1) / pd::SW_WARPS;
+    size_t n = tiles > ew ? tiles : ew;
+    if (stream > n) n = stream;
+    return n * sizeof(float);
 }
 
 int pd_photometric_fwd(const pd_loss_desc* d, const pd_loss_in* in, pd_loss_out* out, void* workspace, pd_stream_t stream) {
@@ -310,6 +326,20 @@ int pd_photometric_fwd(const pd_loss_desc* d, const pd_loss_in* in, pd_loss_out*
     int64_t nparts;
     if (d->loss_mode == PD_LOSS_SSIM_L1) {
         const bool wg = out->g_unit != nullptr;
+        if (!getenv("PD_SSIM_TILES")) {
+            const int rs = pd::ssim_stream_rows(d->B, d->H, d->W);
+            const int strips = (d->W + pd::SW_COLS - 1) / pd::SW_COLS, segs = (d->H + rs - 1) / rs;
+            const int64_t tasks = (int64_t)d->B * strips * segs;
+            const unsigned g = (unsigned)((tasks + pd::SW_WARPS - 1) / pd::SW_WARPS);
+            nparts = g;
+            if (a) { if (m) { wg ? launch_ssim_stream<true, true, true>(p, strips, segs, rs, g, st) : launch_ssim_stream<true, true, false>(p, strips, segs, rs, g, st); }
+                     else   { wg ? launch_ssim_stream<true, false, true>(p, strips, segs, rs, g, st) : launch_ssim_stream<true, false, false>(p, strips, segs, rs, g, st); } }
+            else   { if (m) { wg ? launch_ssim_stream<false, true, true>(p, strips, segs, rs, g, st) : launch_ssim_stream<false, true, false>(p, strips, segs, rs, g, st); }
+                     else   { wg ? launch_ssim_stream<false, false, true>(p, strips, segs, rs, g, st) : launch_ssim_stream<false, false, false>(p, strips, segs, rs, g, st); } }
+            if ((rc = check_launch("ssim_l1_stream"))) return rc;
+            pd::reduce_partials_kernel<<<1, 1024, 0, st>>>(p.partials, nparts, out->ph_sum);
+            return check_launch("reduce_partials");
+        }
         const dim3 g = loss_grid(d);
         nparts = (int64_t)g.x * g.y * g.z;
         if (a) { if (m) { wg ? launch_ssim<true, true, true>(p, g, st) : launch_ssim<true, true, false>(p, g, st); }

@@ -300,6 +300,212 @@ __global__ void __launch_bounds__(LT_THREADS) ssim_l1_fwd_kernel(const LossParam
 }
 
 // ------------------------------------------------------------------------------------------------
+// SSIM + L1 forward (with unit gradient), streamed: no shared memory, no CTA barrier.
+//
+// A warp owns a strip of 28 output columns (lanes 2..29; lanes 0,1,30,31 carry the halo) and walks a segment of
+// rows top to bottom.  Per row every lane loads one value per tensor and channel (coalesced), the horizontal 3-sums
+// of {x, y, xx, yy, xy} come from two warp shuffles per value, the vertical 3-sums from two rows of registers.  The
+// centre finished at row y is (y-1); its derivative coefficients (A, B, C) are summed 3-wide with the reflect-padding
+// multiplicities the same way (shuffles across, registers down), which completes the unit gradient of pixel row
+// (y-2):  g = gate * 0.05 * sgn(pred - tgt) + SA + SB * pred + SC * tgt.
+// ------------------------------------------------------------------------------------------------
+constexpr int SW_COLS = 28, SW_WARPS = 8, SW_THREADS = SW_WARPS * 32;
+
+struct SsimRow {  // one row of loaded values of a lane (prediction already blended with mask_novel)
+    float a[3], b[3], s[3], m;
+};
+
+template <bool AUTO, bool HASMASK>
+__device__ __forceinline__ void ssim_load_row(const LossParams& p, int b, int y, int xv, SsimRow& r) {
+    const int H = p.d.H;
+    const int yv = reflect(min(max(y, -1), H), H);
+    const int64_t o = (int64_t)yv * p.d.W + xv;
+    r.m = HASMASK ? __ldg(p.in.mask_novel + (int64_t)b * p.hw + o) : 1.0f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int64_t oc = ((int64_t)b * 3 + c) * p.hw + o;
+        r.b[c] = __ldg(p.in.tgt + oc);
+        const float rec = __ldg(p.in.rgb_rec + oc);
+        r.a[c] = HASMASK ? blend_pred(rec, r.b[c], r.m) : rec;
+        r.s[c] = AUTO ? __ldg(p.in.src + oc) : 0.0f;
+    }
+}
+
+template <bool AUTO, bool HASMASK, bool WANT_G>
+__global__ void __launch_bounds__(SW_THREADS, 2) ssim_l1_stream_kernel(const LossParams p, int strips, int segs, int rs) {
+    __shared__ float red[SW_WARPS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int H = p.d.H, W = p.d.W;
+    const int64_t task = (int64_t)blockIdx.x * SW_WARPS + wid;
+    const int64_t per_img = (int64_t)segs * strips;
+    const float k3 = 1.0f / 3.0f, k9 = 1.0f / 9.0f, ks = 0.85f * k3, kg = k9 * ks;
+    float ph_acc = 0.0f;
+    {
+        // Control flow is kept warp-uniform by construction (and visibly so: the trip count is a kernel parameter), so the
+        // shuffles need no reconvergence protocol: a warp past the last task repeats it with every store masked off.
+        const int64_t ntask = (int64_t)p.d.B * per_img;
+        const bool live = task < ntask;
+        const int64_t tk = live ? task : ntask - 1;
+        const int b = (int)(tk / per_img);
+        const int rem = (int)(tk - (int64_t)b * per_img);
+        const int seg = rem / strips, strip = rem - seg * strips;
+        const int ys = seg * rs, ye = min(H, ys + rs);
+        const int x = strip * SW_COLS - 2 + lane;
+        const int xv = reflect(min(max(x, -1), W), W);
+        const bool cx_ok = (x >= 0) && (x < W);
+        const bool out_lane = live && (lane >= 2) && (lane < 2 + SW_COLS) && (x < W);
+        // multiplicities of column x inside the windows of the centres x-1, x, x+1 (reflect padding)
+        float wxm = (x - 1 < 0) ? 0.0f : 1.0f + ((x == W - 2 && x - 1 == W - 1) ? 1.0f : 0.0f);
+        float wxp = (x + 1 >= W) ? 0.0f : 1.0f + ((x == W - 2) ? 1.0f : 0.0f);
+        if (x == 1) wxm += 1.0f;  // centre 0 sees column 1 a second time as the reflected column -1
+
+        float H1[3][5], H2[3][5], S1[3][3], S2[3][3];      // horizontal sums of the two previous rows
+        float ap[3], bp[3], sp[3], app[3], bpp[3];          // values one / two rows back
+        float C1[3][3], C2[3][3];                           // column-summed coefficients of the two previous centre rows
+        float gate_p = 0.0f, m_p = 1.0f, m_pp = 1.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) H1[c][k] = H2[c][k] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) S1[c][k] = S2[c][k] = C1[c][k] = C2[c][k] = 0.0f;
+            ap[c] = bp[c] = sp[c] = app[c] = bpp[c] = 0.0f;
+        }
+        SsimRow nxt;
+        ssim_load_row<AUTO, HASMASK>(p, b, ys - 2, xv, nxt);
+        const int iters = rs + 4;  // rows past ye (last segment of an image) are walked with clamped loads and masked stores
+        for (int i = 0; i < iters; ++i) {
+            const int y = ys - 2 + i;  // value row of this iteration; centre row y-1; gradient row y-2
+            const SsimRow cur = nxt;
+            if (i + 1 < iters) ssim_load_row<AUTO, HASMASK>(p, b, y + 1, xv, nxt);
+            if (HASMASK && out_lane && y >= ys && y < ye) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) p.out.pred[((int64_t)b * 3 + c) * p.hw + (int64_t)y * W + x] = cur.a[c];
+            }
+            const int cy = y - 1;
+            const bool inside = cx_ok && (cy >= 0) && (cy < H);
+            float ss = 0.0f, l1 = 0.0f, ssa = 0.0f, l1a = 0.0f;
+            float ca[3], cb[3], cc[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float a = cur.a[c], t = cur.b[c];
+                // neighbours' values come from 4 shuffles; their squares / products are recomputed locally
+                const float al = __shfl_up_sync(0xffffffffu, a, 1), ar = __shfl_down_sync(0xffffffffu, a, 1);
+                const float tl = __shfl_up_sync(0xffffffffu, t, 1), tr = __shfl_down_sync(0xffffffffu, t, 1);
+                float hc[5];
+                hc[0] = al + a + ar, hc[1] = tl + t + tr;
+                hc[2] = fmaf(al, al, fmaf(ar, ar, a * a)), hc[3] = fmaf(tl, tl, fmaf(tr, tr, t * t));
+                hc[4] = fmaf(al, tl, fmaf(ar, tr, a * t));
+                WinStats w;
+                w.mx = (H2[c][0] + H1[c][0] + hc[0]) * k9, w.my = (H2[c][1] + H1[c][1] + hc[1]) * k9;
+                w.sx = (H2[c][2] + H1[c][2] + hc[2]) * k9 - w.mx * w.mx;
+                w.sy = (H2[c][3] + H1[c][3] + hc[3]) * k9 - w.my * w.my;
+                w.sxy = (H2[c][4] + H1[c][4] + hc[4]) * k9 - w.mx * w.my;
+                const float a1c = 2.0f * w.mx * w.my + kC1, a2c = 2.0f * w.sxy + kC2;
+                const float b1c = w.mx * w.mx + w.my * w.my + kC1, b2c = w.sx + w.sy + kC2;
+                const float n = a1c * a2c, d = b1c * b2c;
+                const float id = __fdividef(1.0f, d);
+                const float v = (1.0f - n * id) * 0.5f;  // layers.py:303-306 before the clamp
+                ss += fminf(fmaxf(v, 0.0f), 1.0f);
+                l1 += fabsf(ap[c] - bp[c]);
+                ca[c] = cb[c] = cc[c] = 0.0f;
+                if (WANT_G && v >= 0.0f && v <= 1.0f) {  // clamp backward
+                    const float nd2 = n * id * id;
+                    cb[c] = nd2 * b1c * kg;
+                    cc[c] = -a1c * id * kg;
+                    ca[c] = kg * ((a1c - a2c) * w.my * id + nd2 * (b2c - b1c) * w.mx);
+                }
+                if (AUTO) {
+                    const float s = cur.s[c];
+                    const float sl = __shfl_up_sync(0xffffffffu, s, 1), sr = __shfl_down_sync(0xffffffffu, s, 1);
+                    float hs[3];
+                    hs[0] = sl + s + sr, hs[1] = fmaf(sl, sl, fmaf(sr, sr, s * s)), hs[2] = fmaf(sl, tl, fmaf(sr, tr, s * t));
+                    WinStats u;
+                    u.mx = (S2[c][0] + S1[c][0] + hs[0]) * k9, u.my = w.my;
+                    u.sx = (S2[c][1] + S1[c][1] + hs[1]) * k9 - u.mx * u.mx;
+                    u.sy = w.sy;
+                    u.sxy = (S2[c][2] + S1[c][2] + hs[2]) * k9 - u.mx * u.my;
+                    float na, da;
+                    ssa += fminf(fmaxf(ssim_val(u, na, da), 0.0f), 1.0f);
+                    l1a += fabsf(sp[c] - bp[c]);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) S2[c][k] = S1[c][k], S1[c][k] = hs[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 5; ++k) H2[c][k] = H1[c][k], H1[c][k] = hc[k];
+            }
+            float ph = 0.85f * (ss * k3) + 0.15f * (l1 * k3);
+            float gate = inside ? 1.0f : 0.0f;
+            if (AUTO) {
+                const float pa2 = 0.85f * (ssa * k3) + 0.15f * (l1a * k3);
+                if (!(ph <= pa2)) gate = 0.0f;  // min() routes the gradient to the first minimum
+                ph = fminf(ph, pa2);
+            }
+            if (inside && out_lane && cy >= ys && cy < ye) {
+                ph_acc += ph;
+                if (p.out.ph_map) p.out.ph_map[(int64_t)b * p.hw + (int64_t)cy * W + x] = ph;
+            }
+            if (WANT_G) {
+                const int py = y - 2;
+                // multiplicities of row py inside the windows of the centre rows py-1, py, py+1
+                float wym = (py - 1 < 0) ? 0.0f : 1.0f;
+                float wyp = (py + 1 >= H) ? 0.0f : 1.0f + ((py == H - 2) ? 1.0f : 0.0f);
+                if (py == 1) wym += 1.0f;
+                const bool store = out_lane && py >= ys && py < ye;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float h[3];
+                    const float za = ca[c] * gate, zb = cb[c] * gate, zc = cc[c] * gate;  // gate is 0 / 1
+                    h[0] = fmaf(wxm, __shfl_up_sync(0xffffffffu, za, 1), fmaf(wxp, __shfl_down_sync(0xffffffffu, za, 1), za));
+                    h[1] = fmaf(wxm, __shfl_up_sync(0xffffffffu, zb, 1), fmaf(wxp, __shfl_down_sync(0xffffffffu, zb, 1), zb));
+                    h[2] = fmaf(wxm, __shfl_up_sync(0xffffffffu, zc, 1), fmaf(wxp, __shfl_down_sync(0xffffffffu, zc, 1), zc));
+                    if (store) {
+                        const float sa = fmaf(wym, C2[c][0], fmaf(wyp, h[0], C1[c][0]));
+                        const float sb = fmaf(wym, C2[c][1], fmaf(wyp, h[1], C1[c][1]));
+                        const float sc = fmaf(wym, C2[c][2], fmaf(wyp, h[2], C1[c][2]));
+                        const float pr = app[c], tg = bpp[c];
+                        float g = gate_p * (0.15f * k3) * sgnf(pr - tg) + sa + sb * pr + sc * tg;
+                        if (HASMASK) g *= m_pp;
+                        p.out.g_unit[((int64_t)b * 3 + c) * p.hw + (int64_t)py * W + x] = g;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) C2[c][k] = C1[c][k], C1[c][k] = h[k];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) app[c] = ap[c], bpp[c] = bp[c], ap[c] = cur.a[c], bp[c] = cur.b[c], sp[c] = cur.s[c];
+            m_pp = m_p, m_p = cur.m;
+            gate_p = gate;
+        }
+    }
+    ph_acc = warp_sum(ph_acc);
+    if (lane == 0) red[wid] = ph_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int i = 0; i < SW_WARPS; ++i) t += red[i];
+        p.partials[blockIdx.x] = t;
+    }
+}
+
+// rows per task: the fewest (waves x rows walked per task) over the whole grid of resident warps
+inline int ssim_stream_rows(int B, int H, int W) {
+    const int strips = (W + SW_COLS - 1) / SW_COLS;
+    const long long resident = 148ll * 2 * SW_WARPS;
+    int best = 16;
+    long long best_cost = -1;
+    const int cand[] = {8, 12, 16, 24, 32, 48, 64, 96, 128};
+    for (int rs : cand) {
+        const long long tasks = (long long)B * strips * ((H + rs - 1) / rs);
+        const long long waves = (tasks + resident - 1) / resident;
+        const long long cost = waves * (rs + 4);
+        if (best_cost < 0 || cost < best_cost) best_cost = cost, best = rs;
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------------
 // L1 / mixture forward (elementwise), with unit gradients
 // ------------------------------------------------------------------------------------------------
 constexpr int EW_THREADS = 256;

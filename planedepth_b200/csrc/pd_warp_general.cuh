@@ -21,9 +21,9 @@ struct WarpParams {
     int64_t hw, chw3;      // H*W, 3*H*W
     int g_disp_dense;      // g_disp has no zero stride -> plain stores
     int warp_aligned_rows; // W % 32 == 0: a warp never straddles image rows
-    // Dense-mask row summary kept behind the saved statistics (pd_warp_composite_stats_bytes): per image row two 64-bit
-    // sets over planes, {the plane's mask row is all 1.0, all 0.0}.  Written by the streamed forward (its producer warp
-    // scans the mask rows it staged), lets the streamed backward leave those mask rows in HBM.  NULL = not kept.
+    // Dense-mask row summary kept behind the saved statistics (pd_warp_composite_stats_bytes): per image row a 64-bit set
+    // over planes, bit n = "plane n's mask row is not all 1.0".  Written by the streamed forward (its consumers see every
+    // mask value anyway), lets the streamed backward leave all-ones mask rows in HBM.  NULL = not kept.
     unsigned long long* mask_rows;
 };
 

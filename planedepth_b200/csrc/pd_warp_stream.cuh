@@ -41,8 +41,7 @@ struct __align__(16) PlaneCoef {
     float wl1;       // wc1 * log2(e)
     float m;         // row mask value (1 when the mask is dense or absent)
     int k4;          // k0 * 4: the shift in bytes
-    float skip;      // dense mask, backward: != 0 when the row summary says the mask row is all ones (m = 1) or all
-                     // zeros (m = 0), so the row is neither copied nor read
+    float skip;      // SMASK_SUMMARY (backward): != 0 when the row summary says the mask row is all ones, so it is not read
 };
 
 struct StreamCfg {
@@ -57,8 +56,7 @@ struct StreamCfg {
 };
 
 constexpr int MAX_STAGES = 8;
-constexpr int BAR_FULL = 0, BAR_EMPTY = MAX_STAGES, BAR_SRC = 2 * MAX_STAGES, BAR_SUMM = 2 * MAX_STAGES + 2, BAR_BYTES = 384;
-constexpr int MAX_RPC = 8;  // rows per CTA iteration; BAR_SUMM holds 2 * MAX_RPC 64-bit plane sets of the row summary
+constexpr int BAR_FULL = 0, BAR_EMPTY = MAX_STAGES, BAR_SRC = 2 * MAX_STAGES, BAR_BYTES = 256;
 
 // SMASK_ROW: no mask or one value per (row, plane), folded into the coefficients.  SMASK_DENSE: fp32 mask rows travel
 // through the TMA ring next to the logits.  SMASK_SUMMARY (backward only): dense mask whose rows the forward pass has
@@ -253,11 +251,10 @@ __device__ __forceinline__ void stage_coef(const WarpParams& p, const StreamCfg&
             const float kf = floorf(sd);
             const bool sane = fabsf(sd) < (float)(W + 8);  // otherwise every tap is out of range
             const float w1 = sane ? sd - kf : 0.0f;
-            float m = (MASKMODE == SMASK_ROW) ? load_mask(p.in.mask, p.d.mask_dtype, soff(p.d.mask_stride, b, n, y, 0)) : 1.0f;
+            const float m = (MASKMODE == SMASK_ROW) ? load_mask(p.in.mask, p.d.mask_dtype, soff(p.d.mask_stride, b, n, y, 0)) : 1.0f;
             if (MASKMODE == SMASK_SUMMARY) {
-                const unsigned long long ones = __ldg(p.mask_rows + 2 * (size_t)row), zeros = __ldg(p.mask_rows + 2 * (size_t)row + 1);
-                if ((zeros >> n) & 1ull) m = 0.0f, k.skip = 1.0f;
-                else if ((ones >> n) & 1ull) k.skip = 1.0f;
+                // set bit n = some pixel of the plane's mask row differs from 1.0
+                if (!((__ldg(p.mask_rows + row) >> n) & 1ull)) k.skip = 1.0f;
             }
             k.k0 = sane ? (int)kf : W + 16;
             k.m = m;
@@ -276,61 +273,19 @@ __device__ __forceinline__ void stage_coef(const WarpParams& p, const StreamCfg&
 // arms the stage's full barrier with the byte count and issues one bulk copy per (plane, row, stream).
 // Releases that make reuse safe: the stage's empty barrier is armed by the consumers after their last read
 // of block jb - nst; with nst <= nblk that also covers the coefficient / source-row buffers of group it - 2.
-//
-// SCAN (forward, dense mask): between two issues the otherwise idle producer warp reads the mask rows of the
-// previous block out of the ring and records, per image row, which planes' mask rows are all ones / all zeros
-// (WarpParams::mask_rows); it then counts as one more reader of the stage (the empty barriers expect it).
-struct ScanBlock {
-    int stage, phase, row0, nrows, n0, n1, last;
-};
-
-__device__ __forceinline__ void scan_mask_block(const WarpParams& p, const StreamCfg& c, const Smem& s, const ScanBlock& k) {
-    const int lane = threadIdx.x & 31, W4 = p.d.W / 4;
-    unsigned long long* sets = reinterpret_cast<unsigned long long*>(s.bars + BAR_SUMM);  // [rpc][2], lane 0 only
-    mbar_wait(s.bars + BAR_FULL + k.stage, (uint32_t)k.phase);
-    for (int r = 0; r < k.nrows; ++r) {
-        unsigned long long ones = 0ull, zeros = 0ull;
-        if (k.n0 != 0) ones = sets[2 * r], zeros = sets[2 * r + 1];
-        for (int n = k.n0; n < k.n1; ++n) {
-            const float* row = s.mring + ((size_t)(k.stage * c.hs + (n - k.n0)) * c.rpc + r) * c.pitch + PAD;
-            unsigned band = 0xffffffffu, bor = 0u;
-            for (int i = lane; i < W4; i += 32) {
-                const float4 v = lds128(row + 4 * i);
-                band &= __float_as_uint(v.x) & __float_as_uint(v.y) & __float_as_uint(v.z) & __float_as_uint(v.w);
-                bor |= __float_as_uint(v.x) | __float_as_uint(v.y) | __float_as_uint(v.z) | __float_as_uint(v.w);
-            }
-            band = __reduce_and_sync(0xffffffffu, band);
-            bor = __reduce_or_sync(0xffffffffu, bor);
-            if (band == 0x3f800000u && bor == 0x3f800000u) ones |= 1ull << n;
-            if (bor == 0u) zeros |= 1ull << n;
-        }
-        if (lane == 0) {
-            if (k.last) p.mask_rows[2 * (size_t)(k.row0 + r)] = ones, p.mask_rows[2 * (size_t)(k.row0 + r) + 1] = zeros;
-            else sets[2 * r] = ones, sets[2 * r + 1] = zeros;
-        }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(s.bars + BAR_EMPTY + k.stage);
-}
-
-template <bool MIX, int MASKMODE, bool SCAN>
+template <bool MIX, int MASKMODE>
 __device__ __forceinline__ void producer_loop(const WarpParams& p, const StreamCfg& c, const Smem& s, int nit) {
     constexpr bool DENSE = (MASKMODE == SMASK_DENSE);
     const int lane = threadIdx.x & 31;
     const int W = p.d.W, H = p.d.H, N = p.d.N, rows_total = p.d.B * H;
     const uint32_t rowbytes = (uint32_t)(W * sizeof(float));
     const int streams = 1 + (MIX ? 1 : 0) + (DENSE ? 1 : 0);
-    const bool scan = SCAN && DENSE && p.mask_rows != nullptr;
-    ScanBlock prev;
-    prev.stage = -1;
     int stage = 0, use = 0;  // use = how many times the ring wrapped
     for (int it = 0; it < nit; ++it) {
         const int g = blockIdx.x + it * gridDim.x;
         const int row0 = g * c.rpc;
         const int nrows = min(c.rpc, rows_total - row0);
         for (int j = 0; j < c.nblk; ++j) {
-            // with a single stage the previous block must be scanned (and released) before its stage can be reused
-            if (scan && c.nst == 1 && prev.stage >= 0) scan_mask_block(p, c, s, prev), prev.stage = -1;
             if (use > 0) mbar_wait(s.bars + BAR_EMPTY + stage, (use - 1) & 1);
             if (j == 0) {
                 stage_coef<MASKMODE>(p, c, s.coef + (size_t)(it & 1) * c.rpc * N, g, rows_total);
@@ -363,14 +318,9 @@ __device__ __forceinline__ void producer_loop(const WarpParams& p, const StreamC
                     }
                 }
             }
-            if (scan) {
-                if (prev.stage >= 0) scan_mask_block(p, c, s, prev);
-                prev.stage = stage, prev.phase = use & 1, prev.row0 = row0, prev.nrows = nrows, prev.n0 = n0, prev.n1 = n1, prev.last = (j == c.nblk - 1);
-            }
             if (++stage == c.nst) stage = 0, ++use;
         }
     }
-    if (scan && prev.stage >= 0) scan_mask_block(p, c, s, prev);
 }
 
 __device__ __forceinline__ PlaneCoef load_coef(uint32_t a32) {
@@ -526,7 +476,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
     const Smem s = carve(smem_raw, cfg, N, MIX, DENSE, 0, false);
     zero_pads(s, cfg, W);
     if (threadIdx.x == 0) {
-        const uint32_t readers = (uint32_t)(cfg.nc / 32) + ((DENSE && p.mask_rows) ? 1u : 0u);  // + the scanning producer warp
+        const uint32_t readers = (uint32_t)(cfg.nc / 32);
         for (int i = 0; i < cfg.nst; ++i) {
             mbar_init(s.bars + BAR_FULL + i, 1);
             mbar_init(s.bars + BAR_EMPTY + i, readers);
@@ -538,7 +488,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
     __syncthreads();
     const int nit = (cfg.ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if ((int)threadIdx.x >= cfg.nc) {
-        producer_loop<MIX, MASKMODE, true>(p, cfg, s, nit);
+        producer_loop<MIX, MASKMODE>(p, cfg, s, nit);
         return;
     }
     const int lane = threadIdx.x & 31;
@@ -583,6 +533,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
         uint32_t coef_a = coef0 + (uint32_t)(((it & 1) * rpc + r) * N) * (uint32_t)sizeof(PlaneCoef);
         const uint32_t srow = src0 + (uint32_t)(((it & 1) * rpc + r) * 3) * pitch4;
         mbar_wait(bars + 8 * (BAR_SRC + (it & 1)), (it >> 1) & 1);
+        unsigned long long not_ones = 0ull;  // dense mask: planes whose mask this thread saw differ from 1.0
 
         for (int j = 0; j < NB; ++j) {
             // every consumer thread waits (also idle ones: a warp must not run ahead of the ring and arrive twice
@@ -598,6 +549,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
                     if (DENSE) {
                         load_window<PX>(lrow + mdelta + x04, mm);
                         perpix = !all_ones<PX>(mm);
+                        if (perpix) not_ones |= 1ull << (j * hs + q);
                     }
                     if (DENSE && perpix) fwd_plane_any<MIX, PX, true>(srow, lrow, lrow + sdelta, pitch4, x04 + k.k4, W4, k, mm, acc);
                     else fwd_plane_any<MIX, PX, false>(srow, lrow, lrow + sdelta, pitch4, x04 + k.k4, W4, k, mm, acc);
@@ -606,6 +558,17 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
             __syncwarp();
             if (lane == 0) mbar_arrive(bars + 8 * (BAR_EMPTY + stage));
             if (++stage == cfg.nst) stage = 0, fphase ^= 1;
+        }
+        if (DENSE && p.mask_rows) {
+            // row summary for the backward pass: OR over the threads of the row (rows are zeroed by the host before launch)
+            const unsigned lo = __reduce_or_sync(0xffffffffu, active ? (unsigned)not_ones : 0u);
+            const unsigned hi = __reduce_or_sync(0xffffffffu, active ? (unsigned)(not_ones >> 32) : 0u);
+            const int r_first = (int)((threadIdx.x & ~31u) / cfg.tpr), r_last = (int)((threadIdx.x | 31u) / cfg.tpr);
+            if (r_first == r_last) {
+                if (lane == 0 && active && (lo | hi)) atomicOr(p.mask_rows + row, ((unsigned long long)hi << 32) | lo);
+            } else if (active && not_ones) {
+                atomicOr(p.mask_rows + row, not_ones);  // a warp that straddles rows: per thread
+            }
         }
         if (!active) continue;
         float o0[PX], o1[PX], o2[PX];
@@ -805,7 +768,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
     __syncthreads();
     const int nit = (cfg.ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if ((int)threadIdx.x >= cfg.nc) {
-        producer_loop<MIX, MASKMODE, false>(p, cfg, s, nit);
+        producer_loop<MIX, MASKMODE>(p, cfg, s, nit);
         return;
     }
     const int lane = threadIdx.x & 31;
