@@ -137,6 +137,8 @@ typedef struct pd_warp_grad_in { /* produced gradients; any pointer may be NULL 
 int pd_version(void);
 const char* pd_last_error(void);
 
+/* Scratch the caller passes as `workspace` to both calls below (contents need not survive between them).  Non-zero
+ * for the homography fast path only: the source colour re-packed to one rgbx float4 per pixel. */
 size_t pd_warp_composite_workspace_bytes(const pd_warp_desc* desc);
 size_t pd_warp_composite_stats_bytes(const pd_warp_desc* desc);
 

@@ -11,6 +11,7 @@
 
 #include "pd_loss.cuh"
 #include "pd_warp_general.cuh"
+#include "pd_warp_homo.cuh"
 #include "pd_warp_rows.cuh"
 #include "pd_warp_stream.cuh"
 
@@ -193,8 +194,10 @@ const char* pd_last_error(void) { return g_err; }
 int64_t pd_launch_count(void) { return g_launches.load(); }
 void pd_reset_launch_count(void) { g_launches.store(0); }
 
-size_t pd_warp_composite_workspace_bytes(const pd_warp_desc* desc) {
-    (void)desc;
+size_t pd_warp_composite_workspace_bytes(const pd_warp_desc* d) {
+    // homography fast path: the source colour packed to one rgbx float4 per pixel (pd_warp_homo.cuh)
+    if (!d || d->B < 1 || d->H < 1 || d->W < 1) return 0;
+    if (d->warp_type == PD_WARP_HOMOGRAPHY && ((int64_t)d->H * d->W) % pd::hm::HT == 0 && d->W % 32 == 0) return pd::hm::homo_workspace_bytes(d);
     return 0;
 }
 
@@ -204,7 +207,6 @@ size_t pd_warp_composite_stats_bytes(const pd_warp_desc* d) {
 }
 
 int pd_warp_composite_fwd(const pd_warp_desc* d, const pd_warp_in* in, pd_warp_out* out, void* workspace, pd_stream_t stream) {
-    (void)workspace;
     int rc = validate_warp(d, in);
     if (rc) return rc;
     if (!out || !out->rgb_rec || !out->stats) return fail(PD_ERR_ARG, "rgb_rec / stats outputs must not be NULL");
@@ -231,6 +233,13 @@ int pd_warp_composite_fwd(const pd_warp_desc* d, const pd_warp_in* in, pd_warp_o
         pd::launch_fwd_rows(p, st);
         return check_launch("warp_composite_fwd_rows");
     }
+    if (!debug && !exact_coords(d) && pd::hm::homo_path_supported(p)) {
+        if (!workspace) return fail(PD_ERR_WORKSPACE, "homography warp needs the workspace of pd_warp_composite_workspace_bytes()");
+        pd::hm::homo_pack(p, (float4*)workspace, st);
+        if ((rc = check_launch("pack_rgbx"))) return rc;
+        pd::hm::launch_homo_fwd(p, (const float4*)workspace, st);
+        return check_launch("homo_fwd");
+    }
     const bool mix = d->mixture != 0;
     switch (d->warp_type) {
         case PD_WARP_DISP: mix ? launch_fwd_general<PD_WARP_DISP, true>(p, debug, st) : launch_fwd_general<PD_WARP_DISP, false>(p, debug, st); break;
@@ -242,7 +251,6 @@ int pd_warp_composite_fwd(const pd_warp_desc* d, const pd_warp_in* in, pd_warp_o
 
 int pd_warp_composite_bwd(const pd_warp_desc* d, const pd_warp_in* in, const pd_warp_out* saved, const pd_warp_grad_out* gout,
                           pd_warp_grad_in* gin, void* workspace, pd_stream_t stream) {
-    (void)workspace;
     int rc = validate_warp(d, in);
     if (rc) return rc;
     if (!saved || !saved->rgb_rec || !saved->stats) return fail(PD_ERR_ARG, "saved rgb_rec / stats must not be NULL");
@@ -280,6 +288,13 @@ int pd_warp_composite_bwd(const pd_warp_desc* d, const pd_warp_in* in, const pd_
     if (rows) {
         pd::launch_bwd_rows(p, st);
         return check_launch("warp_composite_bwd_rows");
+    }
+    if (!exact_coords(d) && pd::hm::homo_path_supported(p)) {
+        if (!workspace) return fail(PD_ERR_WORKSPACE, "homography warp needs the workspace of pd_warp_composite_workspace_bytes()");
+        pd::hm::homo_pack(p, (float4*)workspace, st);
+        if ((rc = check_launch("pack_rgbx"))) return rc;
+        pd::hm::launch_homo_bwd(p, (const float4*)workspace, st);
+        return check_launch("homo_bwd");
     }
     const bool mix = d->mixture != 0;
     switch (d->warp_type) {

@@ -404,8 +404,10 @@ __global__ void __launch_bounds__(SW_THREADS, 2) ssim_l1_stream_kernel(const Los
                 const float a1c = 2.0f * w.mx * w.my + kC1, a2c = 2.0f * w.sxy + kC2;
                 const float b1c = w.mx * w.mx + w.my * w.my + kC1, b2c = w.sx + w.sy + kC2;
                 const float n = a1c * a2c, d = b1c * b2c;
+                // the value feeds comparisons (clamp, automask min): IEEE division as in layers.py:306, so that knife-edge
+                // decisions fall the way the reference's do; the smooth derivative terms use the fast reciprocal
+                const float v = (1.0f - __fdiv_rn(n, d)) * 0.5f;
                 const float id = __fdividef(1.0f, d);
-                const float v = (1.0f - n * id) * 0.5f;  // layers.py:303-306 before the clamp
                 ss += fminf(fmaxf(v, 0.0f), 1.0f);
                 l1 += fabsf(ap[c] - bp[c]);
                 ca[c] = cb[c] = cc[c] = 0.0f;

@@ -968,7 +968,9 @@ inline StreamCfg stream_cfg(const WarpParams& p, bool mix, bool dense, int ne_bw
     if (c.nst < 1) c.nst = 1;
     // shrink the pipeline until the CTA fits the shared-memory budget (default: three CTAs per SM)
     // (three CTAs of <= 192 threads per SM, two of the 352-thread CTAs that wide rows need)
-    const size_t budget = (size_t)stream_env_int("PD_STREAM_SMEM_KB", c.nc > 160 ? 110 : 72) * 1024;
+    // (the wide mixture backward runs one CTA per SM on registers anyway: it gets a deep ring instead, cfg3 0.82 -> 0.69 ms)
+    const int dflt_kb = c.nc > 160 ? ((mix && ne_bwd > 0) ? 200 : 110) : 72;
+    const size_t budget = (size_t)stream_env_int("PD_STREAM_SMEM_KB", dflt_kb) * 1024;
     while (stream_smem_bytes(c, p.d.N, mix, dense, ne_bwd, want_disp) > budget) {
         if (c.nst > 2) --c.nst;
         else if (c.hs > 1) --c.hs;

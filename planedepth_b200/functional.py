@@ -67,6 +67,12 @@ def compact_expand_base(t: torch.Tensor) -> torch.Tensor:
     return base
 
 
+def _workspace(lib, desc, dev) -> Optional[torch.Tensor]:
+    """Scratch buffer of pd_warp_composite_workspace_bytes(desc) (caller-owned; the caching allocator recycles it)."""
+    n = int(lib.pd_warp_composite_workspace_bytes(C.byref(desc)))
+    return torch.empty((n + 3) // 4, device=dev, dtype=torch.float32) if n else None
+
+
 @dataclass(frozen=True)
 class WarpConfig:
     warp_type: int
@@ -112,7 +118,7 @@ class _WarpComposite(torch.autograd.Function):
                 layered["pi_rec"] = torch.empty(B, N, H, W, device=dev)
             for k, v in layered.items():
                 setattr(out, k, v.data_ptr())
-        _call("pd_warp_composite_fwd", lib.pd_warp_composite_fwd, C.byref(desc), C.byref(tin), C.byref(out), None, _stream())
+        _call("pd_warp_composite_fwd", lib.pd_warp_composite_fwd, C.byref(desc), C.byref(tin), C.byref(out), _ptr(_workspace(lib, desc, dev)), _stream())
         ctx.cfg = cfg
         ctx.desc = desc
         ctx.save_for_backward(src, tgt, logits, sigma, disp, mask, hmat, cam, rgb_rec, stats)
@@ -169,7 +175,7 @@ class _WarpComposite(torch.autograd.Function):
             g9 = torch.empty(B * N, 9, device=dev, dtype=torch.float32)
             gin.g_hmat = g9.data_ptr()
         _call("pd_warp_composite_bwd", lib.pd_warp_composite_bwd, C.byref(ctx.desc), C.byref(tin), C.byref(saved), C.byref(gout),
-              C.byref(gin), None, _stream())
+              C.byref(gin), _ptr(_workspace(lib, ctx.desc, dev)), _stream())
         if hmat is not None and need[7]:
             g_hmat = torch.cat([g9, torch.zeros(B * N, 3, device=dev)], 1)
         if g_disp is not None and tuple(g_disp.shape) != tuple(disp.shape):

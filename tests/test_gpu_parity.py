@@ -164,6 +164,8 @@ CONFIGS = [
     (2, 9, 6, 256, "disp_warp", False, False, [], False, dict(holes=True)),      # dense mask, 128-pixel segments: row summary
     (1, 7, 5, 128, "disp_warp", True, True, [], True, dict(holes=True)),
     (2, 8, 8, 256, "disp_warp", False, True, [], True, dict(n_xz=3)),            # xz masks: all-zero rows above the horizon
+    (1, 5, 24, 96, "homography_warp", True, True, [-1], True, dict(n_xz=2)),     # homography fast path, division-free round trip
+    (2, 7, 24, 96, "homography_warp", False, False, [1], False, dict(n_xz=2)),
 ]
 
 
