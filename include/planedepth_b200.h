@@ -203,6 +203,40 @@ int pd_photometric_fwd(const pd_loss_desc* desc, const pd_loss_in* in, pd_loss_o
 int pd_photometric_bwd(const pd_loss_desc* desc, const pd_loss_in* in, const pd_loss_out* saved,
                        const pd_loss_grad_out* gout, pd_loss_grad_in* gin, void* workspace, pd_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Occlusion masks + post-processed disparity: replaces trainer.py:421-466 (the part of
+ * Trainer.generate_post_process_disp after the flipped forward pass; no gradients flow).  The decoder
+ * ran on the 2B-image batch cat([img, img.flip(-1)]); B below is the size of one half.
+ *   o_l        = min(1, sum_n warp_l(softmax_n(warp_r(logits[:B]))))                  :441-447
+ *   o_fr       = min(1, sum_n warp_r(softmax_n(warp_l(logits[B:].flip(-1)))))         :449-454
+ *   mask_novel = min(1, sum_n warp_r(probability[:B]))                                 :461-463
+ *   disp_pp    = (mean*o_fr + disp_l*(1-o_fr))*o_l + disp_f*(1-o_l)                    :456-459
+ * with warp_r / warp_l = bilinear sampling at x + disp_layered[:B] / x - disp_layered[B:].
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pd_occl_desc {
+    int32_t B, N, H, W;      /* B = images of one half */
+    int32_t flags;           /* PD_FLAG_EXACT_COORDS: four-tap sampling through the reference's coordinate round trip */
+    pd_strides4 disp_stride; /* element strides of disp_layered [2B,N,H,W] (0 = broadcast) */
+} pd_occl_desc;
+
+typedef struct pd_occl_in {
+    const float* logits;       /* [2B,N,H,W] outputs["logits"] */
+    const float* probability;  /* [2B,N,H,W] outputs["probability"] (first half read) */
+    const float* disp_layered; /* [2B,N,H,W] strided */
+    const float* disp;         /* [2B,1,H,W] outputs["disp"]; required iff out->disp_pp */
+} pd_occl_in;
+
+typedef struct pd_occl_out { /* [B,1,H,W] each */
+    float* o_l;        /* required */
+    float* o_fr;       /* required */
+    float* mask_novel; /* may be NULL */
+    float* disp_pp;    /* may be NULL */
+} pd_occl_out;
+
+size_t pd_occlusion_masks_workspace_bytes(const pd_occl_desc* desc); /* one [B,N,H,W] fp32 plane set */
+int pd_occlusion_masks_fwd(const pd_occl_desc* desc, const pd_occl_in* in, pd_occl_out* out, void* workspace,
+                           pd_stream_t stream);
+
 /* Introspection for tests / bench: number of kernels the library has launched in this process since
  * the last pd_reset_launch_count() (bench.py reports it as gpu_launches). */
 int64_t pd_launch_count(void);

@@ -374,3 +374,42 @@ def hot_path(opt, target_sides, inputs, outputs, pc_net=None, loss_mode=None):
     """pred_novel_images + compute_losses, returning the losses dict (outputs is mutated)."""
     pred_novel_images(opt, target_sides, inputs, outputs)
     return compute_losses(opt, target_sides, inputs, outputs, pc_net, loss_mode)
+
+
+# --------------------------------------------------------------------------------------------
+# generate_post_process_disp (SURVEY.md §8f rank 1): occlusion masks from the flipped pass
+# --------------------------------------------------------------------------------------------
+
+
+def _shift_sample(feat, disp_layered, sign):
+    """F.grid_sample(feat.reshape(B*N,1,H,W), grid(x + sign*disp, y)) of trainer.py:424-445, per plane."""
+    B, N, H, W = feat.shape
+    xs, ys = pixel_centres(H, W, feat.device)
+    u = xs.expand(B, N, H, W) + sign * disp_layered
+    v = ys.expand(B, N, H, W)
+    gx = normalise(u, W).reshape(B * N, H, W)
+    gy = normalise(v, H).reshape(B * N, H, W)
+    return bilinear_sample(feat.reshape(B * N, 1, H, W), gx, gy).reshape(B, N, H, W)
+
+
+def post_process_disp(outputs: Dict):
+    """trainer.py:421-466 — everything after the flipped forward pass of ``generate_post_process_disp``.
+
+    ``outputs`` are the decoder outputs for the batch ``cat([img, img.flip(-1)])`` (2B images):
+    ``probability``, ``logits``, ``disp_layered`` [2B,N,H,W] and ``disp`` [2B,1,H,W].  Returns
+    ``(disp_pp, mask_novel)`` [B,1,H,W] each (detached), plus the two occlusion maps for tests."""
+    B2, N, H, W = outputs["probability"].shape
+    B = B2 // 2
+    dl, df = outputs["disp_layered"][:B], outputs["disp_layered"][B:]
+    # trainer.py:441-447: left logits -> right view, softmax over planes, back to the left view, sum, clip at 1
+    plr = torch.softmax(_shift_sample(outputs["logits"][:B], dl, +1.0), 1)
+    o_l = _shift_sample(plr, df, -1.0).sum(1, True).clamp(max=1.0)
+    # trainer.py:449-454: the flipped half, un-flipped, the other way round
+    pfrl = torch.softmax(_shift_sample(outputs["logits"][B:].flip(-1), df, -1.0), 1)
+    o_fr = _shift_sample(pfrl, dl, +1.0).sum(1, True).clamp(max=1.0)
+    d_l, d_f = outputs["disp"][:B], outputs["disp"][B:].flip(-1)
+    mean_disp = d_l * 0.5 + d_f * 0.5  # :456
+    disp_pp = mean_disp * o_fr + d_l * (1 - o_fr)  # :458
+    disp_pp = disp_pp * o_l + d_f * (1 - o_l)  # :459
+    mask_novel = _shift_sample(outputs["probability"][:B], dl, +1.0).sum(1, True).clamp(max=1.0)  # :461-463
+    return disp_pp.detach(), mask_novel.detach(), o_l.detach(), o_fr.detach()

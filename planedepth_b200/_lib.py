@@ -30,6 +30,7 @@ EXPORTS = [
     "pd_version", "pd_last_error", "pd_launch_count", "pd_reset_launch_count",
     "pd_warp_composite_workspace_bytes", "pd_warp_composite_stats_bytes", "pd_warp_composite_fwd", "pd_warp_composite_bwd",
     "pd_photometric_workspace_bytes", "pd_photometric_fwd", "pd_photometric_bwd", "pd_debug_roundtrip",
+    "pd_occlusion_masks_workspace_bytes", "pd_occlusion_masks_fwd",
 ]
 
 
@@ -62,6 +63,18 @@ class WarpGradOut(C.Structure):
 class WarpGradIn(C.Structure):
     _fields_ = [("g_logits", C.c_void_p), ("g_sigma", C.c_void_p), ("g_disp", C.c_void_p),
                 ("g_disp_stride", Strides4), ("g_hmat", C.c_void_p)]
+
+
+class OcclDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("flags", C.c_int32), ("disp_stride", Strides4)]
+
+
+class OcclIn(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("logits", "probability", "disp_layered", "disp")]
+
+
+class OcclOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("o_l", "o_fr", "mask_novel", "disp_pp")]
 
 
 class LossDesc(C.Structure):
@@ -153,6 +166,10 @@ def lib() -> C.CDLL:
     L.pd_photometric_bwd.restype = C.c_int
     L.pd_photometric_bwd.argtypes = [C.POINTER(LossDesc), C.POINTER(LossIn), C.POINTER(LossOut), C.POINTER(LossGradOut), C.POINTER(LossGradIn),
                                      C.c_void_p, C.c_void_p]
+    L.pd_occlusion_masks_workspace_bytes.restype = C.c_size_t
+    L.pd_occlusion_masks_workspace_bytes.argtypes = [C.POINTER(OcclDesc)]
+    L.pd_occlusion_masks_fwd.restype = C.c_int
+    L.pd_occlusion_masks_fwd.argtypes = [C.POINTER(OcclDesc), C.POINTER(OcclIn), C.POINTER(OcclOut), C.c_void_p, C.c_void_p]
     L.pd_debug_roundtrip.restype = C.c_int
     L.pd_debug_roundtrip.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     if L.pd_version() != ABI_VERSION:

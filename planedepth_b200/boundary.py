@@ -27,7 +27,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib as L
-from .functional import WarpConfig, photometric_loss, warp_composite
+from .functional import WarpConfig, occlusion_masks, photometric_loss, warp_composite
 
 _WARP = {"disp_warp": L.PD_WARP_DISP, "homography_warp": L.PD_WARP_HOMOGRAPHY, "depth_warp": L.PD_WARP_DEPTH}
 
@@ -239,6 +239,43 @@ class HotPathMixin:
             losses["loss/smooth_loss"] = sm
             losses["loss/total_loss"] = losses["loss/total_loss"] + _flag(opt, "alpha_smooth", 0.04) * sm
         return losses
+
+
+    # ------------------------------------------------------------------------------------------
+    def post_process_disp(self, outputs: Dict):
+        """trainer.py:421-466: occlusion masks and the post-processed disparity from the decoder outputs of the 2B-image
+        batch ``cat([img, img.flip(-1)])`` (``probability``, ``logits``, ``disp_layered``, ``disp``).  Returns
+        ``(disp_pp, mask_novel)``, both detached, like the reference."""
+        disp_layered = outputs["disp_layered"]
+        if self.disp_rowwise and disp_layered.dim() == 4 and disp_layered.stride(3) != 0 and disp_layered.shape[3] > 1:
+            disp_layered = disp_layered.detach()[..., :1].expand(-1, -1, -1, disp_layered.shape[3])
+        disp_pp, mask_novel, _, _ = occlusion_masks(outputs["logits"], outputs["probability"], disp_layered, outputs["disp"],
+                                                    exact_coords=bool(self.exact_coords))
+        return disp_pp, mask_novel
+
+    def generate_post_process_disp(self, inputs: Dict):
+        """Drop-in for ``Trainer.generate_post_process_disp`` (trainer.py:404-466).  The flipped forward pass through the
+        frozen networks (:406-419, ``self.fixed_models`` / ``self.models``) stays PyTorch; what follows runs on the library."""
+        opt = self.opt
+        img = inputs[("color_aug", "l")]
+        input_images = torch.cat([img, img.flip(-1)], dim=0)
+        input_grids = None
+        if _flag(opt, "num_ep", 0) > 0:
+            grid_fliped = inputs["grid"].clone()
+            grid_fliped[:, 0, :, :] *= -1.0
+            grid_fliped = grid_fliped.flip(-1)
+            input_grids = torch.cat([inputs["grid"], grid_fliped], dim=0)
+        net_type = _flag(opt, "net_type", "ResNet")
+        if net_type == "ResNet":
+            features = self.fixed_models["encoder"](input_images)
+            outputs = self.fixed_models["depth"](features, input_grids)
+        elif net_type == "PladeNet":
+            outputs = self.models["plade"](input_images, input_grids)
+        elif net_type == "FalNet":
+            outputs = self.models["fal"](input_images)
+        else:
+            raise ValueError("unknown net_type %r" % (net_type,))
+        return self.post_process_disp(outputs)
 
 
 def smooth_loss_disp(disp, img, gamma=1.0):

@@ -10,6 +10,7 @@
 #include <mutex>
 
 #include "pd_loss.cuh"
+#include "pd_occlusion.cuh"
 #include "pd_warp_general.cuh"
 #include "pd_warp_homo.cuh"
 #include "pd_warp_rows.cuh"
@@ -303,6 +304,62 @@ int pd_warp_composite_bwd(const pd_warp_desc* d, const pd_warp_in* in, const pd_
         default: mix ? launch_bwd_general<PD_WARP_DEPTH, true>(p, st) : launch_bwd_general<PD_WARP_DEPTH, false>(p, st); break;
     }
     return check_launch("warp_composite_bwd_general");
+}
+
+// ---------------------------------------------------------------------------------------------
+// occlusion masks / post-processed disparity (trainer.py:421-466)
+// ---------------------------------------------------------------------------------------------
+size_t pd_occlusion_masks_workspace_bytes(const pd_occl_desc* d) {
+    if (!d || d->B < 1 || d->N < 1 || d->H < 1 || d->W < 1) return 0;
+    return (size_t)d->B * d->N * d->H * d->W * sizeof(float);
+}
+
+int pd_occlusion_masks_fwd(const pd_occl_desc* d, const pd_occl_in* in, pd_occl_out* out, void* workspace, pd_stream_t stream) {
+    if (!d || !in || !out) return fail(PD_ERR_ARG, "NULL descriptor");
+    if (d->B < 1 || d->N < 1 || d->H < 2 || d->W < 2) return fail(PD_ERR_SHAPE, "B,N >= 1 and H,W >= 2 required");
+    if ((int64_t)d->H * d->W >= (1ll << 31)) return fail(PD_ERR_SHAPE, "H*W too large");
+    if (!in->logits || !in->disp_layered) return fail(PD_ERR_ARG, "logits / disp_layered must not be NULL");
+    if (!out->o_l || !out->o_fr) return fail(PD_ERR_ARG, "o_l / o_fr outputs must not be NULL");
+    if (out->mask_novel && !in->probability) return fail(PD_ERR_ARG, "mask_novel needs probability");
+    if (out->disp_pp && !in->disp) return fail(PD_ERR_ARG, "disp_pp needs disp");
+    if (!workspace) return fail(PD_ERR_WORKSPACE, "workspace of pd_occlusion_masks_workspace_bytes() required");
+    int rc;
+    if ((rc = check_device())) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    pd::oc::OcclParams p;
+    p.B = d->B, p.N = d->N, p.H = d->H, p.W = d->W;
+    p.hw = (int64_t)d->H * d->W;
+    p.ds = d->disp_stride;
+    p.wm1 = (float)(d->W - 1), p.hm1 = (float)(d->H - 1);
+    const bool exact = (d->flags & PD_FLAG_EXACT_COORDS) || getenv("PD_EXACT_COORDS");
+    const unsigned grid = (unsigned)(((int64_t)d->B * p.hw + 255) / 256);
+    float* Q = (float*)workspace;
+    const float* D = in->disp_layered;
+    const int B = d->B;
+    // left logits -> right view -> softmax -> back to the left view
+    if (exact) pd::oc::warp_softmax_kernel<true, false><<<grid, 256, 0, st>>>(p, in->logits, 0, D, 0, +1.0f, Q);
+    else pd::oc::warp_softmax_kernel<false, false><<<grid, 256, 0, st>>>(p, in->logits, 0, D, 0, +1.0f, Q);
+    if ((rc = check_launch("warp_softmax"))) return rc;
+    if (exact) pd::oc::warp_sum_kernel<true><<<grid, 256, 0, st>>>(p, Q, 0, D, B, -1.0f, out->o_l);
+    else pd::oc::warp_sum_kernel<false><<<grid, 256, 0, st>>>(p, Q, 0, D, B, -1.0f, out->o_l);
+    if ((rc = check_launch("warp_sum"))) return rc;
+    // flipped half, mirrored back, the other way round
+    if (exact) pd::oc::warp_softmax_kernel<true, true><<<grid, 256, 0, st>>>(p, in->logits, B, D, B, -1.0f, Q);
+    else pd::oc::warp_softmax_kernel<false, true><<<grid, 256, 0, st>>>(p, in->logits, B, D, B, -1.0f, Q);
+    if ((rc = check_launch("warp_softmax"))) return rc;
+    if (exact) pd::oc::warp_sum_kernel<true><<<grid, 256, 0, st>>>(p, Q, 0, D, 0, +1.0f, out->o_fr);
+    else pd::oc::warp_sum_kernel<false><<<grid, 256, 0, st>>>(p, Q, 0, D, 0, +1.0f, out->o_fr);
+    if ((rc = check_launch("warp_sum"))) return rc;
+    if (out->mask_novel) {
+        if (exact) pd::oc::warp_sum_kernel<true><<<grid, 256, 0, st>>>(p, in->probability, 0, D, 0, +1.0f, out->mask_novel);
+        else pd::oc::warp_sum_kernel<false><<<grid, 256, 0, st>>>(p, in->probability, 0, D, 0, +1.0f, out->mask_novel);
+        if ((rc = check_launch("warp_sum"))) return rc;
+    }
+    if (out->disp_pp) {
+        pd::oc::disp_pp_kernel<<<grid, 256, 0, st>>>(p, in->disp, out->o_l, out->o_fr, out->disp_pp);
+        if ((rc = check_launch("disp_pp"))) return rc;
+    }
+    return PD_OK;
 }
 
 int pd_debug_roundtrip(const float* u, int64_t n, int32_t size, float* out_exact, float* out_fast, pd_stream_t stream) {

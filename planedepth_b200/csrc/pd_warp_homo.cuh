@@ -5,8 +5,9 @@
 //   * the source colour is packed to one rgbx float4 per pixel by a small pre-pass, so a sample's
 //     12 colour taps are four 128-bit loads;
 //   * zero padding by clamped addresses and zeroed weights: no predicated loads;
-//   * q_xy / max(q_z, 1e-7) through one Newton-refined reciprocal; the normalise / un-normalise round
-//     trip keeps the reference's fp32 rounding (division-free form where the size allows it);
+//   * q_xy / max(q_z, 1e-7) through one Newton-refined reciprocal and a residual correction (correctly
+//     rounded quotients without the IEEE-division sequence); the normalise / un-normalise round trip
+//     keeps the reference's fp32 rounding (division-free form where the size allows it);
 //   * backward: the 9 sums of dL/dH per (plane, warp) shrink to 6 (a warp works inside one row, so the
 //     y-weighted sums are y times the plain ones) and are reduced with a 9-shuffle reduce-scatter
 //     instead of 45 butterfly shuffles, accumulated per CTA in shared memory, flushed once.
@@ -85,8 +86,11 @@ __device__ __forceinline__ HCoord homo_coords(const float4 h0, const float4 h1, 
     c.dz = (qz < 1e-7f) ? 0.0f : 1.0f;
     const float r0 = fast_rcp(zc);
     c.zinv = fmaf(r0, fmaf(-zc, r0, 1.0f), r0);  // one Newton step: ~0.5 ulp
-    c.u = qx * c.zinv;
-    c.v = qy * c.zinv;
+    // quotients with a residual correction (Markstein): the correctly rounded q / zc of layers.py:227-228 in all but
+    // pathological cases, so that floor() of the sample position falls as it does in the reference
+    const float u0 = qx * c.zinv, v0 = qy * c.zinv;
+    c.u = fmaf(fmaf(-u0, zc, qx), c.zinv, u0);
+    c.v = fmaf(fmaf(-v0, zc, qy), c.zinv, v0);
     return c;
 }
 

@@ -279,3 +279,30 @@ def photometric_loss(mode: int, automask: bool, rgb_rec, tgt, src=None, mask_nov
         nll = nll_auto = None
     ph_sum, pred, ph_map = _Photometric.apply(mode, automask, want_map, rgb_rec, tgt, src, mask_novel, nll, nll_auto)
     return ph_sum, (pred if mask_novel is not None else rgb_rec), (ph_map if want_map else None)
+
+
+def occlusion_masks(logits, probability, disp_layered, disp, exact_coords: bool = False):
+    """pd_occlusion_masks_fwd: trainer.py:421-466 on the decoder outputs of the 2B-image batch ``cat([img, img.flip(-1)])``.
+    Returns (disp_pp, mask_novel, o_l, o_fr), [B,1,H,W] each; no gradients (the reference detaches them, :464)."""
+    lib = L.lib()
+    with torch.no_grad():
+        logits = _f32c(logits.detach(), "logits")
+        probability = _f32c(probability.detach(), "probability")
+        disp = _f32c(disp.detach(), "disp")
+        dl = disp_layered.detach()
+        if dl.dtype != torch.float32:
+            dl = dl.float()
+        dl = compact_expand_base(dl)
+        B2, N, H, W = logits.shape
+        if B2 % 2 or tuple(probability.shape) != (B2, N, H, W) or tuple(disp.shape) != (B2, 1, H, W):
+            raise ValueError("occlusion_masks expects the outputs of the 2B-image batch: logits / probability [2B,N,H,W], disp [2B,1,H,W]")
+        B = B2 // 2
+        dev = logits.device
+        desc = L.OcclDesc(B=B, N=N, H=H, W=W, flags=(L.PD_FLAG_EXACT_COORDS if exact_coords else 0), disp_stride=_strides4(dl))
+        outs = [torch.empty(B, 1, H, W, device=dev, dtype=torch.float32) for _ in range(4)]
+        o_l, o_fr, mask_novel, disp_pp = outs
+        ws = torch.empty(lib.pd_occlusion_masks_workspace_bytes(C.byref(desc)) // 4, device=dev, dtype=torch.float32)
+        tin = L.OcclIn(logits=_ptr(logits), probability=_ptr(probability), disp_layered=_ptr(dl), disp=_ptr(disp))
+        out = L.OcclOut(o_l=_ptr(o_l), o_fr=_ptr(o_fr), mask_novel=_ptr(mask_novel), disp_pp=_ptr(disp_pp))
+        _call("pd_occlusion_masks_fwd", lib.pd_occlusion_masks_fwd, C.byref(desc), C.byref(tin), C.byref(out), ws.data_ptr(), _stream())
+    return disp_pp, mask_novel, o_l, o_fr

@@ -34,6 +34,7 @@ def test_ctypes_structs_match_c_layout(tmp_path):
         "pd_strides4": L.Strides4, "pd_warp_desc": L.WarpDesc, "pd_warp_in": L.WarpIn, "pd_warp_out": L.WarpOut,
         "pd_warp_grad_out": L.WarpGradOut, "pd_warp_grad_in": L.WarpGradIn, "pd_loss_desc": L.LossDesc, "pd_loss_in": L.LossIn,
         "pd_loss_out": L.LossOut, "pd_loss_grad_out": L.LossGradOut, "pd_loss_grad_in": L.LossGradIn,
+        "pd_occl_desc": L.OcclDesc, "pd_occl_in": L.OcclIn, "pd_occl_out": L.OcclOut,
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "planedepth_b200.h"', "int main(void){"]
     for cname, st in structs.items():

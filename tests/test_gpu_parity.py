@@ -337,3 +337,60 @@ def test_division_free_round_trip_is_bit_exact(size):
     assert torch.equal(a, b), "division-free round trip differs in %d of %d coordinates" % (int((a != b).sum()), u.numel())
     ref = ((((u.cpu() / (size - 1)) - 0.5) * 2 + 1) / 2) * (size - 1)
     assert torch.equal(a.cpu(), ref), "GPU round trip differs from the CPU (reference) evaluation"
+
+
+# ------------------------------------------------------------------------------------------------
+# generate_post_process_disp (trainer.py:404-466): occlusion masks + post-processed disparity
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("name", ["pp_vertical", "pp_xz"])
+def test_post_process_disp_matches_reference_golden(name, exact):
+    import os
+
+    from helpers import GOLDEN
+    from planedepth_b200.boundary import HotPath
+
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    outputs = {k: torch.from_numpy(z[k]).cuda() for k in ("logits", "probability", "disp_layered", "disp")}
+    hp = HotPath(O.default_opt(), ["r"], exact_coords=exact)
+    disp_pp, mask_novel = hp.post_process_disp(outputs)
+    # disp values are O(20): 1e-4 relative to their scale; the masks are O(1)
+    check(mask_novel, z["mask_novel"], TOL, "mask_novel", allow_frac=2e-4)
+    check(disp_pp, z["disp_pp"], 20 * TOL, "disp_pp", allow_frac=2e-4)
+
+
+@pytest.mark.parametrize("layout", ["expand", "dense", "rowwise"])
+def test_post_process_disp_matches_oracle(layout):
+    """BASELINE width / plane count, the decoder's stride-0 expand, a dense 49+14-style cat, and the cat under the
+    integrator's rowwise promise; also through the drop-in ``generate_post_process_disp`` with stub frozen networks."""
+    from types import SimpleNamespace
+
+    from planedepth_b200.boundary import HotPath
+
+    B, N, H, W, n_xz = 1, 12, 6, 640, (0 if layout == "expand" else 4)
+    g = torch.Generator().manual_seed(77)
+    n_v = N - n_xz
+    lev = torch.arange(n_v, dtype=torch.float32)[None] + torch.rand(2 * B, n_v, generator=g) - 0.5
+    base = (300.0 * (2.0 / 300.0) ** (lev / (n_v - 1))).reshape(2 * B, n_v, 1, 1)
+    disp_layered = base.expand(2 * B, n_v, H, W)
+    if n_xz:
+        gy = torch.linspace(-1, 1, H)[None, None, :, None].expand(2 * B, 1, H, W)
+        h = 0.1852 + 0.1852 * torch.rand(2 * B, n_xz, generator=g)
+        disp_layered = torch.cat([disp_layered, 0.1 * 0.58 * W / (h[:, :, None, None] * 1.92 / (gy.clamp_min(1e-7) / 2.0))], 1)
+    logits = 1.5 * torch.randn(2 * B, N, H, W, generator=g)
+    outs = {"logits": logits, "probability": torch.softmax(logits, 1), "disp_layered": disp_layered,
+            "disp": 1 + 20 * torch.rand(2 * B, 1, H, W, generator=g)}
+    want_pp, want_mn, _, _ = O.post_process_disp(outs)
+    dev = {k: v.cuda() for k, v in outs.items()}
+    if layout == "expand":
+        dev["disp_layered"] = base.cuda().expand(2 * B, n_v, H, W)
+    opt = SimpleNamespace(**vars(O.default_opt()), num_ep=8, net_type="ResNet")
+    hp = HotPath(opt, ["r"], disp_rowwise=(layout == "rowwise"))
+    hp.fixed_models = {"encoder": lambda x: x, "depth": lambda f, grids: dev}
+    xs = torch.linspace(-1, 1, W)[None, None, None, :].expand(B, 1, H, W)
+    ys = torch.linspace(-1, 1, H)[None, None, :, None].expand(B, 1, H, W)
+    inputs = {("color_aug", "l"): torch.rand(B, 3, H, W).cuda(), "grid": torch.cat([xs, ys], 1).contiguous().cuda()}
+    disp_pp, mask_novel = hp.generate_post_process_disp(inputs)
+    assert not disp_pp.requires_grad and not mask_novel.requires_grad
+    check(mask_novel, want_mn, TOL, "mask_novel", allow_frac=2e-4)
+    check(disp_pp, want_pp, 20 * TOL, "disp_pp", allow_frac=2e-4)

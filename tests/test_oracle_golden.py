@@ -77,3 +77,18 @@ def test_oracle_primitives_match_reference():
     ud, vd = O.depth_warp_coords(disp, T("T"), T("K"), T("inv_K"))
     gd = torch.stack([O.normalise(ud, W), O.normalise(vd, H)], -1).reshape(B, H, W, 2)
     assert_close(gd, z["depth_grid"], 2e-4, 1e-4, what="depth grid")
+
+
+@pytest.mark.parametrize("name", ["pp_vertical", "pp_xz"])
+def test_oracle_post_process_disp_matches_reference(name):
+    """Trainer.generate_post_process_disp (trainer.py:404-466) run by tests/golden/make_golden_pp.py vs the restatement."""
+    import os
+
+    from helpers import GOLDEN
+
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    outputs = {k: torch.from_numpy(z[k]) for k in ("logits", "probability", "disp_layered", "disp")}
+    disp_pp, mask_novel, o_l, o_fr = O.post_process_disp(outputs)
+    assert_close(disp_pp, z["disp_pp"], 1e-5, what="disp_pp")
+    assert_close(mask_novel, z["mask_novel"], 1e-6, what="mask_novel")
+    assert float(o_l.max()) <= 1.0 and float(o_fr.max()) <= 1.0 and float(mask_novel.max()) <= 1.0
