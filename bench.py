@@ -459,7 +459,8 @@ def run_ours(args):
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
-            traffic = tj.get(args.config + ("_compact" if args.layout == "compact" else ""), {}).get(dom)
+            key = args.config + ("_compact" if args.layout == "compact" else ("_nopromise" if args.no_rowwise else ""))
+            traffic = tj.get(key, {}).get(dom)
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

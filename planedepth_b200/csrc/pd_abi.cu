@@ -336,20 +336,38 @@ int pd_occlusion_masks_fwd(const pd_occl_desc* d, const pd_occl_in* in, pd_occl_
     float* Q = (float*)workspace;
     const float* D = in->disp_layered;
     const int B = d->B;
-    // left logits -> right view -> softmax -> back to the left view
-    if (exact) pd::oc::warp_softmax_kernel<true, false><<<grid, 256, 0, st>>>(p, in->logits, 0, D, 0, +1.0f, Q);
-    else pd::oc::warp_softmax_kernel<false, false><<<grid, 256, 0, st>>>(p, in->logits, 0, D, 0, +1.0f, Q);
-    if ((rc = check_launch("warp_softmax"))) return rc;
-    if (exact) pd::oc::warp_sum_kernel<true><<<grid, 256, 0, st>>>(p, Q, 0, D, B, -1.0f, out->o_l);
-    else pd::oc::warp_sum_kernel<false><<<grid, 256, 0, st>>>(p, Q, 0, D, B, -1.0f, out->o_l);
-    if ((rc = check_launch("warp_sum"))) return rc;
-    // flipped half, mirrored back, the other way round
-    if (exact) pd::oc::warp_softmax_kernel<true, true><<<grid, 256, 0, st>>>(p, in->logits, B, D, B, -1.0f, Q);
-    else pd::oc::warp_softmax_kernel<false, true><<<grid, 256, 0, st>>>(p, in->logits, B, D, B, -1.0f, Q);
-    if ((rc = check_launch("warp_softmax"))) return rc;
-    if (exact) pd::oc::warp_sum_kernel<true><<<grid, 256, 0, st>>>(p, Q, 0, D, 0, +1.0f, out->o_fr);
-    else pd::oc::warp_sum_kernel<false><<<grid, 256, 0, st>>>(p, Q, 0, D, 0, +1.0f, out->o_fr);
-    if ((rc = check_launch("warp_sum"))) return rc;
+    if (!exact && d->W <= 2048) {
+        // fused per row: warp -> softmax over planes -> warp back -> sum -> clip, nothing parked in HBM
+        const size_t smem = (size_t)2 * (d->W + 2 * pd::oc::OC_PAD) * sizeof(float);
+        const unsigned rows = (unsigned)(d->B * d->H);
+        if (d->W <= 1024) {
+            const int threads = ((d->W + 31) / 32) * 32;
+            pd::oc::occlusion_row_kernel<false, 1><<<rows, threads, smem, st>>>(p, in->logits, 0, D, 0, +1.0f, B, -1.0f, out->o_l);
+            if ((rc = check_launch("occlusion_row"))) return rc;
+            pd::oc::occlusion_row_kernel<true, 1><<<rows, threads, smem, st>>>(p, in->logits, B, D, B, -1.0f, 0, +1.0f, out->o_fr);
+        } else {
+            const int threads = (((d->W + 1) / 2 + 31) / 32) * 32;
+            pd::oc::occlusion_row_kernel<false, 2><<<rows, threads, smem, st>>>(p, in->logits, 0, D, 0, +1.0f, B, -1.0f, out->o_l);
+            if ((rc = check_launch("occlusion_row"))) return rc;
+            pd::oc::occlusion_row_kernel<true, 2><<<rows, threads, smem, st>>>(p, in->logits, B, D, B, -1.0f, 0, +1.0f, out->o_fr);
+        }
+        if ((rc = check_launch("occlusion_row"))) return rc;
+    } else {
+        // left logits -> right view -> softmax -> back to the left view
+        if (exact) pd::oc::warp_softmax_kernel<true, false><<<grid, 256, 0, st>>>(p, in->logits, 0, D, 0, +1.0f, Q);
+        else pd::oc::warp_softmax_kernel<false, false><<<grid, 256, 0, st>>>(p, in->logits, 0, D, 0, +1.0f, Q);
+        if ((rc = check_launch("warp_softmax"))) return rc;
+        if (exact) pd::oc::warp_sum_kernel<true><<<grid, 256, 0, st>>>(p, Q, 0, D, B, -1.0f, out->o_l);
+        else pd::oc::warp_sum_kernel<false><<<grid, 256, 0, st>>>(p, Q, 0, D, B, -1.0f, out->o_l);
+        if ((rc = check_launch("warp_sum"))) return rc;
+        // flipped half, mirrored back, the other way round
+        if (exact) pd::oc::warp_softmax_kernel<true, true><<<grid, 256, 0, st>>>(p, in->logits, B, D, B, -1.0f, Q);
+        else pd::oc::warp_softmax_kernel<false, true><<<grid, 256, 0, st>>>(p, in->logits, B, D, B, -1.0f, Q);
+        if ((rc = check_launch("warp_softmax"))) return rc;
+        if (exact) pd::oc::warp_sum_kernel<true><<<grid, 256, 0, st>>>(p, Q, 0, D, 0, +1.0f, out->o_fr);
+        else pd::oc::warp_sum_kernel<false><<<grid, 256, 0, st>>>(p, Q, 0, D, 0, +1.0f, out->o_fr);
+        if ((rc = check_launch("warp_sum"))) return rc;
+    }
     if (out->mask_novel) {
         if (exact) pd::oc::warp_sum_kernel<true><<<grid, 256, 0, st>>>(p, in->probability, 0, D, 0, +1.0f, out->mask_novel);
         else pd::oc::warp_sum_kernel<false><<<grid, 256, 0, st>>>(p, in->probability, 0, D, 0, +1.0f, out->mask_novel);

@@ -93,6 +93,85 @@ __global__ void __launch_bounds__(256) warp_sum_kernel(const OcclParams p, const
     out[pix] = fminf(acc, 1.0f);  // o[o > 1] = 1
 }
 
+// Both stages of one occlusion map fused per image row (the warps are horizontal, so a row only needs itself):
+//     out[b, y, x] = min(1, sum_n warp2( softmax_n( warp1(P[pb + b, n]) ) ))      warp_i: u = x + sign_i * D[db_i + b, n]
+// One CTA per row, PPT pixels per thread.  Pass 1 runs the softmax statistics (max, sum) of the once-warped logits over the
+// planes; pass 2 recomputes each plane's sample (second read of the row: L1 / L2), turns it into its probability, parks
+// the probability row in shared memory (double-buffered, zero pads = padding_mode "zeros") and gathers the second warp
+// from there.  Nothing but the [B,1,H,W] result goes back to HBM.  Exact sample positions (see the file header).
+constexpr int OC_PAD = 4;
+
+template <bool FLIP, int PPT>
+__global__ void __launch_bounds__(1024) occlusion_row_kernel(const OcclParams p, const float* __restrict__ P, int pb, const float* __restrict__ D,
+                                                             int db1, float sign1, int db2, float sign2, float* __restrict__ out) {
+    extern __shared__ float erow[];  // [2][W + 2 * OC_PAD]
+    const int W = p.W, N = p.N;
+    const int pitch = W + 2 * OC_PAD;
+    const int row = blockIdx.x, b = row / p.H, y = row - b * p.H;
+    for (int i = threadIdx.x; i < 2 * pitch; i += blockDim.x) erow[i] = 0.0f;  // pads stay zero; interiors are rewritten per plane
+    const float* src = P + ((int64_t)(pb + b) * N * p.H + y) * W;  // row y of plane 0; planes are hw apart
+    int x[PPT];
+    bool live[PPT];
+    float M[PPT], S[PPT], acc[PPT];
+    const float* d1[PPT];
+    const float* d2[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        x[k] = threadIdx.x + k * blockDim.x;
+        live[k] = x[k] < W;
+        const int xc = live[k] ? x[k] : W - 1;
+        d1[k] = D + soff(p.ds, db1 + b, 0, y, xc);
+        d2[k] = D + soff(p.ds, db2 + b, 0, y, xc);
+        M[k] = -INFINITY, S[k] = 0.0f, acc[k] = 0.0f;
+    }
+    // sample of the row of plane n at u (two taps, zero padding, optional mirror), in log2 units
+    auto sample = [&](const float* r, float u) -> float {
+        u = fminf(fmaxf(u, -2.0f), (float)(W + 1));
+        const float f0 = floorf(u);
+        const int x0 = (int)f0;
+        const float w1 = u - f0;
+        const float a = ((unsigned)x0 < (unsigned)W) ? __ldg(r + (FLIP ? W - 1 - x0 : x0)) : 0.0f;
+        const float c = ((unsigned)(x0 + 1) < (unsigned)W) ? __ldg(r + (FLIP ? W - 2 - x0 : x0 + 1)) : 0.0f;
+        return fmaf(c, w1, a * (1.0f - w1)) * kLog2e;
+    };
+    for (int n = 0; n < N; ++n) {
+        const float* r = src + (int64_t)n * p.hw;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const float l2 = sample(r, (float)x[k] + sign1 * __ldg(d1[k] + (int64_t)n * p.ds.n));
+            const float mn = fmaxf(M[k], l2);
+            S[k] = fmaf(S[k], fast_exp2(M[k] - mn), fast_exp2(l2 - mn));
+            M[k] = mn;
+        }
+    }
+    float invS[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) invS[k] = 1.0f / S[k];
+    __syncthreads();  // the zero fill above
+    float* e = erow + OC_PAD;
+    for (int n = 0; n < N; ++n, e = (e == erow + OC_PAD) ? erow + pitch + OC_PAD : erow + OC_PAD) {
+        const float* r = src + (int64_t)n * p.hw;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const float l2 = sample(r, (float)x[k] + sign1 * __ldg(d1[k] + (int64_t)n * p.ds.n));
+            if (live[k]) e[x[k]] = fast_exp2(l2 - M[k]) * invS[k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            float u = (float)x[k] + sign2 * __ldg(d2[k] + (int64_t)n * p.ds.n);
+            u = fminf(fmaxf(u, -2.0f), (float)(W + 1));
+            const float f0 = floorf(u);
+            const int x0 = (int)f0;  // in [-2, W+1]: both taps inside the padded row
+            const float w1 = u - f0;
+            acc[k] = fmaf(e[x0 + 1], w1, fmaf(e[x0], 1.0f - w1, acc[k]));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < PPT; ++k)
+        if (live[k]) out[(int64_t)row * W + x[k]] = fminf(acc[k], 1.0f);  // o[o > 1] = 1
+}
+
 // trainer.py:456-459
 __global__ void __launch_bounds__(256) disp_pp_kernel(const OcclParams p, const float* __restrict__ disp, const float* __restrict__ o_l,
                                                       const float* __restrict__ o_fr, float* __restrict__ disp_pp) {

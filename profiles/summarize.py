@@ -67,15 +67,21 @@ def launches(tag):
             tot, 100 * sum(float(r["Metric Value"]) for r in step if "pd::" in r["Kernel Name"]) / tot))
 
 
-def full(tag):
-    rep = os.path.join(ROOT, "gpurun_out", tag + "_prof.ncu-rep")
-    if not os.path.exists(rep):
+def full(tag, suffix=""):
+    """suffix "" = the main capture TAG_prof.ncu-rep; "_cfg3" etc. = secondary captures exported on the box as
+    TAG_prof_cfg3_raw.csv (their .ncu-rep files are too large to bring back)."""
+    rep = os.path.join(ROOT, "gpurun_out", tag + "_prof" + suffix + ".ncu-rep")
+    pre = os.path.join(ROOT, "gpurun_out", tag + "_prof" + suffix + "_raw.csv")
+    if os.path.exists(rep):
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    elif os.path.exists(pre):
+        raw = open(pre).read()
+    else:
         return
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
-    with open(os.path.join(ROOT, "profiles", tag + "_ncu_full.txt"), "w") as f:
-        f.write("ncu --set full --clock-control none (one launch per block below); from gpurun_out/%s_prof.ncu-rep\n" % tag)
+    with open(os.path.join(ROOT, "profiles", tag + "_ncu_full" + suffix + ".txt"), "w") as f:
+        f.write("ncu --set full --clock-control none (one launch per block below); from gpurun_out/%s_prof%s.ncu-rep\n" % (tag, suffix))
         for r in rows[2:]:
             f.write("\n== %s\n" % short(r[hdr.index("Kernel Name")]))
             vals = {}
@@ -97,4 +103,6 @@ if __name__ == "__main__":
     tag = sys.argv[1]
     launches(tag)
     full(tag)
+    for sfx in ("_cfg3", "_cfg4"):
+        full(tag, sfx)
     print("wrote profiles/%s_*" % tag)

@@ -359,7 +359,7 @@ def test_post_process_disp_matches_reference_golden(name, exact):
     check(disp_pp, z["disp_pp"], 20 * TOL, "disp_pp", allow_frac=2e-4)
 
 
-@pytest.mark.parametrize("layout", ["expand", "dense", "rowwise"])
+@pytest.mark.parametrize("layout", ["expand", "dense", "rowwise", "expand1280"])
 def test_post_process_disp_matches_oracle(layout):
     """BASELINE width / plane count, the decoder's stride-0 expand, a dense 49+14-style cat, and the cat under the
     integrator's rowwise promise; also through the drop-in ``generate_post_process_disp`` with stub frozen networks."""
@@ -367,7 +367,7 @@ def test_post_process_disp_matches_oracle(layout):
 
     from planedepth_b200.boundary import HotPath
 
-    B, N, H, W, n_xz = 1, 12, 6, 640, (0 if layout == "expand" else 4)
+    B, N, H, W, n_xz = 1, 12, 6, (1280 if layout == "expand1280" else 640), (0 if layout.startswith("expand") else 4)
     g = torch.Generator().manual_seed(77)
     n_v = N - n_xz
     lev = torch.arange(n_v, dtype=torch.float32)[None] + torch.rand(2 * B, n_v, generator=g) - 0.5
@@ -382,7 +382,7 @@ def test_post_process_disp_matches_oracle(layout):
             "disp": 1 + 20 * torch.rand(2 * B, 1, H, W, generator=g)}
     want_pp, want_mn, _, _ = O.post_process_disp(outs)
     dev = {k: v.cuda() for k, v in outs.items()}
-    if layout == "expand":
+    if layout.startswith("expand"):
         dev["disp_layered"] = base.cuda().expand(2 * B, n_v, H, W)
     opt = SimpleNamespace(**vars(O.default_opt()), num_ep=8, net_type="ResNet")
     hp = HotPath(opt, ["r"], disp_rowwise=(layout == "rowwise"))
