@@ -298,7 +298,7 @@ def run_reference(args):
         "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -494,12 +494,35 @@ def run_ours(args):
         "gpu_launches_per_step": int(launches_per_step),
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "loss": loss_val,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if ws > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def protect_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries write there behind Python's back (NCCL prints its version banner on
+    fd 1 even at NCCL_DEBUG=WARN), so fd 1 is pointed at stderr for the whole run and the line goes to a saved duplicate."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PD_ABI_VERSION 4
+#define PD_ABI_VERSION 5
 
 typedef void* pd_stream_t; /* a cudaStream_t */
 
@@ -164,6 +164,8 @@ typedef struct pd_loss_desc {
     int32_t loss_mode; /* pd_loss_mode */
     int32_t automask;
     int32_t has_mask_novel;
+    float out_scale; /* ph_sum = out_scale * sum ph (0 is read as 1): folds ph_loss.mean()'s 1/(B*H*W) (:742) into the
+                        reduction; the backward pass applies the same factor */
 } pd_loss_desc;
 
 typedef struct pd_loss_in {

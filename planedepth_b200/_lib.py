@@ -23,7 +23,7 @@ PD_WARP_DISP, PD_WARP_HOMOGRAPHY, PD_WARP_DEPTH = 0, 1, 2
 PD_LOSS_L1, PD_LOSS_MIXTURE, PD_LOSS_SSIM_L1 = 0, 1, 2
 PD_MASK_NONE, PD_MASK_F32, PD_MASK_U8 = 0, 1, 2
 PD_FLAG_EXACT_COORDS = 1
-ABI_VERSION = 4  # PD_ABI_VERSION in include/planedepth_b200.h
+ABI_VERSION = 5  # PD_ABI_VERSION in include/planedepth_b200.h
 PD_STATS_PLAIN, PD_STATS_MIXTURE = 2, 4
 
 EXPORTS = [
@@ -79,7 +79,7 @@ class OcclOut(C.Structure):
 
 class LossDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("loss_mode", C.c_int32),
-                ("automask", C.c_int32), ("has_mask_novel", C.c_int32)]
+                ("automask", C.c_int32), ("has_mask_novel", C.c_int32), ("out_scale", C.c_float)]
 
 
 class LossIn(C.Structure):

@@ -212,10 +212,10 @@ class HotPathMixin:
         inv_count = 1.0 / float(B * H * W)
         for side in self.target_sides:
             target = inputs[(color, side)]
-            ph_sum, pred, _ = photometric_loss(
+            # ph_loss.mean() (trainer.py:742): the 1/(B*H*W) is folded into the kernel's reduction
+            ph_loss, pred, _ = photometric_loss(
                 mode, automask, outputs[("rgb_rec", side)], target, src, mask_novel,
-                outputs.get(("nll_rec", side)), outputs.get(("nll_auto_rec", side)))
-            ph_loss = ph_sum * inv_count  # ph_loss.mean(), trainer.py:742
+                outputs.get(("nll_rec", side)), outputs.get(("nll_auto_rec", side)), scale=inv_count)
             add("loss/ph_loss", ph_loss)
             total = ph_loss
             if pc_net is not None:
@@ -231,7 +231,7 @@ class HotPathMixin:
         losses = {}
         for k, v in acc.items():  # trainer.py:765-766
             if v is None:
-                v = torch.zeros((), device=src.device)
+                v = _zero(src.device)
             losses[k] = v / n_t if n_t != 1 else v
         if "disp" in outputs:
             x0 = int(0.2 * W)
@@ -276,6 +276,17 @@ class HotPathMixin:
         else:
             raise ValueError("unknown net_type %r" % (net_type,))
         return self.post_process_disp(outputs)
+
+
+_ZEROS: Dict = {}
+
+
+def _zero(device) -> torch.Tensor:
+    """A cached 0-dim zero per device (absent loss terms): no fill kernel per step."""
+    z = _ZEROS.get(device)
+    if z is None:
+        z = _ZEROS[device] = torch.zeros((), device=device)
+    return z
 
 
 def smooth_loss_disp(disp, img, gamma=1.0):

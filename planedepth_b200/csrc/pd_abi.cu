@@ -427,7 +427,7 @@ int pd_photometric_fwd(const pd_loss_desc* d, const pd_loss_in* in, pd_loss_out*
             else   { if (m) { wg ? launch_ssim_stream<false, true, true>(p, strips, segs, rs, g, st) : launch_ssim_stream<false, true, false>(p, strips, segs, rs, g, st); }
                      else   { wg ? launch_ssim_stream<false, false, true>(p, strips, segs, rs, g, st) : launch_ssim_stream<false, false, false>(p, strips, segs, rs, g, st); } }
             if ((rc = check_launch("ssim_l1_stream"))) return rc;
-            pd::reduce_partials_kernel<<<1, 1024, 0, st>>>(p.partials, nparts, out->ph_sum);
+            pd::reduce_partials_kernel<<<1, 1024, 0, st>>>(p.partials, nparts, out->ph_sum, d->out_scale != 0.0f ? d->out_scale : 1.0f);
             return check_launch("reduce_partials");
         }
         const dim3 g = loss_grid(d);
@@ -450,7 +450,7 @@ int pd_photometric_fwd(const pd_loss_desc* d, const pd_loss_in* in, pd_loss_out*
         }
     }
     if ((rc = check_launch("photometric_fwd"))) return rc;
-    pd::reduce_partials_kernel<<<1, 1024, 0, st>>>(p.partials, nparts, out->ph_sum);
+    pd::reduce_partials_kernel<<<1, 1024, 0, st>>>(p.partials, nparts, out->ph_sum, d->out_scale != 0.0f ? d->out_scale : 1.0f);
     return check_launch("reduce_partials");
 }
 

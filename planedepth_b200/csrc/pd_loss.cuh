@@ -573,12 +573,12 @@ __global__ void __launch_bounds__(EW_THREADS) elementwise_fwd_kernel(const LossP
 }
 
 // deterministic second stage: one CTA sums the per-CTA partials in a fixed order
-__global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ partials, int64_t n, float* __restrict__ out) {
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ partials, int64_t n, float* __restrict__ out, float scale) {
     __shared__ float red[32];
     float acc = 0.0f;
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += partials[i];
     float t = block_sum(acc, red);
-    if (threadIdx.x == 0) *out = t;
+    if (threadIdx.x == 0) *out = t * scale;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __re
 // ------------------------------------------------------------------------------------------------
 template <bool MIXTURE, bool HASMASK>
 __global__ void __launch_bounds__(EW_THREADS) photometric_bwd_kernel(const LossParams p) {
-    const float gph = __ldg(p.gout.g_ph_sum);
+    const float gph = __ldg(p.gout.g_ph_sum) * (p.d.out_scale != 0.0f ? p.d.out_scale : 1.0f);
     const int64_t total = (int64_t)p.d.B * p.hw;
     for (int64_t pix = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; pix < total; pix += (int64_t)gridDim.x * EW_THREADS) {
         const int b = (int)(pix / p.hw);
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(EW_THREADS) photometric_bwd_kernel(const LossP
 // same, 4 consecutive pixels per thread (H*W % 4 == 0 and 16-byte aligned pointers)
 template <bool MIXTURE, bool HASMASK>
 __global__ void __launch_bounds__(EW_THREADS) photometric_bwd_kernel_v4(const LossParams p) {
-    const float gph = __ldg(p.gout.g_ph_sum);
+    const float gph = __ldg(p.gout.g_ph_sum) * (p.d.out_scale != 0.0f ? p.d.out_scale : 1.0f);
     const int64_t hw4 = p.hw / 4;
     for (int64_t q = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; q < p.total4; q += (int64_t)gridDim.x * EW_THREADS) {
         const int b = (int)(q / hw4);

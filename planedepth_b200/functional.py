@@ -220,12 +220,13 @@ class _Photometric(torch.autograd.Function):
     is a streaming scale-and-add."""
 
     @staticmethod
-    def forward(ctx, mode: int, automask: bool, want_map: bool, rgb_rec, tgt, src, mask_novel, nll, nll_auto):
+    def forward(ctx, mode: int, automask: bool, want_map: bool, scale: float, rgb_rec, tgt, src, mask_novel, nll, nll_auto):
         lib = L.lib()
         B, _, H, W = rgb_rec.shape
         dev = rgb_rec.device
         mixture = mode == L.PD_LOSS_MIXTURE
-        desc = L.LossDesc(B=B, H=H, W=W, loss_mode=mode, automask=int(automask), has_mask_novel=int(mask_novel is not None))
+        desc = L.LossDesc(B=B, H=H, W=W, loss_mode=mode, automask=int(automask), has_mask_novel=int(mask_novel is not None),
+                          out_scale=float(scale))
         tin = L.LossIn(rgb_rec=_ptr(rgb_rec), tgt=_ptr(tgt), src=_ptr(src), mask_novel=_ptr(mask_novel), nll=_ptr(nll), nll_auto=_ptr(nll_auto))
         pred = torch.empty_like(rgb_rec) if mask_novel is not None else None
         ph_map = torch.empty(B, 1, H, W, device=dev) if want_map else None
@@ -261,11 +262,12 @@ class _Photometric(torch.autograd.Function):
         gin = L.LossGradIn(g_rgb_rec=_ptr(g_rgb), g_nll=_ptr(g_nll))
         _call("pd_photometric_bwd", lib.pd_photometric_bwd, C.byref(ctx.desc), C.byref(tin), C.byref(saved), C.byref(gout), C.byref(gin), None,
               _stream())
-        return (None, None, None, g_rgb, None, None, None, g_nll, None)
+        return (None, None, None, None, g_rgb, None, None, None, g_nll, None)
 
 
-def photometric_loss(mode: int, automask: bool, rgb_rec, tgt, src=None, mask_novel=None, nll=None, nll_auto=None, want_map=False):
-    """Returns (ph_sum 0-dim, pred [B,3,H,W], ph_map | None).  ``pred`` is ``rgb_rec`` itself (same
+def photometric_loss(mode: int, automask: bool, rgb_rec, tgt, src=None, mask_novel=None, nll=None, nll_auto=None, want_map=False,
+                     scale: float = 1.0):
+    """Returns (scale * ph_sum 0-dim, pred [B,3,H,W], ph_map | None); ``scale = 1/(B*H*W)`` makes the first ``ph.mean()``.  ``pred`` is ``rgb_rec`` itself (same
     autograd node) when there is no ``mask_novel`` blend."""
     rgb_rec = _f32c(rgb_rec, "rgb_rec")
     tgt = _f32c(tgt, "tgt").detach()
@@ -277,7 +279,7 @@ def photometric_loss(mode: int, automask: bool, rgb_rec, tgt, src=None, mask_nov
         nll_auto = _f32c(nll_auto, "nll_auto").detach() if automask else None
     else:
         nll = nll_auto = None
-    ph_sum, pred, ph_map = _Photometric.apply(mode, automask, want_map, rgb_rec, tgt, src, mask_novel, nll, nll_auto)
+    ph_sum, pred, ph_map = _Photometric.apply(mode, automask, want_map, float(scale), rgb_rec, tgt, src, mask_novel, nll, nll_auto)
     return ph_sum, (pred if mask_novel is not None else rgb_rec), (ph_map if want_map else None)
 
 
