@@ -476,7 +476,8 @@ def run_ours(args):
         return
     cpu = None
     if ws == 1 and not args.no_cpu_baseline:
-        cpu, _ = time_cpu(args.config, 2, 2, 1)
+        # bounded sample of the same workload on the host cores: ~10-20 s of CPU work (26 steps of B=4 images at ~0.35 s)
+        cpu, _ = time_cpu(args.config, min(B, 4), 24, 2)
     line = {
         "metric": METRIC, "value": D.aggregate_throughput(B, ws, ms_step), "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

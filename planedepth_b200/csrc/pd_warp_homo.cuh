@@ -49,6 +49,12 @@ __device__ __forceinline__ HTaps make_htaps(float x, float y, int W, int H) {
     HTaps t;
     t.rx1 = x - fx0, t.rx0 = (fx0 + 1.0f) - x;
     t.ry1 = y - fy0, t.ry0 = (fy0 + 1.0f) - y;
+    if ((unsigned)x0 < (unsigned)(W - 1) && (unsigned)y0 < (unsigned)(H - 1)) {  // all four taps inside (the common case)
+        t.ix0 = t.ix1 = t.iy0 = t.iy1 = true;
+        t.o00 = y0 * W + x0, t.o01 = t.o00 + 1, t.o10 = t.o00 + W, t.o11 = t.o10 + 1;
+        t.w00 = t.rx0 * t.ry0, t.w01 = t.rx1 * t.ry0, t.w10 = t.rx0 * t.ry1, t.w11 = t.rx1 * t.ry1;
+        return t;
+    }
     t.ix0 = (unsigned)x0 < (unsigned)W, t.ix1 = (unsigned)(x0 + 1) < (unsigned)W;
     t.iy0 = (unsigned)y0 < (unsigned)H, t.iy1 = (unsigned)(y0 + 1) < (unsigned)H;
     const int xa = min(max(x0, 0), W - 1), xb = min(max(x0 + 1, 0), W - 1);
@@ -137,22 +143,50 @@ __global__ void __launch_bounds__(HT) homo_fwd_kernel(const WarpParams p, const 
         float4 h0, h1, h2;
         load_plane_params(sh, n, h0, h1, h2);
         const HCoord c = homo_coords(h0, h1, h2, fx, fy, rx, ry, rz);
-        const HTaps t = make_htaps(rt(c.u, p.wm1, rcp_w), rt(c.v, p.hm1, rcp_h), W, H);
-        const float4 a = __ldg(src + t.o00), bq = __ldg(src + t.o01), cq = __ldg(src + t.o10), d = __ldg(src + t.o11);
-        const float l00 = __ldg(lg + t.o00), l01 = __ldg(lg + t.o01), l10 = __ldg(lg + t.o10), l11 = __ldg(lg + t.o11);
-        const float cr = hblend(a.x, bq.x, cq.x, d.x, t) * c.m;
-        const float cg = hblend(a.y, bq.y, cq.y, d.y, t) * c.m;
-        const float cb = hblend(a.z, bq.z, cq.z, d.z, t) * c.m;
-        const float l2 = hblend(l00, l01, l10, l11, t) * c.m * kLog2e;
+        float cr = 0.0f, cg = 0.0f, cb = 0.0f, l2 = 0.0f, sraw = 0.0f;  // a masked plane enters with logit 0, colour 0 (:580-583)
+        if (c.m != 0.0f) {
+            float su = rt(c.u, p.wm1, rcp_w), sv = rt(c.v, p.hm1, rcp_h);
+            su = fminf(fmaxf(su, -2.0f), (float)(W + 1));
+            sv = fminf(fmaxf(sv, -2.0f), (float)(H + 1));
+            const float fx0 = floorf(su), fy0 = floorf(sv);
+            const int x0 = (int)fx0, y0 = (int)fy0;
+            if ((unsigned)x0 < (unsigned)(W - 1) && (unsigned)y0 < (unsigned)(H - 1)) {
+                // all four taps inside the image (the common case): one base offset, immediate / row offsets, raw weights
+                const float wx1 = su - fx0, wx0 = (fx0 + 1.0f) - su, wy1 = sv - fy0, wy0 = (fy0 + 1.0f) - sv;
+                const float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
+                const int o = y0 * W + x0;
+                const float4* s0 = src + o;
+                const float* g0 = lg + o;
+                const float4 a = __ldg(s0), bq = __ldg(s0 + 1), cq = __ldg(s0 + W), d = __ldg(s0 + W + 1);
+                const float l00 = __ldg(g0), l01 = __ldg(g0 + 1), l10 = __ldg(g0 + W), l11 = __ldg(g0 + W + 1);
+                cr = fmaf(d.x, w11, fmaf(cq.x, w10, fmaf(bq.x, w01, a.x * w00)));
+                cg = fmaf(d.y, w11, fmaf(cq.y, w10, fmaf(bq.y, w01, a.y * w00)));
+                cb = fmaf(d.z, w11, fmaf(cq.z, w10, fmaf(bq.z, w01, a.z * w00)));
+                l2 = fmaf(l11, w11, fmaf(l10, w10, fmaf(l01, w01, l00 * w00))) * kLog2e;
+                if (MIX) {
+                    const float* q0 = sgp + (int64_t)n * p.hw + o;
+                    sraw = fmaf(__ldg(q0 + W + 1), w11, fmaf(__ldg(q0 + W), w10, fmaf(__ldg(q0 + 1), w01, __ldg(q0) * w00)));
+                }
+            } else {
+                const HTaps t = make_htaps(su, sv, W, H);
+                const float4 a = __ldg(src + t.o00), bq = __ldg(src + t.o01), cq = __ldg(src + t.o10), d = __ldg(src + t.o11);
+                const float l00 = __ldg(lg + t.o00), l01 = __ldg(lg + t.o01), l10 = __ldg(lg + t.o10), l11 = __ldg(lg + t.o11);
+                cr = hblend(a.x, bq.x, cq.x, d.x, t);
+                cg = hblend(a.y, bq.y, cq.y, d.y, t);
+                cb = hblend(a.z, bq.z, cq.z, d.z, t);
+                l2 = hblend(l00, l01, l10, l11, t) * kLog2e;
+                if (MIX) {
+                    const float* sp = sgp + (int64_t)n * p.hw;
+                    sraw = hblend(__ldg(sp + t.o00), __ldg(sp + t.o01), __ldg(sp + t.o10), __ldg(sp + t.o11), t);
+                }
+            }
+        }
         const float mnew = fmaxf(Mx, l2);
         const float sc = fast_exp2(Mx - mnew);
         const float e = fast_exp2(l2 - mnew);
         Mx = mnew;
         S = fmaf(S, sc, e);
         if (MIX) {
-            const float* sp = sgp + (int64_t)n * p.hw;
-            const float s00 = __ldg(sp + t.o00), s01 = __ldg(sp + t.o01), s10 = __ldg(sp + t.o10), s11 = __ldg(sp + t.o11);
-            const float sraw = hblend(s00, s01, s10, s11, t) * c.m;
             const float sg = fminf(fmaxf(sraw, 0.01f), 1.0f);  // trainer.py:597
             const float inv = 1.0f / sg;
             const float es = e * inv;
@@ -279,21 +313,25 @@ __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const 
         float4 h0, h1, h2;
         load_plane_params(sh, n, h0, h1, h2);
         const HCoord c = homo_coords(h0, h1, h2, fx, fy, rx, ry, rz);
-        const HTaps t = make_htaps(rt(c.u, p.wm1, rcp_w), rt(c.v, p.hm1, rcp_h), W, H);
+        float gqx = 0.0f, gqy = 0.0f, gqz = 0.0f, dl = 0.0f, dsg = 0.0f;
+        HTaps t;
+        const bool act = c.m != 0.0f;  // every gradient of a masked plane carries the factor m = 0 (:580)
+        if (act) {
+        t = make_htaps(rt(c.u, p.wm1, rcp_w), rt(c.v, p.hm1, rcp_h), W, H);
         const float4 a = __ldg(src + t.o00), bq = __ldg(src + t.o01), cq = __ldg(src + t.o10), d = __ldg(src + t.o11);
         const float l00 = __ldg(lg + t.o00), l01 = __ldg(lg + t.o01), l10 = __ldg(lg + t.o10), l11 = __ldg(lg + t.o11);
-        const float cr = hblend(a.x, bq.x, cq.x, d.x, t) * c.m;
-        const float cg = hblend(a.y, bq.y, cq.y, d.y, t) * c.m;
-        const float cb = hblend(a.z, bq.z, cq.z, d.z, t) * c.m;
-        const float l = hblend(l00, l01, l10, l11, t) * c.m;
+        const float cr = hblend(a.x, bq.x, cq.x, d.x, t);
+        const float cg = hblend(a.y, bq.y, cq.y, d.y, t);
+        const float cb = hblend(a.z, bq.z, cq.z, d.z, t);
+        const float l = hblend(l00, l01, l10, l11, t);
         const float pi = fast_exp2(fmaf(l, kLog2e, -Ml2)) * invS;
         const float Gn = g0 * cr + g1 * cg + g2 * cb;
-        float dl, dcr, dcg, dcb, dsg = 0.0f;
+        float dcr, dcg, dcb;
         float s00 = 0, s01 = 0, s10 = 0, s11 = 0;
         if (MIX) {
             const float* sp = sgp + (int64_t)n * p.hw;
             s00 = __ldg(sp + t.o00), s01 = __ldg(sp + t.o01), s10 = __ldg(sp + t.o10), s11 = __ldg(sp + t.o11);
-            const float sraw = hblend(s00, s01, s10, s11, t) * c.m;
+            const float sraw = hblend(s00, s01, s10, s11, t);
             const float sg = fminf(fmaxf(sraw, 0.01f), 1.0f);
             const float inv = 1.0f / sg;
             const float w = pi * inv * Zinv;  // compositing weight
@@ -311,10 +349,6 @@ __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const 
             dl = pi * (Gn - Gbar);
             dcr = pi * g0, dcg = pi * g1, dcb = pi * g2;
         }
-        // through the mask multiply
-        dl *= c.m, dsg *= c.m, dcr *= c.m, dcg *= c.m, dcb *= c.m;
-        if (glg && dl != 0.0f) hscatter(glg + (int64_t)n * p.hw, t, dl);
-        if (MIX && gsg && dsg != 0.0f) hscatter(gsg + (int64_t)n * p.hw, t, dsg);
         if (want_h) {
             // The sample is linear in the tap values, so the coordinate gradient (blend_grad() of pd_device.cuh, i.e. ATen's
             // gix / giy) is taken once on the combined tap T = dcr*r + dcg*g + dcb*b + dl*logit (+ dsg*sigma); taps outside
@@ -329,8 +363,13 @@ __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const 
             const float gx = (tne - tnw) * t.ry0 + (tse - tsw) * t.ry1;
             const float gy = (tsw - tnw) * t.rx0 + (tse - tne) * t.rx1;
             // u = qx / zc, v = qy / zc, zc = max(qz, 1e-7)   (layers.py:227-228)
-            const float gqx = gx * c.zinv, gqy = gy * c.zinv;
-            const float gqz = -(gx * c.u + gy * c.v) * c.zinv * c.dz;
+            gqx = gx * c.zinv, gqy = gy * c.zinv;
+            gqz = -(gx * c.u + gy * c.v) * c.zinv * c.dz;
+        }
+        }
+        if (act && glg && dl != 0.0f) hscatter(glg + (int64_t)n * p.hw, t, dl);
+        if (MIX && act && gsg && dsg != 0.0f) hscatter(gsg + (int64_t)n * p.hw, t, dsg);
+        if (want_h) {
             // dL/dH[i][j] = sum_pixels gq_i * (x, y, 1)_j; y is the same for the whole warp
             const float v8[8] = {gqx, gqy, gqz, gqx * fx, gqy * fx, gqz * fx, 0.0f, 0.0f};
             const float tot = warp_reduce_scatter8(v8);
