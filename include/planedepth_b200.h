@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PD_ABI_VERSION 5
+#define PD_ABI_VERSION 6
 
 typedef void* pd_stream_t; /* a cudaStream_t */
 
@@ -204,6 +204,26 @@ int pd_photometric_fwd(const pd_loss_desc* desc, const pd_loss_in* in, pd_loss_o
  * Only in->mask_novel is read from `in` (iff has_mask_novel). */
 int pd_photometric_bwd(const pd_loss_desc* desc, const pd_loss_in* in, const pd_loss_out* saved,
                        const pd_loss_grad_out* gout, pd_loss_grad_in* gin, void* workspace, pd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Edge-aware smoothness term of compute_losses: get_smooth_loss_disp (layers.py:243-256) on the crop
+ * disp[..., x0:], color[..., x0:] with x0 = int(0.2 W) (trainer.py:768-771):
+ *   loss = mean_x |d[x]-d[x+1]| exp(-gamma mean_c|I[x]-I[x+1]|) + mean_y (the same along y)
+ * Gradient w.r.t. disp only (the image is data).  Needs W - x0 >= 2 and H >= 2.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pd_smooth_desc {
+    int32_t B, H, W;
+    int32_t x0;   /* first column of the crop */
+    float gamma;  /* opt.gamma_smooth */
+} pd_smooth_desc;
+
+size_t pd_smooth_loss_workspace_bytes(const pd_smooth_desc* desc);
+/* disp [B,1,H,W], img [B,3,H,W] contiguous; loss [1] */
+int pd_smooth_loss_fwd(const pd_smooth_desc* desc, const float* disp, const float* img, float* loss, void* workspace,
+                       pd_stream_t stream);
+/* g_loss [1] device scalar; g_disp [B,1,H,W], fully written (zero left of the crop) */
+int pd_smooth_loss_bwd(const pd_smooth_desc* desc, const float* disp, const float* img, const float* g_loss,
+                       float* g_disp, pd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Occlusion masks + post-processed disparity: replaces trainer.py:421-466 (the part of

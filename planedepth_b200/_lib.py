@@ -23,7 +23,7 @@ PD_WARP_DISP, PD_WARP_HOMOGRAPHY, PD_WARP_DEPTH = 0, 1, 2
 PD_LOSS_L1, PD_LOSS_MIXTURE, PD_LOSS_SSIM_L1 = 0, 1, 2
 PD_MASK_NONE, PD_MASK_F32, PD_MASK_U8 = 0, 1, 2
 PD_FLAG_EXACT_COORDS = 1
-ABI_VERSION = 5  # PD_ABI_VERSION in include/planedepth_b200.h
+ABI_VERSION = 6  # PD_ABI_VERSION in include/planedepth_b200.h
 PD_STATS_PLAIN, PD_STATS_MIXTURE = 2, 4
 
 EXPORTS = [
@@ -31,6 +31,7 @@ EXPORTS = [
     "pd_warp_composite_workspace_bytes", "pd_warp_composite_stats_bytes", "pd_warp_composite_fwd", "pd_warp_composite_bwd",
     "pd_photometric_workspace_bytes", "pd_photometric_fwd", "pd_photometric_bwd", "pd_debug_roundtrip",
     "pd_occlusion_masks_workspace_bytes", "pd_occlusion_masks_fwd",
+    "pd_smooth_loss_workspace_bytes", "pd_smooth_loss_fwd", "pd_smooth_loss_bwd",
 ]
 
 
@@ -63,6 +64,10 @@ class WarpGradOut(C.Structure):
 class WarpGradIn(C.Structure):
     _fields_ = [("g_logits", C.c_void_p), ("g_sigma", C.c_void_p), ("g_disp", C.c_void_p),
                 ("g_disp_stride", Strides4), ("g_hmat", C.c_void_p)]
+
+
+class SmoothDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("x0", C.c_int32), ("gamma", C.c_float)]
 
 
 class OcclDesc(C.Structure):
@@ -166,6 +171,12 @@ def lib() -> C.CDLL:
     L.pd_photometric_bwd.restype = C.c_int
     L.pd_photometric_bwd.argtypes = [C.POINTER(LossDesc), C.POINTER(LossIn), C.POINTER(LossOut), C.POINTER(LossGradOut), C.POINTER(LossGradIn),
                                      C.c_void_p, C.c_void_p]
+    L.pd_smooth_loss_workspace_bytes.restype = C.c_size_t
+    L.pd_smooth_loss_workspace_bytes.argtypes = [C.POINTER(SmoothDesc)]
+    L.pd_smooth_loss_fwd.restype = C.c_int
+    L.pd_smooth_loss_fwd.argtypes = [C.POINTER(SmoothDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pd_smooth_loss_bwd.restype = C.c_int
+    L.pd_smooth_loss_bwd.argtypes = [C.POINTER(SmoothDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pd_occlusion_masks_workspace_bytes.restype = C.c_size_t
     L.pd_occlusion_masks_workspace_bytes.argtypes = [C.POINTER(OcclDesc)]
     L.pd_occlusion_masks_fwd.restype = C.c_int

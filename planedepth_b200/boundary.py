@@ -27,7 +27,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib as L
-from .functional import WarpConfig, occlusion_masks, photometric_loss, warp_composite
+from .functional import WarpConfig, occlusion_masks, photometric_loss, smooth_loss, warp_composite
 
 _WARP = {"disp_warp": L.PD_WARP_DISP, "homography_warp": L.PD_WARP_HOMOGRAPHY, "depth_warp": L.PD_WARP_DEPTH}
 
@@ -235,7 +235,7 @@ class HotPathMixin:
             losses[k] = v / n_t if n_t != 1 else v
         if "disp" in outputs:
             x0 = int(0.2 * W)
-            sm = smooth_loss_disp(outputs["disp"][..., x0:], inputs[("color", "l")][..., x0:], _flag(opt, "gamma_smooth", 2))
+            sm = smooth_loss(outputs["disp"], inputs[("color", "l")], x0, _flag(opt, "gamma_smooth", 2))  # trainer.py:768-771
             losses["loss/smooth_loss"] = sm
             losses["loss/total_loss"] = losses["loss/total_loss"] + _flag(opt, "alpha_smooth", 0.04) * sm
         return losses
@@ -289,20 +289,7 @@ def _zero(device) -> torch.Tensor:
     return z
 
 
-def smooth_loss_disp(disp, img, gamma=1.0):
-    """Edge-aware first-order smoothness (layers.py:243-256) — out of the hot path, kept in PyTorch."""
-    gdx = (disp[:, :, :, :-1] - disp[:, :, :, 1:]).abs()
-    gdy = (disp[:, :, :-1, :] - disp[:, :, 1:, :]).abs()
-    gix = (img[:, :, :, :-1] - img[:, :, :, 1:]).abs().mean(1, keepdim=True)
-    giy = (img[:, :, :-1, :] - img[:, :, 1:, :]).abs().mean(1, keepdim=True)
-    return (gdx * torch.exp(-gamma * gix)).mean() + (gdy * torch.exp(-gamma * giy)).mean()
-
-
-class HotPath(HotPathMixin):
-    """Stand-alone carrier of the attributes the two methods read from ``self`` (what tests, bench.py
-    and smoke() instantiate instead of the full Trainer, whose constructor needs NCCL + KITTI)."""
-
-    def __init__(self, opt, target_sides=None, pc_net=None, photometric: Optional[str] = None, materialize_layered: bool = False,
+def __init__(self, opt, target_sides=None, pc_net=None, photometric: Optional[str] = None, materialize_layered: bool = False,
                  exact_coords: bool = False, disp_rowwise: bool = False):
         self.opt = opt
         if target_sides is None:

@@ -307,6 +307,62 @@ int pd_warp_composite_bwd(const pd_warp_desc* d, const pd_warp_in* in, const pd_
 }
 
 // ---------------------------------------------------------------------------------------------
+// smoothness term (layers.py:243-256)
+// ---------------------------------------------------------------------------------------------
+namespace {
+int validate_smooth(const pd_smooth_desc* d, const float* disp, const float* img) {
+    if (!d || !disp || !img) return fail(PD_ERR_ARG, "NULL argument");
+    if (d->B < 1 || d->H < 2 || d->x0 < 0 || d->W - d->x0 < 2) return fail(PD_ERR_SHAPE, "smoothness needs H >= 2 and W - x0 >= 2");
+    return PD_OK;
+}
+unsigned smooth_grid(int64_t items) {
+    const int64_t want = (items + pd::EW_THREADS - 1) / pd::EW_THREADS;
+    return (unsigned)(want < 148 * 8 ? (want < 1 ? 1 : want) : 148 * 8);
+}
+}  // namespace
+
+size_t pd_smooth_loss_workspace_bytes(const pd_smooth_desc* d) {
+    (void)d;
+    return (size_t)2 * 148 * 8 * sizeof(float);
+}
+
+int pd_smooth_loss_fwd(const pd_smooth_desc* d, const float* disp, const float* img, float* loss, void* workspace, pd_stream_t stream) {
+    int rc = validate_smooth(d, disp, img);
+    if (rc) return rc;
+    if (!loss) return fail(PD_ERR_ARG, "loss must not be NULL");
+    if (!workspace) return fail(PD_ERR_WORKSPACE, "workspace of pd_smooth_loss_workspace_bytes() required");
+    if ((rc = check_device())) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    pd::SmoothParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = d->B, p.H = d->H, p.W = d->W, p.x0 = d->x0, p.gamma = d->gamma;
+    p.disp = disp, p.img = img, p.partials = (float*)workspace, p.out = loss, p.hw = (int64_t)d->H * d->W;
+    const int Wc = d->W - d->x0;
+    const unsigned g = smooth_grid((int64_t)d->B * d->H * Wc);
+    pd::smooth_fwd_kernel<<<g, pd::EW_THREADS, 0, st>>>(p);
+    if ((rc = check_launch("smooth_fwd"))) return rc;
+    const float inv_nx = 1.0f / ((float)d->B * d->H * (Wc - 1)), inv_ny = 1.0f / ((float)d->B * (d->H - 1) * Wc);
+    pd::smooth_reduce_kernel<<<1, 1024, 0, st>>>(p.partials, (int)g, inv_nx, inv_ny, loss);
+    return check_launch("smooth_reduce");
+}
+
+int pd_smooth_loss_bwd(const pd_smooth_desc* d, const float* disp, const float* img, const float* g_loss, float* g_disp, pd_stream_t stream) {
+    int rc = validate_smooth(d, disp, img);
+    if (rc) return rc;
+    if (!g_loss || !g_disp) return fail(PD_ERR_ARG, "g_loss / g_disp must not be NULL");
+    if ((rc = check_device())) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    pd::SmoothParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = d->B, p.H = d->H, p.W = d->W, p.x0 = d->x0, p.gamma = d->gamma;
+    p.disp = disp, p.img = img, p.g_loss = g_loss, p.g_disp = g_disp, p.hw = (int64_t)d->H * d->W;
+    const int Wc = d->W - d->x0;
+    const float inv_nx = 1.0f / ((float)d->B * d->H * (Wc - 1)), inv_ny = 1.0f / ((float)d->B * (d->H - 1) * Wc);
+    pd::smooth_bwd_kernel<<<smooth_grid((int64_t)d->B * p.hw), pd::EW_THREADS, 0, st>>>(p, inv_nx, inv_ny);
+    return check_launch("smooth_bwd");
+}
+
+// ---------------------------------------------------------------------------------------------
 // occlusion masks / post-processed disparity (trainer.py:421-466)
 // ---------------------------------------------------------------------------------------------
 size_t pd_occlusion_masks_workspace_bytes(const pd_occl_desc* d) {

@@ -639,3 +639,88 @@ __global__ void __launch_bounds__(EW_THREADS) photometric_bwd_kernel_v4(const Lo
 }
 
 }  // namespace pd
+
+// ------------------------------------------------------------------------------------------------
+// Edge-aware first-order smoothness of the composited disparity (layers.py:243-256), on the crop
+// [..., x0:] that compute_losses hands over (trainer.py:768-771):
+//   loss = mean_{x pairs} |d[x]-d[x+1]| exp(-gamma mean_c|I[x]-I[x+1]|) + mean_{y pairs} (same along y)
+// One pass forward (two deterministic sums), one pass backward (gradient w.r.t. the disparity only; the
+// image is data).  Replaces ~12 elementwise launches forward and ~20 backward on [B,1,H,W] tensors.
+// ------------------------------------------------------------------------------------------------
+namespace pd {
+
+struct SmoothParams {
+    int B, H, W, x0;
+    float gamma;
+    const float* disp;  // [B,1,H,W]
+    const float* img;   // [B,3,H,W]
+    float* partials;    // [2][gridDim.x]
+    float* out;         // [1]
+    const float* g_loss;
+    float* g_disp;      // [B,1,H,W]
+    int64_t hw;
+};
+
+// weight of the pixel pair (o, o + step): exp(-gamma * mean_c |I[o] - I[o + step]|)
+__device__ __forceinline__ float smooth_weight(const float* __restrict__ im, int64_t hw, int64_t o, int64_t step, float gamma) {
+    const float g = (fabsf(__ldg(im + o) - __ldg(im + o + step)) + fabsf(__ldg(im + hw + o) - __ldg(im + hw + o + step)) +
+                     fabsf(__ldg(im + 2 * hw + o) - __ldg(im + 2 * hw + o + step))) * (1.0f / 3.0f);
+    return fast_exp(-gamma * g);
+}
+
+__global__ void __launch_bounds__(EW_THREADS) smooth_fwd_kernel(const SmoothParams p) {
+    __shared__ float red[EW_THREADS / 32];
+    const int Wc = p.W - p.x0;
+    const int64_t total = (int64_t)p.B * p.H * Wc;
+    float ax = 0.0f, ay = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
+        const int b = (int)(i / ((int64_t)p.H * Wc));
+        const int r = (int)(i - (int64_t)b * p.H * Wc);
+        const int y = r / Wc, x = p.x0 + (r - y * Wc);
+        const int64_t o = (int64_t)y * p.W + x;
+        const float* d = p.disp + (int64_t)b * p.hw;
+        const float* im = p.img + (int64_t)b * 3 * p.hw;
+        const float dc = __ldg(d + o);
+        if (x + 1 < p.W) ax += fabsf(dc - __ldg(d + o + 1)) * smooth_weight(im, p.hw, o, 1, p.gamma);
+        if (y + 1 < p.H) ay += fabsf(dc - __ldg(d + o + p.W)) * smooth_weight(im, p.hw, o, p.W, p.gamma);
+    }
+    float t = block_sum(ax, red);
+    if (threadIdx.x == 0) p.partials[blockIdx.x] = t;
+    __syncthreads();
+    t = block_sum(ay, red);
+    if (threadIdx.x == 0) p.partials[gridDim.x + blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(1024) smooth_reduce_kernel(const float* __restrict__ partials, int n, float inv_nx, float inv_ny, float* __restrict__ out) {
+    __shared__ float red[32];
+    float ax = 0.0f, ay = 0.0f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) ax += partials[i], ay += partials[n + i];
+    const float tx = block_sum(ax, red);
+    __syncthreads();
+    const float ty = block_sum(ay, red);
+    if (threadIdx.x == 0) *out = tx * inv_nx + ty * inv_ny;  // grad_disp_x.mean() + grad_disp_y.mean()
+}
+
+__global__ void __launch_bounds__(EW_THREADS) smooth_bwd_kernel(const SmoothParams p, float inv_nx, float inv_ny) {
+    const float gl = __ldg(p.g_loss);
+    const float kx = gl * inv_nx, ky = gl * inv_ny;
+    const int64_t total = (int64_t)p.B * p.hw;
+    for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
+        const int b = (int)(i / p.hw);
+        const int64_t o = i - (int64_t)b * p.hw;
+        const int y = (int)(o / p.W), x = (int)(o - (int64_t)y * p.W);
+        float g = 0.0f;
+        if (x >= p.x0) {
+            const float* d = p.disp + (int64_t)b * p.hw;
+            const float* im = p.img + (int64_t)b * 3 * p.hw;
+            const float dc = __ldg(d + o);
+            if (x + 1 < p.W) g += kx * sgnf(dc - __ldg(d + o + 1)) * smooth_weight(im, p.hw, o, 1, p.gamma);
+            if (x - 1 >= p.x0) g -= kx * sgnf(__ldg(d + o - 1) - dc) * smooth_weight(im, p.hw, o - 1, 1, p.gamma);
+            if (y + 1 < p.H) g += ky * sgnf(dc - __ldg(d + o + p.W)) * smooth_weight(im, p.hw, o, p.W, p.gamma);
+            if (y >= 1) g -= ky * sgnf(__ldg(d + o - p.W) - dc) * smooth_weight(im, p.hw, o - p.W, p.W, p.gamma);
+        }
+        p.g_disp[i] = g;
+    }
+}
+
+}  // namespace pd

@@ -308,3 +308,37 @@ def occlusion_masks(logits, probability, disp_layered, disp, exact_coords: bool 
         out = L.OcclOut(o_l=_ptr(o_l), o_fr=_ptr(o_fr), mask_novel=_ptr(mask_novel), disp_pp=_ptr(disp_pp))
         _call("pd_occlusion_masks_fwd", lib.pd_occlusion_masks_fwd, C.byref(desc), C.byref(tin), C.byref(out), ws.data_ptr(), _stream())
     return disp_pp, mask_novel, o_l, o_fr
+
+
+class _SmoothLoss(torch.autograd.Function):
+    """pd_smooth_loss_fwd / _bwd: get_smooth_loss_disp (layers.py:243-256) on the crop [..., x0:] (trainer.py:768-771)."""
+
+    @staticmethod
+    def forward(ctx, x0: int, gamma: float, disp, img):
+        lib = L.lib()
+        B, _, H, W = disp.shape
+        desc = L.SmoothDesc(B=B, H=H, W=W, x0=int(x0), gamma=float(gamma))
+        loss = torch.empty((), device=disp.device, dtype=torch.float32)
+        ws = torch.empty(lib.pd_smooth_loss_workspace_bytes(C.byref(desc)) // 4, device=disp.device, dtype=torch.float32)
+        _call("pd_smooth_loss_fwd", lib.pd_smooth_loss_fwd, C.byref(desc), disp.data_ptr(), img.data_ptr(), loss.data_ptr(), ws.data_ptr(), _stream())
+        ctx.desc = desc
+        ctx.save_for_backward(disp, img)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.lib()
+        disp, img = ctx.saved_tensors
+        g = _f32c(g, "grad smooth loss")
+        g_disp = torch.empty_like(disp)
+        _call("pd_smooth_loss_bwd", lib.pd_smooth_loss_bwd, C.byref(ctx.desc), disp.data_ptr(), img.data_ptr(), g.data_ptr(), g_disp.data_ptr(), _stream())
+        return None, None, g_disp, None
+
+
+def smooth_loss(disp, img, x0: int = 0, gamma: float = 1.0):
+    """``get_smooth_loss_disp(disp[..., x0:], img[..., x0:], gamma)`` for ``disp`` [B,1,H,W], ``img`` [B,3,H,W] (0-dim tensor)."""
+    disp = _f32c(disp, "disp")
+    img = _f32c(img, "img").detach()
+    if disp.dim() != 4 or disp.shape[1] != 1 or img.dim() != 4 or img.shape[1] != 3 or disp.shape[-2:] != img.shape[-2:]:
+        raise ValueError("smooth_loss expects disp [B,1,H,W] and img [B,3,H,W]")
+    return _SmoothLoss.apply(int(x0), float(gamma), disp, img)

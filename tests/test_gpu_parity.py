@@ -394,3 +394,25 @@ def test_post_process_disp_matches_oracle(layout):
     assert not disp_pp.requires_grad and not mask_novel.requires_grad
     check(mask_novel, want_mn, TOL, "mask_novel", allow_frac=2e-4)
     check(disp_pp, want_pp, 20 * TOL, "disp_pp", allow_frac=2e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+# smoothness term (layers.py:243-256) through pd_smooth_loss_fwd / _bwd
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,x0,gamma", [((2, 24, 40), 8, 2.0), ((1, 192, 640), 128, 2.0), ((3, 7, 33), 0, 1.0), ((1, 2, 2), 0, 5.0)])
+def test_smooth_loss_matches_oracle(shape, x0, gamma):
+    from planedepth_b200.functional import smooth_loss
+
+    B, H, W = shape
+    g = torch.Generator().manual_seed(5)
+    disp = (1 + 20 * torch.rand(B, 1, H, W, generator=g)).round(decimals=1)  # ties: |d[x]-d[x+1]| = 0 has gradient 0
+    img = torch.rand(B, 3, H, W, generator=g)
+    dc = disp.clone().requires_grad_(True)
+    want = O.smooth_loss_disp(dc[..., x0:], img[..., x0:], gamma)
+    (3.0 * want).backward()
+    dg = disp.cuda().requires_grad_(True)
+    got = smooth_loss(dg, img.cuda(), x0, gamma)
+    (3.0 * got).backward()
+    check(got, want, 1e-5 * max(1.0, float(want)), "smooth loss")
+    scale = float(dc.grad.abs().max()) + 1e-12
+    check(dg.grad, dc.grad, TOL * scale, "grad disp")
