@@ -289,7 +289,11 @@ def _zero(device) -> torch.Tensor:
     return z
 
 
-def __init__(self, opt, target_sides=None, pc_net=None, photometric: Optional[str] = None, materialize_layered: bool = False,
+class HotPath(HotPathMixin):
+    """Stand-alone carrier of the attributes the methods read from ``self`` (what tests, bench.py
+    and smoke() instantiate instead of the full Trainer, whose constructor needs NCCL + KITTI)."""
+
+    def __init__(self, opt, target_sides=None, pc_net=None, photometric: Optional[str] = None, materialize_layered: bool = False,
                  exact_coords: bool = False, disp_rowwise: bool = False):
         self.opt = opt
         if target_sides is None:
