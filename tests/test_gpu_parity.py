@@ -413,6 +413,6 @@ def test_smooth_loss_matches_oracle(shape, x0, gamma):
     dg = disp.cuda().requires_grad_(True)
     got = smooth_loss(dg, img.cuda(), x0, gamma)
     (3.0 * got).backward()
-    check(got, want, 1e-5 * max(1.0, float(want)), "smooth loss")
+    check(got, want, 1e-5 * max(1.0, float(want.detach())), "smooth loss")
     scale = float(dc.grad.abs().max()) + 1e-12
     check(dg.grad, dc.grad, TOL * scale, "grad disp")
