@@ -416,3 +416,28 @@ def test_smooth_loss_matches_oracle(shape, x0, gamma):
     check(got, want, 1e-5 * max(1.0, float(want.detach())), "smooth loss")
     scale = float(dc.grad.abs().max()) + 1e-12
     check(dg.grad, dc.grad, TOL * scale, "grad disp")
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 storage of the network outputs (BASELINE.md parity gate: <= 2e-2): the boundary accepts bf16 logits / sigma,
+# computes in fp32 and hands bf16 gradients back
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("idx", [0, 2])
+def test_bf16_storage_within_2e_2(idx):
+    cfg = CONFIGS[idx]
+    cc = build_on("cpu", cfg, seed=500 + idx)
+    cg = build_on("cuda", cfg, seed=500 + idx)
+    lo = O.hot_path(cc.opt, cc.target_sides, cc.inputs, cc.outputs, pyramid_features)
+    lo["loss/total_loss"].backward()
+    leaves16 = {}
+    for k in ("logits", "sigma"):
+        if k in cg.outputs:
+            leaves16[k] = cg.outputs[k].detach().to(torch.bfloat16).requires_grad_(True)
+            cg.outputs[k] = leaves16[k]
+    lg = run_cuda(cg, None, "fused")
+    check(cg.outputs[("rgb_rec", "r")], cc.outputs[("rgb_rec", "r")], 2e-2, "rgb_rec (bf16 storage)")
+    check(lg["loss/total_loss"], lo["loss/total_loss"], 2e-2, "total loss (bf16 storage)")
+    for k, leaf in leaves16.items():
+        assert leaf.grad is not None and leaf.grad.dtype == torch.bfloat16
+        want = cc.leaves[k].grad
+        check(leaf.grad.float(), want, 2e-2 * float(want.abs().max()), "grad_%s (bf16 storage)" % k, allow_frac=2e-3)
