@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PD_ABI_VERSION 6
+#define PD_ABI_VERSION 7
 
 typedef void* pd_stream_t; /* a cudaStream_t */
 
@@ -224,6 +224,58 @@ int pd_smooth_loss_fwd(const pd_smooth_desc* desc, const float* disp, const floa
 /* g_loss [1] device scalar; g_disp [B,1,H,W], fully written (zero left of the crop) */
 int pd_smooth_loss_bwd(const pd_smooth_desc* desc, const float* disp, const float* img, const float* g_loss,
                        float* g_disp, pd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decoder tail: replaces networks/depth_decoder.py:258-291 (render_probability off) — what DepthDecoder.forward
+ * does after its dispconv / sigmaconv convolutions:
+ *   logits = raw * padding_mask (:259);  pi = softmax_n(logits) (:276)
+ *   mixture: sigma = clamp(sigmoid(sigma_raw), 0.01, 1) (:279-280);  w = pi / sigma * padding_mask;
+ *            probability = w / sum_n w (:282-285)                      (else probability = pi)
+ *   disp = sum_n probability * disp_layered (:288);  depth = 0.1 * 0.58 * W / disp (:290)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pd_tail_desc {
+    int32_t B, N, H, W;
+    int32_t mixture;
+    int32_t mask_dtype;      /* pd_mask_dtype of padding_mask */
+    pd_strides4 disp_stride; /* element strides of disp_layered (0 = broadcast) */
+    pd_strides4 mask_stride; /* element strides of padding_mask */
+} pd_tail_desc;
+
+typedef struct pd_tail_in {
+    const float* logits_raw;   /* [B,N,H,W] convs["dispconv"](x) */
+    const float* sigma_raw;    /* [B,N,H,W] convs["sigmaconv"](x); required iff mixture */
+    const float* disp_layered; /* strided */
+    const void* mask;          /* padding_mask, strided; NULL = all ones */
+} pd_tail_in;
+
+typedef struct pd_tail_out {
+    float* logits;      /* [B,N,H,W] outputs["logits"] */
+    float* sigma;       /* [B,N,H,W] outputs["sigma"]; required iff mixture */
+    float* probability; /* [B,N,H,W] outputs["probability"] */
+    float* pi;          /* [B,N,H,W] outputs["pi"] (mixture); may be NULL: nothing reads it */
+    float* disp;        /* [B,1,H,W] outputs["disp"] */
+    float* depth;       /* [B,1,H,W] outputs["depth"]; may be NULL */
+    float* stats;       /* [B,3,H,W] saved for pd_plane_tail_bwd */
+} pd_tail_out;
+
+typedef struct pd_tail_grad_out { /* upstream gradients, any may be NULL (= 0) */
+    const float* g_logits;      /* [B,N,H,W] */
+    const float* g_sigma;       /* [B,N,H,W] */
+    const float* g_probability; /* [B,N,H,W] */
+    const float* g_disp;        /* [B,1,H,W] */
+    const float* g_depth;       /* [B,1,H,W] */
+} pd_tail_grad_out;
+
+typedef struct pd_tail_grad_in { /* any may be NULL (= not needed) */
+    float* g_logits_raw;   /* [B,N,H,W] */
+    float* g_sigma_raw;    /* [B,N,H,W] mixture only */
+    float* g_disp_layered; /* laid out with g_disp_stride; a 0 stride means "reduce over that dimension" */
+    pd_strides4 g_disp_stride;
+} pd_tail_grad_in;
+
+int pd_plane_tail_fwd(const pd_tail_desc* desc, const pd_tail_in* in, pd_tail_out* out, pd_stream_t stream);
+int pd_plane_tail_bwd(const pd_tail_desc* desc, const pd_tail_in* in, const pd_tail_out* saved,
+                      const pd_tail_grad_out* gout, pd_tail_grad_in* gin, pd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Occlusion masks + post-processed disparity: replaces trainer.py:421-466 (the part of

@@ -413,3 +413,28 @@ def post_process_disp(outputs: Dict):
     disp_pp = disp_pp * o_l + d_f * (1 - o_l)  # :459
     mask_novel = _shift_sample(outputs["probability"][:B], dl, +1.0).sum(1, True).clamp(max=1.0)  # :461-463
     return disp_pp.detach(), mask_novel.detach(), o_l.detach(), o_fr.detach()
+
+
+# --------------------------------------------------------------------------------------------
+# decoder tail: depth_decoder.py:258-291 after the dispconv / sigmaconv convolutions
+# --------------------------------------------------------------------------------------------
+
+
+def decoder_tail(logits_raw, sigma_raw, padding_mask, disp_layered, mixture: bool):
+    """``logits_raw`` / ``sigma_raw`` = outputs of ``convs["dispconv"]`` / ``convs["sigmaconv"]`` [B,N,H,W].
+    Returns the dict entries the decoder writes: logits, probability, [sigma, pi], disp, depth (``render_probability`` off)."""
+    W = logits_raw.shape[-1]
+    out = {}
+    out["logits"] = logits_raw * padding_mask  # :259
+    out["probability"] = torch.softmax(out["logits"], 1)  # :276
+    if mixture:
+        sigma = torch.clamp(torch.sigmoid(sigma_raw), 0.01, 1.0)  # :279-280
+        out["sigma"] = sigma
+        out["pi"] = pi = out["probability"]
+        weights = pi / sigma
+        weights = weights * padding_mask
+        weights = weights / weights.sum(1, True)  # :282-284
+        out["probability"] = weights
+    out["disp"] = (out["probability"] * disp_layered).sum(1, True)  # :288
+    out["depth"] = 0.1 * 0.58 * W / out["disp"]  # :290
+    return out

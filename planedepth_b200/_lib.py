@@ -23,7 +23,7 @@ PD_WARP_DISP, PD_WARP_HOMOGRAPHY, PD_WARP_DEPTH = 0, 1, 2
 PD_LOSS_L1, PD_LOSS_MIXTURE, PD_LOSS_SSIM_L1 = 0, 1, 2
 PD_MASK_NONE, PD_MASK_F32, PD_MASK_U8 = 0, 1, 2
 PD_FLAG_EXACT_COORDS = 1
-ABI_VERSION = 6  # PD_ABI_VERSION in include/planedepth_b200.h
+ABI_VERSION = 7  # PD_ABI_VERSION in include/planedepth_b200.h
 PD_STATS_PLAIN, PD_STATS_MIXTURE = 2, 4
 
 EXPORTS = [
@@ -32,6 +32,7 @@ EXPORTS = [
     "pd_photometric_workspace_bytes", "pd_photometric_fwd", "pd_photometric_bwd", "pd_debug_roundtrip",
     "pd_occlusion_masks_workspace_bytes", "pd_occlusion_masks_fwd",
     "pd_smooth_loss_workspace_bytes", "pd_smooth_loss_fwd", "pd_smooth_loss_bwd",
+    "pd_plane_tail_fwd", "pd_plane_tail_bwd",
 ]
 
 
@@ -64,6 +65,27 @@ class WarpGradOut(C.Structure):
 class WarpGradIn(C.Structure):
     _fields_ = [("g_logits", C.c_void_p), ("g_sigma", C.c_void_p), ("g_disp", C.c_void_p),
                 ("g_disp_stride", Strides4), ("g_hmat", C.c_void_p)]
+
+
+class TailDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("mixture", C.c_int32), ("mask_dtype", C.c_int32),
+                ("disp_stride", Strides4), ("mask_stride", Strides4)]
+
+
+class TailIn(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("logits_raw", "sigma_raw", "disp_layered", "mask")]
+
+
+class TailOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("logits", "sigma", "probability", "pi", "disp", "depth", "stats")]
+
+
+class TailGradOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("g_logits", "g_sigma", "g_probability", "g_disp", "g_depth")]
+
+
+class TailGradIn(C.Structure):
+    _fields_ = [("g_logits_raw", C.c_void_p), ("g_sigma_raw", C.c_void_p), ("g_disp_layered", C.c_void_p), ("g_disp_stride", Strides4)]
 
 
 class SmoothDesc(C.Structure):
@@ -171,6 +193,10 @@ def lib() -> C.CDLL:
     L.pd_photometric_bwd.restype = C.c_int
     L.pd_photometric_bwd.argtypes = [C.POINTER(LossDesc), C.POINTER(LossIn), C.POINTER(LossOut), C.POINTER(LossGradOut), C.POINTER(LossGradIn),
                                      C.c_void_p, C.c_void_p]
+    L.pd_plane_tail_fwd.restype = C.c_int
+    L.pd_plane_tail_fwd.argtypes = [C.POINTER(TailDesc), C.POINTER(TailIn), C.POINTER(TailOut), C.c_void_p]
+    L.pd_plane_tail_bwd.restype = C.c_int
+    L.pd_plane_tail_bwd.argtypes = [C.POINTER(TailDesc), C.POINTER(TailIn), C.POINTER(TailOut), C.POINTER(TailGradOut), C.POINTER(TailGradIn), C.c_void_p]
     L.pd_smooth_loss_workspace_bytes.restype = C.c_size_t
     L.pd_smooth_loss_workspace_bytes.argtypes = [C.POINTER(SmoothDesc)]
     L.pd_smooth_loss_fwd.restype = C.c_int

@@ -27,7 +27,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib as L
-from .functional import WarpConfig, occlusion_masks, photometric_loss, smooth_loss, warp_composite
+from .functional import WarpConfig, occlusion_masks, photometric_loss, plane_tail, smooth_loss, warp_composite
 
 _WARP = {"disp_warp": L.PD_WARP_DISP, "homography_warp": L.PD_WARP_HOMOGRAPHY, "depth_warp": L.PD_WARP_DEPTH}
 
@@ -276,6 +276,13 @@ class HotPathMixin:
         else:
             raise ValueError("unknown net_type %r" % (net_type,))
         return self.post_process_disp(outputs)
+
+
+def decoder_tail(logits_raw, sigma_raw, padding_mask, disp_layered, use_mixture_loss: bool) -> Dict:
+    """Drop-in for the tail of ``DepthDecoder.forward`` (networks/depth_decoder.py:258-291, ``render_probability`` off): call it
+    with the outputs of ``convs["dispconv"]`` / ``convs["sigmaconv"]`` and ``self.outputs.update(...)`` the result
+    (INTEGRATION.md shows the patch).  One fused kernel each way instead of ~10-20 elementwise passes over [B,N,H,W]."""
+    return plane_tail(logits_raw, sigma_raw, padding_mask, disp_layered, bool(use_mixture_loss))
 
 
 _ZEROS: Dict = {}

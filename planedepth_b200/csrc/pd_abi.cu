@@ -11,6 +11,7 @@
 
 #include "pd_loss.cuh"
 #include "pd_occlusion.cuh"
+#include "pd_tail.cuh"
 #include "pd_warp_general.cuh"
 #include "pd_warp_homo.cuh"
 #include "pd_warp_rows.cuh"
@@ -304,6 +305,68 @@ int pd_warp_composite_bwd(const pd_warp_desc* d, const pd_warp_in* in, const pd_
         default: mix ? launch_bwd_general<PD_WARP_DEPTH, true>(p, st) : launch_bwd_general<PD_WARP_DEPTH, false>(p, st); break;
     }
     return check_launch("warp_composite_bwd_general");
+}
+
+// ---------------------------------------------------------------------------------------------
+// decoder tail (networks/depth_decoder.py:258-291)
+// ---------------------------------------------------------------------------------------------
+namespace {
+int tail_params(const pd_tail_desc* d, const pd_tail_in* in, pd::tl::TailParams& p) {
+    if (!d || !in) return fail(PD_ERR_ARG, "NULL descriptor");
+    if (d->B < 1 || d->N < 1 || d->H < 1 || d->W < 1 || d->N > PD_MAX_PLANES) return fail(PD_ERR_SHAPE, "bad B,N,H,W");
+    if ((int64_t)d->H * d->W >= (1ll << 31)) return fail(PD_ERR_SHAPE, "H*W too large");
+    if (!in->disp_layered) return fail(PD_ERR_ARG, "disp_layered must not be NULL");
+    if (d->mask_dtype < PD_MASK_NONE || d->mask_dtype > PD_MASK_U8) return fail(PD_ERR_ARG, "bad mask_dtype");
+    memset(&p, 0, sizeof(p));
+    p.B = d->B, p.N = d->N, p.H = d->H, p.W = d->W;
+    p.mask_dtype = in->mask ? d->mask_dtype : PD_MASK_NONE;
+    p.hw = (int64_t)d->H * d->W;
+    p.ds = d->disp_stride, p.ms = d->mask_stride;
+    p.depth_c = 0.1f * 0.58f * (float)d->W;
+    p.raw = in->logits_raw, p.sraw = in->sigma_raw, p.disp_layered = in->disp_layered, p.mask = in->mask;
+    p.warp_rows = (d->W % 32 == 0);
+    return PD_OK;
+}
+}  // namespace
+
+int pd_plane_tail_fwd(const pd_tail_desc* d, const pd_tail_in* in, pd_tail_out* out, pd_stream_t stream) {
+    pd::tl::TailParams p;
+    int rc = tail_params(d, in, p);
+    if (rc) return rc;
+    if (!in->logits_raw || (d->mixture && !in->sigma_raw)) return fail(PD_ERR_ARG, "logits_raw (and sigma_raw with mixture) must not be NULL");
+    if (!out || !out->logits || !out->probability || !out->disp || !out->stats || (d->mixture && !out->sigma))
+        return fail(PD_ERR_ARG, "logits / probability / disp / stats (and sigma with mixture) outputs must not be NULL");
+    if ((rc = check_device())) return rc;
+    p.logits = out->logits, p.sigma = out->sigma, p.prob = out->probability, p.pi = out->pi, p.disp = out->disp, p.depth = out->depth, p.stats = out->stats;
+    const unsigned grid = (unsigned)(((int64_t)d->B * p.hw + 255) / 256);
+    if (d->mixture) pd::tl::tail_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    else pd::tl::tail_fwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("tail_fwd");
+}
+
+int pd_plane_tail_bwd(const pd_tail_desc* d, const pd_tail_in* in, const pd_tail_out* saved, const pd_tail_grad_out* gout,
+                      pd_tail_grad_in* gin, pd_stream_t stream) {
+    pd::tl::TailParams p;
+    int rc = tail_params(d, in, p);
+    if (rc) return rc;
+    if (!saved || !saved->logits || !saved->stats || !saved->disp || (d->mixture && !saved->sigma))
+        return fail(PD_ERR_ARG, "saved logits / disp / stats (and sigma with mixture) must not be NULL");
+    if (!gout || !gin) return fail(PD_ERR_ARG, "NULL gradient structs");
+    if ((rc = check_device())) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    p.logits = saved->logits, p.sigma = saved->sigma, p.disp = saved->disp, p.stats = saved->stats;
+    p.g_logits = gout->g_logits, p.g_sigma = gout->g_sigma, p.g_prob = gout->g_probability, p.g_disp = gout->g_disp, p.g_depth = gout->g_depth;
+    p.g_raw = gin->g_logits_raw, p.g_sraw = d->mixture ? gin->g_sigma_raw : nullptr, p.g_dl = gin->g_disp_layered, p.gds = gin->g_disp_stride;
+    const pd_strides4& gs = p.gds;
+    p.g_dl_dense = p.g_dl && gs.b != 0 && gs.n != 0 && gs.y != 0 && gs.x != 0;
+    if (p.g_dl && !p.g_dl_dense) {
+        cudaError_t e = cudaMemsetAsync(p.g_dl, 0, (size_t)strided_extent(gs, d->B, d->N, d->H, d->W) * sizeof(float), st);
+        if (e != cudaSuccess) return fail(PD_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    }
+    const unsigned grid = (unsigned)(((int64_t)d->B * p.hw + 255) / 256);
+    if (d->mixture) pd::tl::tail_bwd_kernel<true><<<grid, 256, 0, st>>>(p);
+    else pd::tl::tail_bwd_kernel<false><<<grid, 256, 0, st>>>(p);
+    return check_launch("tail_bwd");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -342,3 +342,78 @@ def smooth_loss(disp, img, x0: int = 0, gamma: float = 1.0):
     if disp.dim() != 4 or disp.shape[1] != 1 or img.dim() != 4 or img.shape[1] != 3 or disp.shape[-2:] != img.shape[-2:]:
         raise ValueError("smooth_loss expects disp [B,1,H,W] and img [B,3,H,W]")
     return _SmoothLoss.apply(int(x0), float(gamma), disp, img)
+
+
+class _PlaneTail(torch.autograd.Function):
+    """pd_plane_tail_fwd / _bwd: networks/depth_decoder.py:258-291 after the dispconv / sigmaconv convolutions."""
+
+    @staticmethod
+    def forward(ctx, mixture: bool, logits_raw, sigma_raw, disp_layered, mask):
+        lib = L.lib()
+        B, N, H, W = logits_raw.shape
+        dev = logits_raw.device
+        desc = L.TailDesc(B=B, N=N, H=H, W=W, mixture=int(mixture), mask_dtype=L.PD_MASK_NONE, disp_stride=_strides4(disp_layered))
+        if mask is not None:
+            desc.mask_stride = _strides4(mask)
+            desc.mask_dtype = L.PD_MASK_F32 if mask.dtype == torch.float32 else L.PD_MASK_U8
+        f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        logits, prob, disp, depth, stats = f(B, N, H, W), f(B, N, H, W), f(B, 1, H, W), f(B, 1, H, W), f(B, 3, H, W)
+        sigma = f(B, N, H, W) if mixture else None
+        tin = L.TailIn(logits_raw=_ptr(logits_raw), sigma_raw=_ptr(sigma_raw), disp_layered=_ptr(disp_layered), mask=_ptr(mask))
+        out = L.TailOut(logits=_ptr(logits), sigma=_ptr(sigma), probability=_ptr(prob), pi=None, disp=_ptr(disp), depth=_ptr(depth), stats=_ptr(stats))
+        _call("pd_plane_tail_fwd", lib.pd_plane_tail_fwd, C.byref(desc), C.byref(tin), C.byref(out), _stream())
+        ctx.desc, ctx.mixture = desc, mixture
+        ctx.save_for_backward(disp_layered, mask, logits, sigma, disp, stats)
+        return logits, (sigma if mixture else torch.empty(0, device=dev)), prob, disp, depth
+
+    @staticmethod
+    def backward(ctx, g_logits, g_sigma, g_prob, g_disp, g_depth):
+        lib = L.lib()
+        disp_layered, mask, logits, sigma, disp, stats = ctx.saved_tensors
+        dev = logits.device
+        need = ctx.needs_input_grad  # (mixture, logits_raw, sigma_raw, disp_layered, mask)
+        c = lambda g, what: None if g is None else _f32c(g, what)
+        g_logits, g_prob, g_disp, g_depth = c(g_logits, "grad logits"), c(g_prob, "grad probability"), c(g_disp, "grad disp"), c(g_depth, "grad depth")
+        g_sigma = c(g_sigma, "grad sigma") if (ctx.mixture and g_sigma is not None and g_sigma.numel()) else None
+        tin = L.TailIn(disp_layered=_ptr(disp_layered), mask=_ptr(mask))
+        saved = L.TailOut(logits=_ptr(logits), sigma=_ptr(sigma), disp=_ptr(disp), stats=_ptr(stats))
+        gout = L.TailGradOut(g_logits=_ptr(g_logits), g_sigma=_ptr(g_sigma), g_probability=_ptr(g_prob), g_disp=_ptr(g_disp), g_depth=_ptr(g_depth))
+        g_raw = torch.empty_like(logits) if need[1] else None
+        g_sraw = torch.empty_like(logits) if (ctx.mixture and need[2]) else None
+        gin = L.TailGradIn(g_logits_raw=_ptr(g_raw), g_sigma_raw=_ptr(g_sraw))
+        g_dl, spread = None, 1
+        if need[3]:
+            # broadcast dimensions are reduced inside the kernel and handed back spread evenly (see _WarpComposite.backward)
+            shape = [1 if (disp_layered.size(i) == 1 or disp_layered.stride(i) == 0) else disp_layered.size(i) for i in range(4)]
+            for i in range(4):
+                if shape[i] == 1:
+                    spread *= disp_layered.size(i)
+            g_dl = torch.empty(shape, device=dev, dtype=torch.float32)
+            gin.g_disp_layered = g_dl.data_ptr()
+            gin.g_disp_stride = _strides4(g_dl)
+        _call("pd_plane_tail_bwd", lib.pd_plane_tail_bwd, C.byref(ctx.desc), C.byref(tin), C.byref(saved), C.byref(gout), C.byref(gin), _stream())
+        if g_dl is not None and tuple(g_dl.shape) != tuple(disp_layered.shape):
+            g_dl = (g_dl / spread if spread > 1 else g_dl).expand(disp_layered.shape)
+        return None, g_raw, g_sraw, g_dl, None
+
+
+def plane_tail(logits_raw, sigma_raw, padding_mask, disp_layered, mixture: bool):
+    """The decoder's outputs after its last convolutions (depth_decoder.py:258-291): returns a dict with ``logits``,
+    ``probability``, ``disp``, ``depth`` and, with ``mixture``, ``sigma`` and ``pi`` (= softmax before the reweighting is
+    not materialised: nothing reads it; the key maps to ``None``)."""
+    logits_raw = _f32c(logits_raw, "logits_raw")
+    sigma_raw = _f32c(sigma_raw, "sigma_raw") if mixture else None
+    dl = disp_layered if disp_layered.dtype == torch.float32 else disp_layered.float()
+    dl = compact_expand_base(dl)
+    mask = padding_mask
+    if mask is not None:
+        if mask.dtype == torch.bool:
+            mask = mask.view(torch.uint8)
+        elif mask.dtype not in (torch.float32, torch.uint8):
+            mask = mask.float()
+        mask = mask.detach()
+    logits, sigma, prob, disp, depth = _PlaneTail.apply(bool(mixture), logits_raw, sigma_raw, dl, mask)
+    out = {"logits": logits, "probability": prob, "disp": disp, "depth": depth}
+    if mixture:
+        out["sigma"], out["pi"] = sigma, None
+    return out

@@ -34,7 +34,9 @@ def test_ctypes_structs_match_c_layout(tmp_path):
         "pd_strides4": L.Strides4, "pd_warp_desc": L.WarpDesc, "pd_warp_in": L.WarpIn, "pd_warp_out": L.WarpOut,
         "pd_warp_grad_out": L.WarpGradOut, "pd_warp_grad_in": L.WarpGradIn, "pd_loss_desc": L.LossDesc, "pd_loss_in": L.LossIn,
         "pd_loss_out": L.LossOut, "pd_loss_grad_out": L.LossGradOut, "pd_loss_grad_in": L.LossGradIn,
-        "pd_occl_desc": L.OcclDesc, "pd_occl_in": L.OcclIn, "pd_occl_out": L.OcclOut,
+        "pd_occl_desc": L.OcclDesc, "pd_occl_in": L.OcclIn, "pd_occl_out": L.OcclOut, "pd_smooth_desc": L.SmoothDesc,
+        "pd_tail_desc": L.TailDesc, "pd_tail_in": L.TailIn, "pd_tail_out": L.TailOut, "pd_tail_grad_out": L.TailGradOut,
+        "pd_tail_grad_in": L.TailGradIn,
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "planedepth_b200.h"', "int main(void){"]
     for cname, st in structs.items():

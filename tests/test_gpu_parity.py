@@ -441,3 +441,79 @@ def test_bf16_storage_within_2e_2(idx):
         assert leaf.grad is not None and leaf.grad.dtype == torch.bfloat16
         want = cc.leaves[k].grad
         check(leaf.grad.float(), want, 2e-2 * float(want.abs().max()), "grad_%s (bf16 storage)" % k, allow_frac=2e-3)
+
+
+# ------------------------------------------------------------------------------------------------
+# decoder tail (networks/depth_decoder.py:258-291) through pd_plane_tail_fwd / _bwd
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["tail_plain", "tail_mix"])
+def test_decoder_tail_matches_reference_golden(name):
+    import os
+
+    from helpers import GOLDEN
+    from planedepth_b200.boundary import decoder_tail
+
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    mix = bool(z["mixture"])
+    T = lambda k: torch.from_numpy(z[k]).cuda()
+    lr = T("logits_raw").requires_grad_(True)
+    sr = T("sigma_raw").requires_grad_(True) if mix else None
+    dl = T("disp_layered").requires_grad_(True)
+    out = decoder_tail(lr, sr, T("padding_mask"), dl, mix)
+    L = (out["logits"] * T("A")).sum() + (out["disp"] * T("Cd")).sum()
+    if mix:
+        L = L + (out["sigma"] * T("Bm")).sum()
+    L.backward()
+    for k in ["logits", "probability"] + (["sigma"] if mix else []):
+        check(out[k], z["out_" + k], TOL, k)
+    for k in ("disp", "depth"):  # O(10..100): relative
+        check(out[k], z["out_" + k], TOL * float(np.abs(z["out_" + k]).max()), k)
+    for leaf, k in ((lr, "grad_logits_raw"), (dl, "grad_disp_layered")) + (((sr, "grad_sigma_raw"),) if mix else ()):
+        check(leaf.grad, z[k], TOL * (float(np.abs(z[k]).max()) + 1e-12), k, allow_frac=2e-4)
+
+
+@pytest.mark.parametrize("mix", [False, True])
+@pytest.mark.parametrize("layout", ["expand", "dense_u8"])
+def test_decoder_tail_matches_oracle(mix, layout):
+    """Saturating sigmas (clamp gate), masked planes, the decoder's stride-0 disparity (compact gradient), upstream
+    gradients on every output incl. probability and depth."""
+    from planedepth_b200.boundary import decoder_tail
+
+    B, N, H, W = 2, 9, 12, 64
+    g = torch.Generator().manual_seed(31)
+    lr = 2.0 * torch.randn(B, N, H, W, generator=g)
+    sr = 4.0 * torch.randn(B, N, H, W, generator=g)  # sigmoid reaches below 0.01
+    base = (0.3 * W * (1.3 / (0.3 * W)) ** (torch.arange(N) / (N - 1.0))).reshape(1, N, 1, 1).repeat(B, 1, 1, 1)
+    mask = torch.ones(B, N, H, W)
+    mask[:, N - 3:, : H // 2] = 0.0
+    if layout == "dense_u8":
+        bump = 0.3 * torch.randn(B, N, H, W, generator=g)
+        mask = mask.bool()
+    ws = [torch.randn(B, N, H, W, generator=g) for _ in range(3)] + [torch.randn(B, 1, H, W, generator=g) for _ in range(2)]
+
+    def run(dev, fn):
+        l_ = lr.to(dev).requires_grad_(True)
+        s_ = sr.to(dev).requires_grad_(True) if mix else None
+        b_ = base.to(dev).requires_grad_(True)
+        dl = b_.expand(B, N, H, W)
+        if layout == "dense_u8":
+            dl = dl + bump.to(dev)
+        out = fn(l_, s_, mask.to(dev), dl, mix)
+        w = [t.to(dev) for t in ws]
+        L = (out["logits"] * w[0]).sum() + (out["probability"] * w[2]).sum() + (out["disp"] * w[3]).sum() + 50.0 * (out["depth"] * w[4]).sum()
+        if mix:
+            L = L + (out["sigma"] * w[1]).sum()
+        L.backward()
+        return out, (l_, s_, b_)
+
+    want, lw = run("cpu", O.decoder_tail)
+    got, lg = run("cuda", decoder_tail)
+    for k in ["logits", "probability"] + (["sigma"] if mix else []):
+        check(got[k], want[k], TOL, k)
+    for k in ("disp", "depth"):
+        check(got[k], want[k], TOL * float(want[k].abs().max()), k)
+    for a, b_, nm in zip(lg, lw, ("logits_raw", "sigma_raw", "base")):
+        if b_ is None:
+            continue
+        scale = float(b_.grad.abs().max()) + 1e-12
+        check(a.grad, b_.grad, (5e-4 if nm == "base" else TOL) * scale, "grad_" + nm, allow_frac=2e-3)

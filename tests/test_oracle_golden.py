@@ -92,3 +92,29 @@ def test_oracle_post_process_disp_matches_reference(name):
     assert_close(disp_pp, z["disp_pp"], 1e-5, what="disp_pp")
     assert_close(mask_novel, z["mask_novel"], 1e-6, what="mask_novel")
     assert float(o_l.max()) <= 1.0 and float(o_fr.max()) <= 1.0 and float(mask_novel.max()) <= 1.0
+
+
+@pytest.mark.parametrize("name", ["tail_plain", "tail_mix"])
+def test_oracle_decoder_tail_matches_reference(name):
+    """A real reference DepthDecoder's forward/backward (tests/golden/make_golden_tail.py) vs the restated tail."""
+    import os
+
+    from helpers import GOLDEN
+
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    mix = bool(z["mixture"])
+    T = lambda k: torch.from_numpy(z[k])
+    lr = T("logits_raw").requires_grad_(True)
+    sr = T("sigma_raw").requires_grad_(True) if mix else None
+    dl = T("disp_layered").requires_grad_(True)
+    out = O.decoder_tail(lr, sr, T("padding_mask"), dl, mix)
+    L = (out["logits"] * T("A")).sum() + (out["disp"] * T("Cd")).sum()
+    if mix:
+        L = L + (out["sigma"] * T("Bm")).sum()
+    L.backward()
+    for k in ["logits", "probability", "disp", "depth"] + (["sigma", "pi"] if mix else []):
+        assert_close(out[k], z["out_" + k], 1e-6, 1e-6, what=k)
+    assert_close(lr.grad, z["grad_logits_raw"], 1e-6, 1e-5, what="grad logits_raw")
+    assert_close(dl.grad, z["grad_disp_layered"], 1e-6, 1e-5, what="grad disp_layered")
+    if mix:
+        assert_close(sr.grad, z["grad_sigma_raw"], 1e-6, 1e-5, what="grad sigma_raw")
