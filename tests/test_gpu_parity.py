@@ -492,9 +492,9 @@ def test_decoder_tail_matches_oracle(mix, layout):
     ws = [torch.randn(B, N, H, W, generator=g) for _ in range(3)] + [torch.randn(B, 1, H, W, generator=g) for _ in range(2)]
 
     def run(dev, fn):
-        l_ = lr.to(dev).requires_grad_(True)
-        s_ = sr.to(dev).requires_grad_(True) if mix else None
-        b_ = base.to(dev).requires_grad_(True)
+        l_ = lr.detach().clone().to(dev).requires_grad_(True)
+        s_ = sr.detach().clone().to(dev).requires_grad_(True) if mix else None
+        b_ = base.detach().clone().to(dev).requires_grad_(True)
         dl = b_.expand(B, N, H, W)
         if layout == "dense_u8":
             dl = dl + bump.to(dev)
@@ -511,7 +511,7 @@ def test_decoder_tail_matches_oracle(mix, layout):
     for k in ["logits", "probability"] + (["sigma"] if mix else []):
         check(got[k], want[k], TOL, k)
     for k in ("disp", "depth"):
-        check(got[k], want[k], TOL * float(want[k].abs().max()), k)
+        check(got[k], want[k], TOL * float(want[k].detach().abs().max()), k)
     for a, b_, nm in zip(lg, lw, ("logits_raw", "sigma_raw", "base")):
         if b_ is None:
             continue
