@@ -311,6 +311,9 @@ int pd_warp_composite_bwd(const pd_warp_desc* d, const pd_warp_in* in, const pd_
 // decoder tail (networks/depth_decoder.py:258-291)
 // ---------------------------------------------------------------------------------------------
 namespace {
+// pixels per CTA: the [N][T] column cache stays within 64 KB
+int tail_threads(int N) { return N <= 64 ? 256 : (N <= 128 ? 128 : (N <= 256 ? 64 : 32)); }
+
 int tail_params(const pd_tail_desc* d, const pd_tail_in* in, pd::tl::TailParams& p) {
     if (!d || !in) return fail(PD_ERR_ARG, "NULL descriptor");
     if (d->B < 1 || d->N < 1 || d->H < 1 || d->W < 1 || d->N > PD_MAX_PLANES) return fail(PD_ERR_SHAPE, "bad B,N,H,W");
@@ -338,9 +341,16 @@ int pd_plane_tail_fwd(const pd_tail_desc* d, const pd_tail_in* in, pd_tail_out* 
         return fail(PD_ERR_ARG, "logits / probability / disp / stats (and sigma with mixture) outputs must not be NULL");
     if ((rc = check_device())) return rc;
     p.logits = out->logits, p.sigma = out->sigma, p.prob = out->probability, p.pi = out->pi, p.disp = out->disp, p.depth = out->depth, p.stats = out->stats;
-    const unsigned grid = (unsigned)(((int64_t)d->B * p.hw + 255) / 256);
-    if (d->mixture) pd::tl::tail_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
-    else pd::tl::tail_fwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    const int T = tail_threads(d->N);
+    const size_t smem = (size_t)d->N * T * sizeof(float);
+    const unsigned grid = (unsigned)(((int64_t)d->B * p.hw + T - 1) / T);
+    if (d->mixture) {
+        loss_smem_optin(pd::tl::tail_fwd_kernel<true>, smem);
+        pd::tl::tail_fwd_kernel<true><<<grid, T, smem, (cudaStream_t)stream>>>(p);
+    } else {
+        loss_smem_optin(pd::tl::tail_fwd_kernel<false>, smem);
+        pd::tl::tail_fwd_kernel<false><<<grid, T, smem, (cudaStream_t)stream>>>(p);
+    }
     return check_launch("tail_fwd");
 }
 
@@ -363,9 +373,19 @@ int pd_plane_tail_bwd(const pd_tail_desc* d, const pd_tail_in* in, const pd_tail
         cudaError_t e = cudaMemsetAsync(p.g_dl, 0, (size_t)strided_extent(gs, d->B, d->N, d->H, d->W) * sizeof(float), st);
         if (e != cudaSuccess) return fail(PD_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
     }
-    const unsigned grid = (unsigned)(((int64_t)d->B * p.hw + 255) / 256);
-    if (d->mixture) pd::tl::tail_bwd_kernel<true><<<grid, 256, 0, st>>>(p);
-    else pd::tl::tail_bwd_kernel<false><<<grid, 256, 0, st>>>(p);
+    const int T = tail_threads(d->N);
+    const size_t smem = ((size_t)d->N * T + d->N) * sizeof(float);
+    // fully compact disparity gradient ([B,N,1,1]): summed per CTA in shared memory, one flush of N atomics per CTA
+    // (needs CTAs that do not straddle images)
+    if (p.g_dl && !p.g_dl_dense && gs.y == 0 && gs.x == 0 && p.hw % T == 0) p.smem_acc = 1;
+    const unsigned grid = (unsigned)(((int64_t)d->B * p.hw + T - 1) / T);
+    if (d->mixture) {
+        loss_smem_optin(pd::tl::tail_bwd_kernel<true>, smem);
+        pd::tl::tail_bwd_kernel<true><<<grid, T, smem, st>>>(p);
+    } else {
+        loss_smem_optin(pd::tl::tail_bwd_kernel<false>, smem);
+        pd::tl::tail_bwd_kernel<false><<<grid, T, smem, st>>>(p);
+    }
     return check_launch("tail_bwd");
 }
 
