@@ -17,6 +17,8 @@ python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_referenc
 python scratch/ref_gpu_probe.py cfg2 cfg3 cfg4 cfg5 > $O/${TAG}_reference_gpu_probe.json 2> $O/${TAG}_reference_gpu_probe.err; echo "ref gpu probe rc=$?"
 python scratch/pp_bench.py 12 49 192 640 > $O/${TAG}_pp_cfg2.json 2> $O/${TAG}_pp.err
 python scratch/pp_bench.py 8 63 384 1280 > $O/${TAG}_pp_cfg5.json 2>> $O/${TAG}_pp.err
+python scratch/tail_bench.py 12 49 192 640 0 > $O/${TAG}_tail_cfg2.json 2> $O/${TAG}_tail.err
+python scratch/tail_bench.py 4 49 384 1280 1 > $O/${TAG}_tail_cfg3.json 2>> $O/${TAG}_tail.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'rows_|ssim_l1_stream|photometric_bwd' -s 12 -c 4 -o $O/${TAG}_prof -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > $O/${TAG}_ncu_full.log 2>&1
 ncu --set full --clock-control none -k regex:'rows_|homo_' -s 4 -c 2 -o $O/${TAG}_prof_cfg3 -f python bench.py --config cfg3 --steps 2 --warmup 3 --no-cpu-baseline --no-graph > $O/${TAG}_ncu_cfg3.log 2>&1
