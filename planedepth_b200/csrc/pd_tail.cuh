@@ -148,18 +148,9 @@ __global__ void __launch_bounds__(256) tail_bwd_kernel(const TailParams p) {
         const float gp = (has_gp ? __ldg(p.g_prob + o) : 0.0f) + gd * __ldg(p.disp_layered + d0 + (int64_t)n * p.ds.n);
         dotp = fmaf(pr, gp, dotp);
     }
-    // pass 2 (mixture): dotpi = sum_k pi_k * g_pi_k,  g_pi_k = (gp_k - dotp) / Z * m_k / sigma_k
-    float dotpi = 0.0f;
-    if (MIX) {
-    #pragma unroll 8
-    for (int n = 0; n < p.N; ++n) {
-            const int64_t o = base + (int64_t)n * p.hw;
-            const float m = load_mask(p.mask, p.mask_dtype, m0 + (int64_t)n * p.ms.n);
-            const float gp = (has_gp ? __ldg(p.g_prob + o) : 0.0f) + gd * __ldg(p.disp_layered + d0 + (int64_t)n * p.ds.n);
-            dotpi = fmaf(c[n * T], (gp - dotp) * invZ * m / __ldg(p.sigma + o), dotpi);
-        }
-    }
-    // pass 3: gradients
+    // (mixture) the softmax-normaliser term sum_k pi_k g_pi_k, g_pi_k = (gp_k - dotp) m_k / (sigma_k Z), vanishes identically:
+    // it equals sum_k probability_k (gp_k - dotp) = dotp - dotp — probability = w / sum w does not change when pi is rescaled
+    // pass 2: gradients
 #pragma unroll 8
     for (int n = 0; n < p.N; ++n) {
         const int64_t o = base + (int64_t)n * p.hw;
@@ -173,7 +164,7 @@ __global__ void __launch_bounds__(256) tail_bwd_kernel(const TailParams p) {
             pr = pi * a * m * invZ;
             const float gw = (gp - dotp) * invZ;  // d / d w_n with probability = w / sum w
             const float gpi = gw * m * a;
-            gl = pi * (gpi - dotpi) + glo;
+            gl = pi * gpi + glo;
             const float gsg = -gw * pi * m * a * a + ((p.g_sigma && live) ? __ldg(p.g_sigma + o) : 0.0f);
             // clamp passes the gradient inside [0.01, 1]; sigmoid' = s (1 - s) with s = sigma there
             if (live && p.g_sraw) p.g_sraw[o] = (sg > 0.01f) ? gsg * sg * (1.0f - sg) : 0.0f;
