@@ -317,55 +317,55 @@ __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const 
         HTaps t;
         const bool act = c.m != 0.0f;  // every gradient of a masked plane carries the factor m = 0 (:580)
         if (act) {
-        t = make_htaps(rt(c.u, p.wm1, rcp_w), rt(c.v, p.hm1, rcp_h), W, H);
-        const float4 a = __ldg(src + t.o00), bq = __ldg(src + t.o01), cq = __ldg(src + t.o10), d = __ldg(src + t.o11);
-        const float l00 = __ldg(lg + t.o00), l01 = __ldg(lg + t.o01), l10 = __ldg(lg + t.o10), l11 = __ldg(lg + t.o11);
-        const float cr = hblend(a.x, bq.x, cq.x, d.x, t);
-        const float cg = hblend(a.y, bq.y, cq.y, d.y, t);
-        const float cb = hblend(a.z, bq.z, cq.z, d.z, t);
-        const float l = hblend(l00, l01, l10, l11, t);
-        const float pi = fast_exp2(fmaf(l, kLog2e, -Ml2)) * invS;
-        const float Gn = g0 * cr + g1 * cg + g2 * cb;
-        float dcr, dcg, dcb;
-        float s00 = 0, s01 = 0, s10 = 0, s11 = 0;
-        if (MIX) {
-            const float* sp = sgp + (int64_t)n * p.hw;
-            s00 = __ldg(sp + t.o00), s01 = __ldg(sp + t.o01), s10 = __ldg(sp + t.o10), s11 = __ldg(sp + t.o11);
-            const float sraw = hblend(s00, s01, s10, s11, t);
-            const float sg = fminf(fmaxf(sraw, 0.01f), 1.0f);
-            const float inv = 1.0f / sg;
-            const float w = pi * inv * Zinv;  // compositing weight
-            const float err = (fabsf(cr - tr) + fabsf(cg - tg) + fabsf(cb - tb)) * (1.0f / 3.0f);
-            const float lap = 0.5f * fast_exp(-err * inv) * inv;
-            const float P = (Gn - Gbar) * inv * Zinv + gD * lap;
-            dl = pi * (P - gDD);
-            const float dsgt = -(Gn - Gbar) * w * inv + gD * pi * lap * (err - sg) * inv * inv;
-            dsg = (sraw >= 0.01f && sraw <= 1.0f) ? dsgt : 0.0f;  // clamp backward
-            const float ce = -gD * pi * lap * inv * (1.0f / 3.0f);
-            dcr = w * g0 + ce * ((cr > tr) ? 1.0f : ((cr < tr) ? -1.0f : 0.0f));
-            dcg = w * g1 + ce * ((cg > tg) ? 1.0f : ((cg < tg) ? -1.0f : 0.0f));
-            dcb = w * g2 + ce * ((cb > tb) ? 1.0f : ((cb < tb) ? -1.0f : 0.0f));
-        } else {
-            dl = pi * (Gn - Gbar);
-            dcr = pi * g0, dcg = pi * g1, dcb = pi * g2;
-        }
-        if (want_h) {
-            // The sample is linear in the tap values, so the coordinate gradient (blend_grad() of pd_device.cuh, i.e. ATen's
-            // gix / giy) is taken once on the combined tap T = dcr*r + dcg*g + dcb*b + dl*logit (+ dsg*sigma); taps outside
-            // the image read as zero (their loads were clamped onto a neighbour)
-            float tnw = fmaf(dcr, a.x, fmaf(dcg, a.y, fmaf(dcb, a.z, dl * l00)));
-            float tne = fmaf(dcr, bq.x, fmaf(dcg, bq.y, fmaf(dcb, bq.z, dl * l01)));
-            float tsw = fmaf(dcr, cq.x, fmaf(dcg, cq.y, fmaf(dcb, cq.z, dl * l10)));
-            float tse = fmaf(dcr, d.x, fmaf(dcg, d.y, fmaf(dcb, d.z, dl * l11)));
-            if (MIX) tnw = fmaf(dsg, s00, tnw), tne = fmaf(dsg, s01, tne), tsw = fmaf(dsg, s10, tsw), tse = fmaf(dsg, s11, tse);
-            tnw = (t.ix0 && t.iy0) ? tnw : 0.0f, tne = (t.ix1 && t.iy0) ? tne : 0.0f;
-            tsw = (t.ix0 && t.iy1) ? tsw : 0.0f, tse = (t.ix1 && t.iy1) ? tse : 0.0f;
-            const float gx = (tne - tnw) * t.ry0 + (tse - tsw) * t.ry1;
-            const float gy = (tsw - tnw) * t.rx0 + (tse - tne) * t.rx1;
-            // u = qx / zc, v = qy / zc, zc = max(qz, 1e-7)   (layers.py:227-228)
-            gqx = gx * c.zinv, gqy = gy * c.zinv;
-            gqz = -(gx * c.u + gy * c.v) * c.zinv * c.dz;
-        }
+            t = make_htaps(rt(c.u, p.wm1, rcp_w), rt(c.v, p.hm1, rcp_h), W, H);
+            const float4 a = __ldg(src + t.o00), bq = __ldg(src + t.o01), cq = __ldg(src + t.o10), d = __ldg(src + t.o11);
+            const float l00 = __ldg(lg + t.o00), l01 = __ldg(lg + t.o01), l10 = __ldg(lg + t.o10), l11 = __ldg(lg + t.o11);
+            const float cr = hblend(a.x, bq.x, cq.x, d.x, t);
+            const float cg = hblend(a.y, bq.y, cq.y, d.y, t);
+            const float cb = hblend(a.z, bq.z, cq.z, d.z, t);
+            const float l = hblend(l00, l01, l10, l11, t);
+            const float pi = fast_exp2(fmaf(l, kLog2e, -Ml2)) * invS;
+            const float Gn = g0 * cr + g1 * cg + g2 * cb;
+            float dcr, dcg, dcb;
+            float s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+            if (MIX) {
+                const float* sp = sgp + (int64_t)n * p.hw;
+                s00 = __ldg(sp + t.o00), s01 = __ldg(sp + t.o01), s10 = __ldg(sp + t.o10), s11 = __ldg(sp + t.o11);
+                const float sraw = hblend(s00, s01, s10, s11, t);
+                const float sg = fminf(fmaxf(sraw, 0.01f), 1.0f);
+                const float inv = 1.0f / sg;
+                const float w = pi * inv * Zinv;  // compositing weight
+                const float err = (fabsf(cr - tr) + fabsf(cg - tg) + fabsf(cb - tb)) * (1.0f / 3.0f);
+                const float lap = 0.5f * fast_exp(-err * inv) * inv;
+                const float P = (Gn - Gbar) * inv * Zinv + gD * lap;
+                dl = pi * (P - gDD);
+                const float dsgt = -(Gn - Gbar) * w * inv + gD * pi * lap * (err - sg) * inv * inv;
+                dsg = (sraw >= 0.01f && sraw <= 1.0f) ? dsgt : 0.0f;  // clamp backward
+                const float ce = -gD * pi * lap * inv * (1.0f / 3.0f);
+                dcr = w * g0 + ce * ((cr > tr) ? 1.0f : ((cr < tr) ? -1.0f : 0.0f));
+                dcg = w * g1 + ce * ((cg > tg) ? 1.0f : ((cg < tg) ? -1.0f : 0.0f));
+                dcb = w * g2 + ce * ((cb > tb) ? 1.0f : ((cb < tb) ? -1.0f : 0.0f));
+            } else {
+                dl = pi * (Gn - Gbar);
+                dcr = pi * g0, dcg = pi * g1, dcb = pi * g2;
+            }
+            if (want_h) {
+                // The sample is linear in the tap values, so the coordinate gradient (blend_grad() of pd_device.cuh, i.e. ATen's
+                // gix / giy) is taken once on the combined tap T = dcr*r + dcg*g + dcb*b + dl*logit (+ dsg*sigma); taps outside
+                // the image read as zero (their loads were clamped onto a neighbour)
+                float tnw = fmaf(dcr, a.x, fmaf(dcg, a.y, fmaf(dcb, a.z, dl * l00)));
+                float tne = fmaf(dcr, bq.x, fmaf(dcg, bq.y, fmaf(dcb, bq.z, dl * l01)));
+                float tsw = fmaf(dcr, cq.x, fmaf(dcg, cq.y, fmaf(dcb, cq.z, dl * l10)));
+                float tse = fmaf(dcr, d.x, fmaf(dcg, d.y, fmaf(dcb, d.z, dl * l11)));
+                if (MIX) tnw = fmaf(dsg, s00, tnw), tne = fmaf(dsg, s01, tne), tsw = fmaf(dsg, s10, tsw), tse = fmaf(dsg, s11, tse);
+                tnw = (t.ix0 && t.iy0) ? tnw : 0.0f, tne = (t.ix1 && t.iy0) ? tne : 0.0f;
+                tsw = (t.ix0 && t.iy1) ? tsw : 0.0f, tse = (t.ix1 && t.iy1) ? tse : 0.0f;
+                const float gx = (tne - tnw) * t.ry0 + (tse - tsw) * t.ry1;
+                const float gy = (tsw - tnw) * t.rx0 + (tse - tne) * t.rx1;
+                // u = qx / zc, v = qy / zc, zc = max(qz, 1e-7)   (layers.py:227-228)
+                gqx = gx * c.zinv, gqy = gy * c.zinv;
+                gqz = -(gx * c.u + gy * c.v) * c.zinv * c.dz;
+            }
         }
         if (act && glg && dl != 0.0f) hscatter(glg + (int64_t)n * p.hw, t, dl);
         if (MIX && act && gsg && dsg != 0.0f) hscatter(gsg + (int64_t)n * p.hw, t, dsg);
