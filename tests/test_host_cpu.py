@@ -28,3 +28,62 @@ def test_no_cpu_fallback():
 
     with pytest.raises(_lib.PlaneDepthLibraryError):
         smooth_loss(torch.rand(1, 1, 4, 8), torch.rand(1, 3, 4, 8))
+
+
+def test_compact_expand_base_recovers_the_decoders_stride0_expand():
+    """depth_decoder.py:156 hands out ``disp_layered`` as a stride-0 expand of [B,N,1,1]: the boundary finds that base so that
+    the kernels reduce the gradient into the compact shape; anything else is left alone."""
+    from planedepth_b200.functional import _strides4, compact_expand_base
+
+    base = torch.rand(2, 5, 1, 1)
+    ex = base.expand(2, 5, 6, 8)
+    got = compact_expand_base(ex)
+    assert got.shape == (2, 5, 1, 1) and got.data_ptr() == base.data_ptr()
+    s = _strides4(got)
+    assert (s.y, s.x) == (0, 0) and s.n == 1 and s.b == 5
+    dense = torch.rand(2, 5, 6, 8)
+    assert compact_expand_base(dense) is dense
+    rows = torch.rand(2, 5, 6, 1).expand(2, 5, 6, 8)  # per-row values (xz planes)
+    r = compact_expand_base(rows)
+    assert r.shape == (2, 5, 6, 1) and _strides4(r).x == 0
+    assert compact_expand_base(dense[:, :, ::2]).shape == (2, 5, 3, 8)  # a strided slice is not an expand
+
+
+def test_rowwise_view_gradient_sums_to_the_x_reduced_gradient():
+    """``disp_rowwise``: the dense, x-constant ``cat`` is read at column 0 and the gradient comes back spread over x, so that
+    any x-constant producer receives exactly the x-reduced gradient."""
+    from planedepth_b200.boundary import rowwise_view
+
+    h = torch.rand(2, 3, 4, 1, requires_grad=True)
+    dense = (h * 2.0).expand(2, 3, 4, 8).contiguous()  # what a cat of x-constant planes looks like
+    v = rowwise_view(dense)
+    assert v.stride(3) == 0 and torch.equal(v, dense)
+    w = torch.rand(2, 3, 4, 8)
+    (v * w).sum().backward()
+    assert torch.allclose(h.grad, 2.0 * w.sum(3, keepdim=True), atol=1e-6)
+
+
+def test_homography_params_match_the_reference_formula():
+    """boundary.homography_params = layers.py:206-226 up to the projective divide: H_t2s = inv(K (R + t n^T / d) K^-1), R n."""
+    from planedepth_b200.boundary import homography_params
+    from oracle import pd_oracle as O
+
+    g = torch.Generator().manual_seed(3)
+    B, N, H, W = 2, 4, 24, 32
+    K = torch.tensor([[0.58 * W, 0, 0.5 * W, 0], [0, 1.92 * H, 0.5 * H, 0], [0, 0, 1, 0], [0, 0, 0, 1.0]])[None].repeat(B, 1, 1)
+    iK = torch.linalg.pinv(K)
+    T = torch.eye(4)[None].repeat(B, 1, 1)
+    T[:, :3, 3] = 0.05 * torch.randn(B, 3, generator=g)
+    T[:, 0, 1], T[:, 1, 0] = 0.02, -0.02
+    dist = 0.5 + 5 * torch.rand(B, N, generator=g)
+    nrm = torch.nn.functional.normalize(torch.tensor([0.0, 0.0, 1.0]) + 0.2 * torch.randn(B, N, 3, generator=g), dim=-1)
+    hmat, cam = homography_params(dist, nrm, T, K, iK)
+    assert hmat.shape == (B * N, 12) and cam.shape == (B, 9)
+    u, v, mask = O.homography_coords(dist, nrm, T, K, iK, H, W)
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    p = torch.stack([xs, ys, torch.ones_like(xs)], 0).reshape(3, -1)
+    q = hmat[:, :9].reshape(B * N, 3, 3) @ p
+    uu = (q[:, 0] / q[:, 2].clamp_min(1e-7)).reshape(B, N, H, W)
+    vv = (q[:, 1] / q[:, 2].clamp_min(1e-7)).reshape(B, N, H, W)
+    sane = u.abs() < 1e4
+    assert torch.allclose(uu[sane], u[sane], rtol=1e-4, atol=2e-3) and torch.allclose(vv[sane], v[sane], rtol=1e-4, atol=2e-3)
