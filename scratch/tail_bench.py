@@ -6,8 +6,23 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import pd_oracle as O  # the reference's formulas, run here on the GPU as the eager baseline
 from planedepth_b200.boundary import decoder_tail
+
+
+def eager_tail(logits_raw, sigma_raw, padding_mask, disp_layered, mixture):
+    """The operations of networks/depth_decoder.py:258-291 as the reference's decoder issues them (eager PyTorch baseline)."""
+    W = logits_raw.shape[-1]
+    out = {"logits": logits_raw * padding_mask}
+    out["probability"] = torch.softmax(out["logits"], 1)
+    if mixture:
+        sigma = torch.clamp(torch.sigmoid(sigma_raw), 0.01, 1.0)
+        out["sigma"] = sigma
+        weights = out["probability"] / sigma
+        weights = weights * padding_mask
+        out["probability"] = weights / weights.sum(1, True)
+    out["disp"] = (out["probability"] * disp_layered).sum(1, True)
+    out["depth"] = 0.1 * 0.58 * W / out["disp"]
+    return out
 
 
 def timeit(fn, n=10, w=3):
@@ -40,7 +55,7 @@ def main():
 
     res = {"shape": [B, N, H, W], "mixture": mix}
     res["ours_fwd_bwd_ms"] = timeit(lambda: step(decoder_tail))
-    res["eager_torch_fwd_bwd_ms"] = timeit(lambda: step(O.decoder_tail), n=5, w=2)
+    res["eager_torch_fwd_bwd_ms"] = timeit(lambda: step(eager_tail), n=5, w=2)
     res["speedup"] = res["eager_torch_fwd_bwd_ms"] / res["ours_fwd_bwd_ms"]
     x = B * N * H * W * 4
     m = 1 if mix else 0
