@@ -309,7 +309,8 @@ __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const 
     float* glg = p.gin.g_logits ? p.gin.g_logits + (int64_t)b * N * p.hw : nullptr;
     float* gsg = (MIX && p.gin.g_sigma) ? p.gin.g_sigma + (int64_t)b * N * p.hw : nullptr;
 
-    for (int n = 0; n < N; ++n, lg += p.hw) {
+    // per-plane base pointers advance by one plane per iteration (no 64-bit multiply per access)
+    for (int n = 0; n < N; ++n, lg += p.hw, sgp += MIX ? p.hw : 0, glg += glg ? p.hw : 0, gsg += gsg ? p.hw : 0) {
         float4 h0, h1, h2;
         load_plane_params(sh, n, h0, h1, h2);
         const HCoord c = homo_coords(h0, h1, h2, fx, fy, rx, ry, rz);
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const 
             float dcr, dcg, dcb;
             float s00 = 0, s01 = 0, s10 = 0, s11 = 0;
             if (MIX) {
-                const float* sp = sgp + (int64_t)n * p.hw;
+                const float* sp = sgp;
                 s00 = __ldg(sp + t.o00), s01 = __ldg(sp + t.o01), s10 = __ldg(sp + t.o10), s11 = __ldg(sp + t.o11);
                 const float sraw = hblend(s00, s01, s10, s11, t);
                 const float sg = fminf(fmaxf(sraw, 0.01f), 1.0f);
@@ -367,8 +368,8 @@ __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const 
                 gqz = -(gx * c.u + gy * c.v) * c.zinv * c.dz;
             }
         }
-        if (act && glg && dl != 0.0f) hscatter(glg + (int64_t)n * p.hw, t, dl);
-        if (MIX && act && gsg && dsg != 0.0f) hscatter(gsg + (int64_t)n * p.hw, t, dsg);
+        if (act && glg && dl != 0.0f) hscatter(glg, t, dl);
+        if (MIX && act && gsg && dsg != 0.0f) hscatter(gsg, t, dsg);
         if (want_h) {
             // dL/dH[i][j] = sum_pixels gq_i * (x, y, 1)_j; y is the same for the whole warp
             const float v8[8] = {gqx, gqy, gqz, gqx * fx, gqy * fx, gqz * fx, 0.0f, 0.0f};
