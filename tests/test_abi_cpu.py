@@ -78,3 +78,32 @@ def test_product_path_refuses_cpu_tensors():
     cfg = WarpConfig(L.PD_WARP_DISP, False, False, 1.0, (1, 2, 8, 8))
     with pytest.raises(L.PlaneDepthLibraryError):
         warp_composite(cfg, torch.zeros(1, 3, 8, 8), None, torch.zeros(1, 2, 8, 8), None, torch.ones(1, 2, 8, 8), None)
+
+
+def test_argument_validation_returns_codes_not_crashes():
+    """Error behaviour of the C ABI that needs no device: NULL / inconsistent arguments come back as pd_status codes with a
+    message in pd_last_error(); nothing aborts or throws across the boundary."""
+    lib = L.lib()
+    PD_ERR_ARG, PD_ERR_SHAPE = 1, 2
+    assert lib.pd_warp_composite_fwd(None, None, None, None, None) == PD_ERR_ARG
+    assert b"NULL" in lib.pd_last_error()
+    d = L.WarpDesc(B=1, N=300, H=8, W=8, warp_type=L.PD_WARP_DISP)
+    tin = L.WarpIn(src=1, logits=1, disp=1)  # non-NULL dummies: validation stops before anything is dereferenced
+    assert lib.pd_warp_composite_fwd(C.byref(d), C.byref(tin), None, None, None) == PD_ERR_SHAPE
+    assert b"PD_MAX_PLANES" in lib.pd_last_error()
+    d = L.WarpDesc(B=1, N=4, H=8, W=8, warp_type=L.PD_WARP_HOMOGRAPHY)
+    assert lib.pd_warp_composite_fwd(C.byref(d), C.byref(L.WarpIn(src=1, logits=1)), None, None, None) == PD_ERR_ARG
+    assert b"hmat" in lib.pd_last_error()
+    sd = L.SmoothDesc(B=1, H=1, W=8, x0=0, gamma=1.0)
+    assert lib.pd_smooth_loss_fwd(C.byref(sd), 1, 1, 1, 1, None) == PD_ERR_SHAPE
+    od = L.OcclDesc(B=1, N=2, H=4, W=4)
+    assert lib.pd_occlusion_masks_fwd(C.byref(od), C.byref(L.OcclIn(logits=1, disp_layered=1)), C.byref(L.OcclOut()), None, None) == PD_ERR_ARG
+    td = L.TailDesc(B=1, N=2, H=4, W=4, mixture=1)
+    assert lib.pd_plane_tail_fwd(C.byref(td), C.byref(L.TailIn(logits_raw=1, disp_layered=1)), C.byref(L.TailOut()), None) == PD_ERR_ARG
+    # sizes are pure functions of the descriptor
+    wd = L.WarpDesc(B=2, N=5, H=16, W=32, warp_type=L.PD_WARP_HOMOGRAPHY)
+    assert lib.pd_warp_composite_workspace_bytes(C.byref(wd)) == 2 * 16 * 32 * 16
+    wd.warp_type = L.PD_WARP_DISP
+    assert lib.pd_warp_composite_workspace_bytes(C.byref(wd)) == 0
+    assert lib.pd_warp_composite_stats_bytes(C.byref(wd)) == 2 * 2 * 16 * 32 * 4 + 2 * 16 * 8
+    assert lib.pd_occlusion_masks_workspace_bytes(C.byref(od)) == 1 * 2 * 4 * 4 * 4
