@@ -13,7 +13,8 @@
  *  - every pointer is a DEVICE pointer to fp32 unless stated otherwise; tensors are NCHW-contiguous
  *    unless a pd_strides4 says otherwise (element strides, 0 = broadcast along that dimension);
  *  - the caller owns every buffer (incl. workspace); the library allocates nothing persistent and
- *    keeps no global state apart from a thread-local error string;
+ *    keeps no global state apart from a thread-local error string, small caches of device / kernel
+ *    attributes and the explicit tuning block below (pd_set_tuning; tests and benchmarks only);
  *  - all work is enqueued on the given stream; no entry point synchronises the host;
  *  - return value: PD_OK (0) or a pd_status error code; never aborts, never throws;
  *    pd_last_error() returns the message of the last failing call on this thread;
@@ -29,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PD_ABI_VERSION 7
+#define PD_ABI_VERSION 8
 
 typedef void* pd_stream_t; /* a cudaStream_t */
 
@@ -60,7 +61,9 @@ typedef enum pd_mask_dtype { PD_MASK_NONE = 0, PD_MASK_F32 = 1, PD_MASK_U8 = 2 }
  * sample positions by a few ulp of the coordinate (<= 1.2e-4 px at W = 1280).  Without the flag the
  * stereo disparity fast path samples at the exact positions u = x + sign*d, v = y (deviations);
  * homography / depth warps and dense disparities always use the reference's arithmetic. */
-typedef enum pd_warp_flags { PD_FLAG_EXACT_COORDS = 1 } pd_warp_flags;
+/* PD_FLAG_NO_MASK_SUMMARY: the streamed forward does not summarise a dense padding_mask per row (the saved
+ * statistics then say "read every mask row" and the backward streams the mask again); a measurement knob. */
+typedef enum pd_warp_flags { PD_FLAG_EXACT_COORDS = 1, PD_FLAG_NO_MASK_SUMMARY = 2 } pd_warp_flags;
 
 typedef struct pd_strides4 {
     int64_t b, n, y, x;
@@ -120,8 +123,19 @@ typedef struct pd_warp_out {
 } pd_warp_out;
 
 typedef struct pd_warp_grad_out { /* upstream gradients */
-    const float* g_rgb_rec; /* [B,3,H,W] d loss / d rgb_rec (photometric + perceptual) */
+    const float* g_rgb_rec; /* [B,3,H,W] d loss / d rgb_rec (photometric + perceptual); may be NULL (= 0) iff g_ph_sum is set */
     const float* g_nll;     /* [B,1,H,W] d loss / d nll map; mixture only, may be NULL (= 0) */
+    /* Fused photometric backward (optional): with g_ph_sum != NULL the kernels form pd_photometric_bwd's result in
+     * their prologue instead of reading it from HBM (one launch and one [B,3,H,W] round trip less per step):
+     *     g_rgb_rec_eff = [g_rgb_rec] + ph_scale * g_ph_sum[0] * g_unit + [g_pred * mask_novel]
+     *     g_nll_eff     = [g_nll]     + ph_scale * g_ph_sum[0] * g_unit_nll
+     * g_unit / g_unit_nll are what pd_photometric_fwd left in pd_loss_out (trainer.py:720-742 differentiated). */
+    const float* g_ph_sum;   /* [1] device scalar d loss / d ph_sum */
+    float ph_scale;          /* pd_loss_desc.out_scale of the forward call (0 is read as 1) */
+    const float* g_unit;     /* [B,3,H,W] d ph_sum / d rgb_rec; may be NULL (mixture: the photometric term acts through nll) */
+    const float* g_unit_nll; /* [B,1,H,W] d ph_sum / d nll; mixture only, may be NULL */
+    const float* g_pred;     /* [B,3,H,W] d loss / d pred from outside (perceptual term); may be NULL */
+    const float* mask_novel; /* [B,1,H,W] multiplies g_pred (trainer.py:724-726); NULL = ones */
 } pd_warp_grad_out;
 
 typedef struct pd_warp_grad_in { /* produced gradients; any pointer may be NULL (= not needed) */
@@ -136,6 +150,32 @@ typedef struct pd_warp_grad_in { /* produced gradients; any pointer may be NULL 
 
 int pd_version(void);
 const char* pd_last_error(void);
+
+/* Launch tuning of the streamed row kernels: a process-wide block for tests (forcing the persistent loop to iterate),
+ * benchmarks and kernel experiments.  Initialised ONCE at library load from the environment (PD_STREAM_CTAS,
+ * PD_STREAM_HS, PD_STREAM_NST, PD_STREAM_SMEM_KB, PD_STREAM_PX8, PD_SSIM_TILES), values clamped to legal ranges;
+ * 0 = the library's default.  Numerics never depend on it (PD_FLAG_EXACT_COORDS is a per-call descriptor flag). */
+typedef struct pd_tuning {
+    int32_t stream_ctas_per_sm; /* cap on resident CTAs per SM of the persistent grids (0 = occupancy limit) */
+    int32_t stream_hs;          /* planes per ring stage (default 4) */
+    int32_t stream_nst;         /* ring stages (default 3, <= 8) */
+    int32_t stream_smem_kb;     /* shared-memory budget per CTA the ring is shrunk to (0 = per-shape default) */
+    int32_t stream_px8;         /* 8 pixels per thread where the width allows */
+    int32_t ssim_tiles;         /* SSIM+L1 forward: shared-memory tile kernel instead of the streamed warp-column kernel */
+    int32_t homo_tiles;         /* homography warp: 0 = auto, 1 = force the TMA tile kernels, -1 = force the gather kernels */
+    int32_t reserved[9];
+} pd_tuning;
+void pd_get_tuning(pd_tuning* out);
+void pd_set_tuning(const pd_tuning* in); /* NULL restores the values read from the environment at load */
+
+/* ------------------------------------------------------------------------------------------------
+ * Verification of the integrator's "plane geometry does not vary along x" promise (HotPathMixin.disp_rowwise,
+ * INTEGRATION.md): compares every element of a [B,N,H,W] tensor with column 0 of its row and adds the number of
+ * rows that differ to *violations (a device-accessible int32: device memory or pinned host memory, which lets the
+ * host poll it without a synchronisation).  One streaming pass over the tensor; enqueue it on first use of a buffer.
+ * ---------------------------------------------------------------------------------------------- */
+int pd_x_constant_check(const void* data, int32_t dtype /* pd_mask_dtype: PD_MASK_F32 | PD_MASK_U8 */, const pd_strides4* strides,
+                        int32_t B, int32_t N, int32_t H, int32_t W, int32_t* violations, pd_stream_t stream);
 
 /* Scratch the caller passes as `workspace` to both calls below (contents need not survive between them).  Non-zero
  * for the homography fast path only: the source colour re-packed to one rgbx float4 per pixel. */

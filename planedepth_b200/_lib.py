@@ -14,16 +14,15 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.environ.get("PLANEDEPTH_B200_LIB") or os.path.join(CSRC, "libplanedepth_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC",
-]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+BUILD_DIR = os.path.join(CSRC, "build")  # git-ignored object files (one per translation unit)
 
 PD_WARP_DISP, PD_WARP_HOMOGRAPHY, PD_WARP_DEPTH = 0, 1, 2
 PD_LOSS_L1, PD_LOSS_MIXTURE, PD_LOSS_SSIM_L1 = 0, 1, 2
 PD_MASK_NONE, PD_MASK_F32, PD_MASK_U8 = 0, 1, 2
 PD_FLAG_EXACT_COORDS = 1
-ABI_VERSION = 7  # PD_ABI_VERSION in include/planedepth_b200.h
+PD_FLAG_NO_MASK_SUMMARY = 2
+ABI_VERSION = 8  # PD_ABI_VERSION in include/planedepth_b200.h
 PD_STATS_PLAIN, PD_STATS_MIXTURE = 2, 4
 
 EXPORTS = [
@@ -33,6 +32,7 @@ EXPORTS = [
     "pd_occlusion_masks_workspace_bytes", "pd_occlusion_masks_fwd",
     "pd_smooth_loss_workspace_bytes", "pd_smooth_loss_fwd", "pd_smooth_loss_bwd",
     "pd_plane_tail_fwd", "pd_plane_tail_bwd",
+    "pd_get_tuning", "pd_set_tuning", "pd_x_constant_check",
 ]
 
 
@@ -59,7 +59,13 @@ class WarpOut(C.Structure):
 
 
 class WarpGradOut(C.Structure):
-    _fields_ = [("g_rgb_rec", C.c_void_p), ("g_nll", C.c_void_p)]
+    _fields_ = [("g_rgb_rec", C.c_void_p), ("g_nll", C.c_void_p), ("g_ph_sum", C.c_void_p), ("ph_scale", C.c_float),
+                ("g_unit", C.c_void_p), ("g_unit_nll", C.c_void_p), ("g_pred", C.c_void_p), ("mask_novel", C.c_void_p)]
+
+
+class Tuning(C.Structure):
+    _fields_ = [("stream_ctas_per_sm", C.c_int32), ("stream_hs", C.c_int32), ("stream_nst", C.c_int32), ("stream_smem_kb", C.c_int32),
+                ("stream_px8", C.c_int32), ("ssim_tiles", C.c_int32), ("homo_tiles", C.c_int32), ("reserved", C.c_int32 * 9)]
 
 
 class WarpGradIn(C.Structure):
@@ -129,16 +135,108 @@ class PlaneDepthLibraryError(RuntimeError):
     pass
 
 
-def build_library(verbose: bool = False) -> str:
-    """Compile csrc/pd_abi.cu (which includes every kernel) into libplanedepth_b200.so for sm_100a.
-    nvcc cross-compiles without a GPU."""
-    src = os.path.join(CSRC, "pd_abi.cu")
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-o", LIB_PATH, src]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise PlaneDepthLibraryError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
-    if verbose:
-        sys.stderr.write(res.stderr)
+def _sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _includes(path, seen=None):
+    """Transitive closure of the quoted #include s of one source file (the headers its object depends on)."""
+    seen = set() if seen is None else seen
+    try:
+        text = open(path).read()
+    except OSError:
+        return seen
+    for line in text.splitlines():
+        line = line.strip()
+        if line.startswith("#include \""):
+            dep = os.path.normpath(os.path.join(os.path.dirname(path), line.split('"')[1]))
+            if dep not in seen and os.path.exists(dep):
+                seen.add(dep)
+                _includes(dep, seen)
+    return seen
+
+
+def _digest(src):
+    """Content hash of one translation unit and every header it includes (mtimes do not survive a snapshot copy)."""
+    import hashlib
+
+    h = hashlib.sha1()
+    for path in [src] + sorted(_includes(src)):
+        h.update(os.path.basename(path).encode())
+        h.update(open(path, "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _manifest_path():
+    return os.path.join(BUILD_DIR, "manifest.json")
+
+
+def _load_manifest():
+    import json
+
+    try:
+        return json.load(open(_manifest_path()))
+    except (OSError, ValueError):
+        return {}
+
+
+class _BuildLock:
+    """Exclusive file lock around the build: one process per GPU means every rank reaches lib() at the same time; one
+    builds, the others wait and then find a fresh library."""
+
+    def __enter__(self):
+        import fcntl
+
+        os.makedirs(BUILD_DIR, exist_ok=True)
+        self.f = open(os.path.join(BUILD_DIR, ".lock"), "w")
+        fcntl.flock(self.f, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *exc):
+        import fcntl
+
+        fcntl.flock(self.f, fcntl.LOCK_UN)
+        self.f.close()
+
+
+def build_library(verbose: bool = False, force: bool = False) -> str:
+    """Compile every translation unit of csrc/ (pd_abi.cu + one pd_tu_*.cu per kernel family) for sm_100a, in parallel,
+    and link libplanedepth_b200.so.  Objects whose sources / headers did not change are reused.  nvcc cross-compiles
+    without a GPU.  The library is linked to a temporary name and renamed into place, under a file lock."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import json
+
+    with _BuildLock():
+        old = {} if force else _load_manifest()
+        new, jobs, objs = {}, [], []
+        for src in _sources():
+            name = os.path.basename(src)
+            obj = os.path.join(BUILD_DIR, name[:-3] + ".o")
+            objs.append(obj)
+            new[name] = _digest(src)
+            if old.get(name) != new[name] or not os.path.exists(obj):
+                jobs.append(["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-c", "-o", obj, src])
+
+        def run(cmd):
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                raise PlaneDepthLibraryError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
+            return res.stderr
+
+        with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
+            for err in pool.map(run, jobs):
+                if verbose:
+                    sys.stderr.write(err)
+        if jobs or not os.path.exists(LIB_PATH) or old.get("__lib__") != "linked":
+            tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+            run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs)
+            os.replace(tmp, LIB_PATH)
+        new["__lib__"] = "linked"
+        with open(_manifest_path() + ".tmp", "w") as f:
+            json.dump(new, f, indent=1, sort_keys=True)
+        os.replace(_manifest_path() + ".tmp", _manifest_path())
     return LIB_PATH
 
 
@@ -147,10 +245,10 @@ def _needs_rebuild() -> bool:
         return False  # explicit library (kernel-variant experiments): use as is
     if not os.path.exists(LIB_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
-    srcs.append(os.path.join(INCLUDE, "planedepth_b200.h"))
-    return any(os.path.getmtime(s) > t for s in srcs)
+    man = _load_manifest()
+    if man.get("__lib__") != "linked":
+        return True
+    return any(man.get(os.path.basename(src)) != _digest(src) for src in _sources())
 
 
 _lib = None
@@ -207,12 +305,39 @@ def lib() -> C.CDLL:
     L.pd_occlusion_masks_workspace_bytes.argtypes = [C.POINTER(OcclDesc)]
     L.pd_occlusion_masks_fwd.restype = C.c_int
     L.pd_occlusion_masks_fwd.argtypes = [C.POINTER(OcclDesc), C.POINTER(OcclIn), C.POINTER(OcclOut), C.c_void_p, C.c_void_p]
+    L.pd_get_tuning.restype = None
+    L.pd_get_tuning.argtypes = [C.POINTER(Tuning)]
+    L.pd_set_tuning.restype = None
+    L.pd_set_tuning.argtypes = [C.POINTER(Tuning)]
+    L.pd_x_constant_check.restype = C.c_int
+    L.pd_x_constant_check.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Strides4), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     L.pd_debug_roundtrip.restype = C.c_int
     L.pd_debug_roundtrip.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     if L.pd_version() != ABI_VERSION:
         raise PlaneDepthLibraryError("ABI version mismatch: library %d, binding %d" % (L.pd_version(), ABI_VERSION))
     _lib = L
     return L
+
+
+class tuned:
+    """Context manager for tests / experiments: ``with tuned(stream_ctas_per_sm=1): ...`` (pd_set_tuning)."""
+
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        L = lib()
+        self.old = Tuning()
+        L.pd_get_tuning(C.byref(self.old))
+        new = Tuning()
+        C.memmove(C.byref(new), C.byref(self.old), C.sizeof(Tuning))
+        for k, v in self.kw.items():
+            setattr(new, k, int(v))
+        L.pd_set_tuning(C.byref(new))
+        return self
+
+    def __exit__(self, *exc):
+        lib().pd_set_tuning(C.byref(self.old))
 
 
 def check(rc: int, what: str) -> None:

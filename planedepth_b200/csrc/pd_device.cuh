@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include "../../include/planedepth_b200.h"
+#include "pd_common.h"
 
 namespace pd {
 
@@ -48,6 +49,10 @@ __device__ __forceinline__ float roundtrip_fast(float p, float size_m1, float rc
     // ((g+1)*0.5)*(size-1) == (g+1)*((size-1)/2): the halving is exact and (size-1)/2 is representable
     return __fmul_rn(__fadd_rn(g, 1.0f), 0.5f * size_m1);
 }
+
+// reciprocal handed to roundtrip_fast(); 0 = "use the IEEE-division form" (size-1 = 2^k - 1: the Newton step is not
+// guaranteed to round correctly)
+inline float rows_rcp(int size) { return ((size & (size - 1)) == 0) ? 0.0f : 1.0f / (float)(size - 1); }
 
 struct Taps {
     // integer corner (x0,y0), fractional weights exactly as ATen forms them

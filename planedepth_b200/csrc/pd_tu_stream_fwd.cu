@@ -1,0 +1,9 @@
+// Translation unit: TMA-streamed forward row kernels (pd_warp_stream.cuh, rows_fwd_stream instantiations).
+#include "pd_warp_stream.cuh"
+
+namespace pd {
+namespace api {
+bool stream_supported(const WarpParams& p) { return ts::stream_path_supported(p); }
+bool stream_fwd(const WarpParams& p, cudaStream_t st) { return ts::launch_fwd_stream(p, st); }
+}  // namespace api
+}  // namespace pd

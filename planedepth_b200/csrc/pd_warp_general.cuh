@@ -27,6 +27,60 @@ struct WarpParams {
     unsigned long long* mask_rows;
 };
 
+// Upstream gradients in pd_warp_grad_out's (optionally fused) form: what pd_photometric_bwd would have written,
+//   g_rgb_rec_eff = [g_rgb_rec] + gph * g_unit + [g_pred * mask_novel],   g_nll_eff = [g_nll] + gph * g_unit_nll,
+// with gph = ph_scale * g_ph_sum[0] (same operation order as photometric_bwd_kernel: product, then fused add).
+__device__ __forceinline__ float upstream_scale(const WarpParams& p) {
+    return p.gout.g_ph_sum ? __ldg(p.gout.g_ph_sum) * (p.gout.ph_scale != 0.0f ? p.gout.ph_scale : 1.0f) : 0.0f;
+}
+// i = offset into [B,3,H,W], pix = offset into [B,1,H,W]
+__device__ __forceinline__ float upstream_rgb(const WarpParams& p, float gph, int64_t i, int64_t pix) {
+    float g = 0.0f;
+    if (p.gout.g_ph_sum) {
+        if (p.gout.g_unit) g = gph * __ldg(p.gout.g_unit + i);
+        if (p.gout.g_pred) g = fmaf(__ldg(p.gout.g_pred + i), p.gout.mask_novel ? __ldg(p.gout.mask_novel + pix) : 1.0f, g);
+    }
+    if (p.gout.g_rgb_rec) g += __ldg(p.gout.g_rgb_rec + i);
+    return g;
+}
+__device__ __forceinline__ float upstream_nll(const WarpParams& p, float gph, int64_t pix) {
+    float g = (p.gout.g_ph_sum && p.gout.g_unit_nll) ? gph * __ldg(p.gout.g_unit_nll + pix) : 0.0f;
+    if (p.gout.g_nll) g += __ldg(p.gout.g_nll + pix);
+    return g;
+}
+__device__ __forceinline__ float4 upstream_rgb4(const WarpParams& p, float gph, int64_t i, int64_t pix) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.gout.g_ph_sum) {
+        if (p.gout.g_unit) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(p.gout.g_unit + i));
+            g = make_float4(gph * u.x, gph * u.y, gph * u.z, gph * u.w);
+        }
+        if (p.gout.g_pred) {
+            const float4 e = __ldg(reinterpret_cast<const float4*>(p.gout.g_pred + i));
+            float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (p.gout.mask_novel) m = __ldg(reinterpret_cast<const float4*>(p.gout.mask_novel + pix));
+            g.x = fmaf(e.x, m.x, g.x), g.y = fmaf(e.y, m.y, g.y), g.z = fmaf(e.z, m.z, g.z), g.w = fmaf(e.w, m.w, g.w);
+        }
+    }
+    if (p.gout.g_rgb_rec) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(p.gout.g_rgb_rec + i));
+        g.x += r.x, g.y += r.y, g.z += r.z, g.w += r.w;
+    }
+    return g;
+}
+__device__ __forceinline__ float4 upstream_nll4(const WarpParams& p, float gph, int64_t pix) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.gout.g_ph_sum && p.gout.g_unit_nll) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(p.gout.g_unit_nll + pix));
+        g = make_float4(gph * u.x, gph * u.y, gph * u.z, gph * u.w);
+    }
+    if (p.gout.g_nll) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(p.gout.g_nll + pix));
+        g.x += r.x, g.y += r.y, g.z += r.z, g.w += r.w;
+    }
+    return g;
+}
+
 // Source coordinates (u,v) of target pixel (x,y) on plane n, plus the multiplicative validity mask.
 // aux[] receives what the backward needs to chain the coordinate gradient to the warp parameters.
 template <int WARP>
@@ -219,8 +273,10 @@ __global__ void __launch_bounds__(256) warp_composite_bwd_general(const WarpPara
     const int N = p.d.N, W = p.d.W, H = p.d.H;
     const int lane = threadIdx.x & 31;
 
-    const float* gp = p.gout.g_rgb_rec + (int64_t)b * p.chw3 + rem;
-    float g0 = live ? __ldg(gp) : 0.0f, g1 = live ? __ldg(gp + p.hw) : 0.0f, g2 = live ? __ldg(gp + 2 * p.hw) : 0.0f;
+    const float gph = upstream_scale(p);
+    const int64_t gi = (int64_t)b * p.chw3 + rem;
+    float g0 = live ? upstream_rgb(p, gph, gi, pc) : 0.0f, g1 = live ? upstream_rgb(p, gph, gi + p.hw, pc) : 0.0f,
+          g2 = live ? upstream_rgb(p, gph, gi + 2 * p.hw, pc) : 0.0f;
     const float* rp = p.out.rgb_rec + (int64_t)b * p.chw3 + rem;
     const float Gbar = g0 * __ldg(rp) + g1 * __ldg(rp + p.hw) + g2 * __ldg(rp + 2 * p.hw);
     const float* st = p.out.stats + (int64_t)b * (MIX ? PD_STATS_MIXTURE : PD_STATS_PLAIN) * p.hw + rem;
@@ -231,7 +287,7 @@ __global__ void __launch_bounds__(256) warp_composite_bwd_general(const WarpPara
         tr = __ldg(tp), tg = __ldg(tp + p.hw), tb = __ldg(tp + 2 * p.hw);
         invA = 1.0f / __ldg(st + 2 * p.hw);
         float D = __ldg(st + 3 * p.hw);
-        float gn = (p.gout.g_nll && live) ? __ldg(p.gout.g_nll + pc) : 0.0f;
+        float gn = live ? upstream_nll(p, gph, pc) : 0.0f;
         gD = -gn / D;            // d loss / d D,  nll = -log D
         gDD = gD * (D - 1e-7f);  // = sum_k pi_k P_k (backward algebra)
     }

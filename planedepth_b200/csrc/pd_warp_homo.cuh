@@ -14,7 +14,6 @@
 // PD_FLAG_EXACT_COORDS keeps the general kernels (IEEE divisions).
 #pragma once
 #include "pd_warp_general.cuh"
-#include "pd_warp_rows.cuh"
 
 namespace pd {
 namespace hm {
@@ -287,8 +286,9 @@ __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const 
     const float ry = fmaf(__ldg(ik + 4), fy, __ldg(ik + 3) * fx) + __ldg(ik + 5);
     const float rz = fmaf(__ldg(ik + 7), fy, __ldg(ik + 6) * fx) + __ldg(ik + 8);
 
-    const float* gp = p.gout.g_rgb_rec + (int64_t)b * p.chw3 + rem;
-    const float g0 = __ldg(gp), g1 = __ldg(gp + p.hw), g2 = __ldg(gp + 2 * p.hw);
+    const float gph = upstream_scale(p);
+    const int64_t gi = (int64_t)b * p.chw3 + rem;
+    const float g0 = upstream_rgb(p, gph, gi, pix), g1 = upstream_rgb(p, gph, gi + p.hw, pix), g2 = upstream_rgb(p, gph, gi + 2 * p.hw, pix);
     const float* rp = p.out.rgb_rec + (int64_t)b * p.chw3 + rem;
     const float Gbar = g0 * __ldg(rp) + g1 * __ldg(rp + p.hw) + g2 * __ldg(rp + 2 * p.hw);
     const float* st = p.out.stats + (int64_t)b * (MIX ? PD_STATS_MIXTURE : PD_STATS_PLAIN) * p.hw + rem;
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const 
         tr = __ldg(tp), tg = __ldg(tp + p.hw), tb = __ldg(tp + 2 * p.hw);
         Zinv = Sv / __ldg(st + 2 * p.hw);  // 1/Z, Z = sum pi/sigma = A/S
         const float D = __ldg(st + 3 * p.hw);
-        const float gn = p.gout.g_nll ? __ldg(p.gout.g_nll + pix) : 0.0f;
+        const float gn = upstream_nll(p, gph, pix);
         gD = -gn / D;            // d loss / d D,  nll = -log D
         gDD = gD * (D - 1e-7f);  // = sum_k pi_k P_k
     }

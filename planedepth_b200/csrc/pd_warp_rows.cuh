@@ -15,12 +15,6 @@
 // un-normalise round trip of the coordinates); see DESIGN.md for the two documented deviations
 // (row pre-blend order, dropped <=6.2e-5-weighted cross-row taps in the backward).
 #pragma once
-#include <stdlib.h>
-
-#include <atomic>
-#include <map>
-#include <mutex>
-
 #include "pd_warp_general.cuh"
 
 namespace pd {
@@ -522,9 +516,10 @@ __global__ void __launch_bounds__(THREADS, MINB) warp_composite_bwd_rows(const W
         float g0[RP], g1[RP], g2[RP], Gbar[RP], Ml2[RP], invS[RP];
         float tr[RP], tg[RP], tb[RP], Zinv[RP], gD[RP], gDD[RP];
         if (c.active) {
-            const float* gp = p.gout.g_rgb_rec + (int64_t)c.b * p.chw3 + rem;
+            const float gph = upstream_scale(p);
+            const int64_t gi = (int64_t)c.b * p.chw3 + rem, gpix = (int64_t)c.b * p.hw + rem;
             const float* rp = p.out.rgb_rec + (int64_t)c.b * p.chw3 + rem;
-            float4 a = ldg4(gp), bq = ldg4(gp + p.hw), cq = ldg4(gp + 2 * p.hw);
+            float4 a = upstream_rgb4(p, gph, gi, gpix), bq = upstream_rgb4(p, gph, gi + p.hw, gpix), cq = upstream_rgb4(p, gph, gi + 2 * p.hw, gpix);
             float4 ra = ldg4(rp), rb = ldg4(rp + p.hw), rc = ldg4(rp + 2 * p.hw);
             g0[0] = a.x, g0[1] = a.y, g0[2] = a.z, g0[3] = a.w;
             g1[0] = bq.x, g1[1] = bq.y, g1[2] = bq.z, g1[3] = bq.w;
@@ -546,7 +541,7 @@ __global__ void __launch_bounds__(THREADS, MINB) warp_composite_bwd_rows(const W
                 tg[0] = tbq.x, tg[1] = tbq.y, tg[2] = tbq.z, tg[3] = tbq.w;
                 tb[0] = tcq.x, tb[1] = tcq.y, tb[2] = tcq.z, tb[3] = tcq.w;
                 float4 a4 = ldg4(st + 2 * p.hw), d4 = ldg4(st + 3 * p.hw);
-                float4 gn = p.gout.g_nll ? ldg4(p.gout.g_nll + (int64_t)c.b * p.hw + rem) : zero4();
+                float4 gn = upstream_nll4(p, gph, gpix);
                 float Av[RP] = {a4.x, a4.y, a4.z, a4.w}, Dv[RP] = {d4.x, d4.y, d4.z, d4.w}, gv[RP] = {gn.x, gn.y, gn.z, gn.w};
 #pragma unroll
                 for (int i = 0; i < RP; ++i) {
@@ -667,7 +662,6 @@ inline int rows_mask_mode(const WarpParams& p) {
 }
 
 inline bool rows_path_supported(const WarpParams& p) {
-    if (getenv("PD_DISABLE_ROWS")) return false;
     if (p.d.warp_type != PD_WARP_DISP) return false;
     const int W = p.d.W;
     if (W % 4 != 0 || W < 8 || W > 1280) return false;
@@ -681,24 +675,18 @@ inline bool rows_path_supported(const WarpParams& p) {
     // w.r.t. disp_layered the fast backward supports no gradient or a gradient reduced over x
     if (p.gin.g_disp && p.gin.g_disp_stride.x != 0) return false;
     const void* ptrs[] = {p.in.src, p.in.tgt, p.in.logits, p.in.sigma, p.out.rgb_rec, p.out.stats, p.out.nll, p.out.nll_auto,
-                          p.gout.g_rgb_rec, p.gout.g_nll, p.gin.g_logits, p.gin.g_sigma};
+                          p.gout.g_rgb_rec, p.gout.g_nll, p.gout.g_unit, p.gout.g_unit_nll, p.gout.g_pred, p.gout.mask_novel,
+                          p.gin.g_logits, p.gin.g_sigma};
     for (const void* q : ptrs)
         if (q && !aligned16(q)) return false;
     return true;
 }
 
 inline int rows_grid(int rows_total, int threads, size_t smem, const void* kernel) {
-    int dev = 0, sms = 148, per_sm = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
-    if (per_sm < 1) per_sm = 1;
-    long long g = (long long)sms * per_sm;
+    const long long g = (long long)sm_count() * resident_ctas(kernel, threads, smem);
     return (int)(g < rows_total ? g : rows_total);
 }
 
-// reciprocal for the division-free round trip (rows_path_supported excludes W-1 = 2^k - 1)
-inline float rows_rcp(int W) { return ((W & (W - 1)) == 0) ? 0.0f : 1.0f / (float)(W - 1); }
 inline int rows_threads(int W) { return ((W / RP + 31) / 32) * 32; }
 inline size_t rows_smem_fwd(int N, int W) { return (size_t)3 * (W + 2 * ROW_PAD) * sizeof(float) + (size_t)N * sizeof(PlaneRow); }
 
@@ -707,15 +695,7 @@ inline size_t rows_smem_fwd(int N, int W) { return (size_t)3 * (W + 2 * ROW_PAD)
 // into a CUDA graph.
 template <typename K>
 inline void rows_launch_cfg(K kern, size_t smem) {
-    static std::mutex mu;
-    static std::map<const void*, size_t> granted;  // keyed by kernel: instantiations share this function's type
-    if (smem <= 48 * 1024) return;
-    std::lock_guard<std::mutex> lock(mu);
-    size_t& g = granted[(const void*)kern];
-    if (smem > g) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        g = smem;
-    }
+    smem_optin((const void*)kern, smem);
 }
 
 template <bool MIX, int MASKMODE>

@@ -22,11 +22,6 @@
 // 1.2e-4 px at W=1280); pd_warp_rows.cuh reproduces that perturbation bit for bit and is selected with
 // PD_FLAG_EXACT_COORDS.  DESIGN.md (deviations) quantifies the difference.
 #pragma once
-#include <stdlib.h>
-
-#include <map>
-#include <mutex>
-
 #include "pd_warp_general.cuh"
 
 namespace pd {
@@ -163,6 +158,15 @@ __device__ __forceinline__ void load_px_global(const float* q, float (&v)[PX]) {
     for (int i = 0; i < PX / 4; ++i) {
         float4 t = __ldg(reinterpret_cast<const float4*>(q) + i);
         v[4 * i] = t.x, v[4 * i + 1] = t.y, v[4 * i + 2] = t.z, v[4 * i + 3] = t.w;
+    }
+}
+
+template <int PX>
+__device__ __forceinline__ void load_upstream(const WarpParams& p, float gph, int64_t i, int64_t pix, float (&v)[PX]) {
+#pragma unroll
+    for (int k = 0; k < PX / 4; ++k) {
+        const float4 t = upstream_rgb4(p, gph, i + 4 * k, pix + 4 * k);
+        v[4 * k] = t.x, v[4 * k + 1] = t.y, v[4 * k + 2] = t.z, v[4 * k + 3] = t.w;
     }
 }
 
@@ -781,6 +785,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
     const int x04 = x0 * 4, W4 = W * 4;
     int stage = 0, jb = 0;
     uint32_t fphase = 0;
+    const float gph = upstream_scale(p);
 
     for (int it = 0; it < nit; ++it) {
         const int g = blockIdx.x + it * gridDim.x;
@@ -795,12 +800,13 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
 
         BwdCtx<MIX, PX> c;
         if (active) {
-            const float* gp = p.gout.g_rgb_rec + (int64_t)b * p.chw3 + rem;
             const float* rp = p.out.rgb_rec + (int64_t)b * p.chw3 + rem;
             float ra[PX], rb[PX], rc[PX], Sv[PX];
-            load_px_global<PX>(gp, c.g0);
-            load_px_global<PX>(gp + p.hw, c.g1);
-            load_px_global<PX>(gp + 2 * p.hw, c.g2);
+            // upstream gradient, optionally formed from the photometric forward's unit gradient (pd_warp_grad_out)
+            const int64_t gi = (int64_t)b * p.chw3 + rem, gpix = (int64_t)b * p.hw + rem;
+            load_upstream<PX>(p, gph, gi, gpix, c.g0);
+            load_upstream<PX>(p, gph, gi + p.hw, gpix, c.g1);
+            load_upstream<PX>(p, gph, gi + 2 * p.hw, gpix, c.g2);
             load_px_global<PX>(rp, ra);
             load_px_global<PX>(rp + p.hw, rb);
             load_px_global<PX>(rp + 2 * p.hw, rc);
@@ -820,10 +826,11 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
                 load_px_global<PX>(tp + 2 * p.hw, c.tb);
                 load_px_global<PX>(st + 2 * p.hw, Av);
                 load_px_global<PX>(st + 3 * p.hw, Dv);
-                if (p.gout.g_nll) load_px_global<PX>(p.gout.g_nll + (int64_t)b * p.hw + rem, gv);
-                else
 #pragma unroll
-                    for (int i = 0; i < PX; ++i) gv[i] = 0.0f;
+                for (int i = 0; i < PX / 4; ++i) {
+                    const float4 t4 = upstream_nll4(p, gph, gpix + 4 * i);
+                    gv[4 * i] = t4.x, gv[4 * i + 1] = t4.y, gv[4 * i + 2] = t4.z, gv[4 * i + 3] = t4.w;
+                }
 #pragma unroll
                 for (int i = 0; i < PX; ++i) {
                     c.Zinv[i] = Sv[i] / Av[i];              // 1/Z, Z = sum pi/sigma = A/S
@@ -941,15 +948,11 @@ inline bool stream_path_supported(const WarpParams& p) {
     }
     if (p.gin.g_disp && p.gin.g_disp_stride.x != 0) return false;  // d/d disp only reduced over x
     const void* ptrs[] = {p.in.src, p.in.tgt, p.in.logits, p.in.sigma, p.out.rgb_rec, p.out.stats, p.out.nll, p.out.nll_auto,
-                          p.gout.g_rgb_rec, p.gout.g_nll, p.gin.g_logits, p.gin.g_sigma};
+                          p.gout.g_rgb_rec, p.gout.g_nll, p.gout.g_unit, p.gout.g_unit_nll, p.gout.g_pred, p.gout.mask_novel,
+                          p.gin.g_logits, p.gin.g_sigma};
     for (const void* q : ptrs)
         if (q && !ts_aligned16(q)) return false;
     return true;
-}
-
-inline int stream_env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
 }
 
 template <int PX, int THREADS>
@@ -961,16 +964,16 @@ inline StreamCfg stream_cfg(const WarpParams& p, bool mix, bool dense, int ne_bw
     if (c.rpc > 8) c.rpc = 8;
     c.pitch = p.d.W + 2 * PAD;
     c.nc = ((c.rpc * c.tpr + 31) / 32) * 32;
-    c.hs = stream_env_int("PD_STREAM_HS", 4);
+    const pd_tuning& tn = tuning();  // clamped when it was set: hs >= 1, 1 <= nst <= MAX_STAGES
+    c.hs = tn.stream_hs > 0 ? tn.stream_hs : 4;
     if (c.hs > p.d.N) c.hs = p.d.N;
-    c.nst = stream_env_int("PD_STREAM_NST", 3);
+    c.nst = tn.stream_nst > 0 ? tn.stream_nst : 3;
     if (c.nst > MAX_STAGES) c.nst = MAX_STAGES;
-    if (c.nst < 1) c.nst = 1;
     // shrink the pipeline until the CTA fits the shared-memory budget (default: three CTAs per SM)
     // (three CTAs of <= 192 threads per SM, two of the 352-thread CTAs that wide rows need)
     // (the wide mixture backward runs one CTA per SM on registers anyway: it gets a deep ring instead, cfg3 0.82 -> 0.69 ms)
     const int dflt_kb = c.nc > 160 ? ((mix && ne_bwd > 0) ? 200 : 110) : 72;
-    const size_t budget = (size_t)stream_env_int("PD_STREAM_SMEM_KB", dflt_kb) * 1024;
+    const size_t budget = (size_t)(tn.stream_smem_kb > 0 ? tn.stream_smem_kb : dflt_kb) * 1024;
     while (stream_smem_bytes(c, p.d.N, mix, dense, ne_bwd, want_disp) > budget) {
         if (c.nst > 2) --c.nst;
         else if (c.hs > 1) --c.hs;
@@ -984,37 +987,26 @@ inline StreamCfg stream_cfg(const WarpParams& p, bool mix, bool dense, int ne_bw
 
 template <typename K>
 inline void stream_smem_optin(K kern, size_t smem) {
-    static std::mutex mu;
-    static std::map<const void*, size_t> granted;
-    if (smem <= 48 * 1024) return;
-    std::lock_guard<std::mutex> lock(mu);
-    size_t& g = granted[(const void*)kern];
-    if (smem > g) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        g = smem;
-    }
+    smem_optin((const void*)kern, smem);
 }
 
 inline int stream_grid(int ngroups, int threads, size_t smem, const void* kernel) {
-    int dev = 0, sms = 148, per_sm = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
-    if (per_sm < 1) per_sm = 1;
-    const int cap = stream_env_int("PD_STREAM_CTAS", 0);
+    int per_sm = resident_ctas(kernel, threads, smem);
+    const int cap = tuning().stream_ctas_per_sm;
     if (cap > 0 && per_sm > cap) per_sm = cap;
-    long long g = (long long)sms * per_sm;
+    const long long g = (long long)sm_count() * per_sm;
     return (int)(g < ngroups ? g : ngroups);
 }
 
 // THREADS = consumer threads the row groups are packed into + the producer warp
 template <bool MIX, int MASKMODE, int PX, int THREADS, int MINB>
-inline bool launch_fwd_stream_t(const WarpParams& p, cudaStream_t st) {
+inline bool launch_fwd_stream_t(const WarpParams& p, cudaStream_t st, bool dry) {
     const StreamCfg c = stream_cfg<PX, THREADS - 32>(p, MIX, MASKMODE == SMASK_DENSE, 0, false);
     const int threads = c.nc + 32;
     if (threads > THREADS) return false;
     const size_t smem = stream_smem_bytes(c, p.d.N, MIX, MASKMODE == SMASK_DENSE, 0, false);
     if (smem > 220 * 1024) return false;
+    if (dry) return true;
     auto kern = rows_fwd_stream<MIX, MASKMODE, PX, THREADS, MINB>;
     stream_smem_optin(kern, smem);
     kern<<<stream_grid(c.ngroups, threads, smem, (const void*)kern), threads, smem, st>>>(p, c);
@@ -1022,12 +1014,13 @@ inline bool launch_fwd_stream_t(const WarpParams& p, cudaStream_t st) {
 }
 
 template <bool MIX, int MASKMODE, bool WANT_DISP, int PX, int THREADS, int MINB>
-inline bool launch_bwd_stream_t(const WarpParams& p, cudaStream_t st) {
+inline bool launch_bwd_stream_t(const WarpParams& p, cudaStream_t st, bool dry) {
     const StreamCfg c = stream_cfg<PX, THREADS - 32>(p, MIX, MASKMODE == SMASK_DENSE, MIX ? 2 : 1, WANT_DISP);
     const int threads = c.nc + 32;
     if (threads > THREADS) return false;
     const size_t smem = stream_smem_bytes(c, p.d.N, MIX, MASKMODE == SMASK_DENSE, MIX ? 2 : 1, WANT_DISP);
     if (smem > 220 * 1024) return false;
+    if (dry) return true;
     auto kern = rows_bwd_stream<MIX, MASKMODE, WANT_DISP, PX, THREADS, MINB>;
     stream_smem_optin(kern, smem);
     kern<<<stream_grid(c.ngroups, threads, smem, (const void*)kern), threads, smem, st>>>(p, c);
@@ -1035,50 +1028,44 @@ inline bool launch_bwd_stream_t(const WarpParams& p, cudaStream_t st) {
 }
 
 template <bool MIX, int MASKMODE>
-inline bool launch_fwd_stream_m(const WarpParams& p, cudaStream_t st) {
+inline bool launch_fwd_stream_m(const WarpParams& p, cudaStream_t st, bool dry) {
     const int W = p.d.W;
-    if (W % 8 == 0 && W / 8 <= 160 && stream_env_int("PD_STREAM_PX8", 0)) return launch_fwd_stream_t<MIX, MASKMODE, 8, 192, 2>(p, st);
-    if (W / 4 <= 160) return launch_fwd_stream_t<MIX, MASKMODE, 4, 192, MIX ? 2 : 4>(p, st);
-    if (W / 4 <= 320) return launch_fwd_stream_t<MIX, MASKMODE, 4, 352, MIX ? 2 : 2>(p, st);
+    if (W % 8 == 0 && W / 8 <= 160 && tuning().stream_px8) return launch_fwd_stream_t<MIX, MASKMODE, 8, 192, 2>(p, st, dry);
+    if (W / 4 <= 160) return launch_fwd_stream_t<MIX, MASKMODE, 4, 192, MIX ? 2 : 4>(p, st, dry);
+    if (W / 4 <= 320) return launch_fwd_stream_t<MIX, MASKMODE, 4, 352, MIX ? 2 : 2>(p, st, dry);
     return false;
 }
 
-inline bool launch_fwd_stream(const WarpParams& p, cudaStream_t st) {
+inline bool launch_fwd_stream(const WarpParams& p, cudaStream_t st, bool dry = false) {
     const int mm = stream_mask_mode(p);
-    if (p.d.mixture) return mm == SMASK_ROW ? launch_fwd_stream_m<true, SMASK_ROW>(p, st) : launch_fwd_stream_m<true, SMASK_DENSE>(p, st);
-    return mm == SMASK_ROW ? launch_fwd_stream_m<false, SMASK_ROW>(p, st) : launch_fwd_stream_m<false, SMASK_DENSE>(p, st);
+    if (p.d.mixture) return mm == SMASK_ROW ? launch_fwd_stream_m<true, SMASK_ROW>(p, st, dry) : launch_fwd_stream_m<true, SMASK_DENSE>(p, st, dry);
+    return mm == SMASK_ROW ? launch_fwd_stream_m<false, SMASK_ROW>(p, st, dry) : launch_fwd_stream_m<false, SMASK_DENSE>(p, st, dry);
 }
 
 template <bool MIX, int MASKMODE, bool WANT_DISP>
-inline bool launch_bwd_stream_w(const WarpParams& p, cudaStream_t st) {
+inline bool launch_bwd_stream_w(const WarpParams& p, cudaStream_t st, bool dry) {
     const int W = p.d.W;
-    if (W % 8 == 0 && W / 8 <= 160 && stream_env_int("PD_STREAM_PX8", 0)) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 8, 192, 1>(p, st);
-    if (W / 4 <= 160) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 4, 192, MIX ? 2 : 3>(p, st);
-    if (W / 4 <= 320) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 4, 352, 1>(p, st);
+    if (W % 8 == 0 && W / 8 <= 160 && tuning().stream_px8) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 8, 192, 1>(p, st, dry);
+    if (W / 4 <= 160) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 4, 192, MIX ? 2 : 3>(p, st, dry);
+    if (W / 4 <= 320) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 4, 352, 1>(p, st, dry);
     return false;
 }
 
-// true when launch_bwd_stream() will find a configuration (so that the caller may skip the zero-fill the
-// scatter kernels need)
-inline bool stream_bwd_fits(const WarpParams& p) {
-    const int W = p.d.W;
-    return (W % 8 == 0 && W / 8 <= 160) || W / 4 <= 320;
-}
 
 template <bool MIX, int MASKMODE>
-inline bool launch_bwd_stream_m(const WarpParams& p, cudaStream_t st) {
-    return p.gin.g_disp ? launch_bwd_stream_w<MIX, MASKMODE, true>(p, st) : launch_bwd_stream_w<MIX, MASKMODE, false>(p, st);
+inline bool launch_bwd_stream_m(const WarpParams& p, cudaStream_t st, bool dry) {
+    return p.gin.g_disp ? launch_bwd_stream_w<MIX, MASKMODE, true>(p, st, dry) : launch_bwd_stream_w<MIX, MASKMODE, false>(p, st, dry);
 }
 
-inline bool launch_bwd_stream(const WarpParams& p, cudaStream_t st) {
+inline bool launch_bwd_stream(const WarpParams& p, cudaStream_t st, bool dry = false) {
     int mm = stream_mask_mode(p);
     if (mm == SMASK_DENSE && p.mask_rows) mm = SMASK_SUMMARY;  // the forward pass left a row summary of the mask
     if (p.d.mixture) {
-        if (mm == SMASK_SUMMARY) return launch_bwd_stream_m<true, SMASK_SUMMARY>(p, st);
-        return mm == SMASK_ROW ? launch_bwd_stream_m<true, SMASK_ROW>(p, st) : launch_bwd_stream_m<true, SMASK_DENSE>(p, st);
+        if (mm == SMASK_SUMMARY) return launch_bwd_stream_m<true, SMASK_SUMMARY>(p, st, dry);
+        return mm == SMASK_ROW ? launch_bwd_stream_m<true, SMASK_ROW>(p, st, dry) : launch_bwd_stream_m<true, SMASK_DENSE>(p, st, dry);
     }
-    if (mm == SMASK_SUMMARY) return launch_bwd_stream_m<false, SMASK_SUMMARY>(p, st);
-    return mm == SMASK_ROW ? launch_bwd_stream_m<false, SMASK_ROW>(p, st) : launch_bwd_stream_m<false, SMASK_DENSE>(p, st);
+    if (mm == SMASK_SUMMARY) return launch_bwd_stream_m<false, SMASK_SUMMARY>(p, st, dry);
+    return mm == SMASK_ROW ? launch_bwd_stream_m<false, SMASK_ROW>(p, st, dry) : launch_bwd_stream_m<false, SMASK_DENSE>(p, st, dry);
 }
 
 }  // namespace ts

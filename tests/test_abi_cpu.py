@@ -36,7 +36,7 @@ def test_ctypes_structs_match_c_layout(tmp_path):
         "pd_loss_out": L.LossOut, "pd_loss_grad_out": L.LossGradOut, "pd_loss_grad_in": L.LossGradIn,
         "pd_occl_desc": L.OcclDesc, "pd_occl_in": L.OcclIn, "pd_occl_out": L.OcclOut, "pd_smooth_desc": L.SmoothDesc,
         "pd_tail_desc": L.TailDesc, "pd_tail_in": L.TailIn, "pd_tail_out": L.TailOut, "pd_tail_grad_out": L.TailGradOut,
-        "pd_tail_grad_in": L.TailGradIn,
+        "pd_tail_grad_in": L.TailGradIn, "pd_tuning": L.Tuning,
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "planedepth_b200.h"', "int main(void){"]
     for cname, st in structs.items():
@@ -107,3 +107,35 @@ def test_argument_validation_returns_codes_not_crashes():
     assert lib.pd_warp_composite_workspace_bytes(C.byref(wd)) == 0
     assert lib.pd_warp_composite_stats_bytes(C.byref(wd)) == 2 * 2 * 16 * 32 * 4 + 2 * 16 * 8
     assert lib.pd_occlusion_masks_workspace_bytes(C.byref(od)) == 1 * 2 * 4 * 4 * 4
+
+
+def test_tuning_block_is_clamped_and_restorable():
+    """pd_set_tuning replaces the per-call getenv knobs of round 1: values are clamped when they are set (a zero or negative
+    ring depth can no longer reach a division), NULL restores what the environment said at load."""
+    lib = L.lib()
+    t = L.Tuning(stream_ctas_per_sm=-3, stream_hs=-1, stream_nst=99, stream_smem_kb=10 ** 6, stream_px8=7, ssim_tiles=-2, homo_tiles=5)
+    lib.pd_set_tuning(C.byref(t))
+    got = L.Tuning()
+    lib.pd_get_tuning(C.byref(got))
+    assert (got.stream_ctas_per_sm, got.stream_hs, got.stream_nst, got.stream_smem_kb, got.stream_px8, got.ssim_tiles, got.homo_tiles) == (0, 0, 8, 220, 1, 1, 1)
+    lib.pd_set_tuning(None)
+    lib.pd_get_tuning(C.byref(got))
+    assert got.stream_nst == int(os.environ.get("PD_STREAM_NST", "0") or 0)
+    with L.tuned(stream_ctas_per_sm=1):
+        lib.pd_get_tuning(C.byref(got))
+        assert got.stream_ctas_per_sm == 1
+    lib.pd_get_tuning(C.byref(got))
+    assert got.stream_ctas_per_sm == int(os.environ.get("PD_STREAM_CTAS", "0") or 0)
+
+
+def test_no_per_call_environment_reads():
+    """kernel selection must not depend on getenv() at call time.  The only getenv in the library sits in the
+    load-time initialiser of the tuning block."""
+    csrc = os.path.join(ROOT, "planedepth_b200", "csrc")
+    hits = []
+    for f in sorted(os.listdir(csrc)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            for i, line in enumerate(open(os.path.join(csrc, f)), 1):
+                if "getenv(" in line and not line.lstrip().startswith("//"):
+                    hits.append((f, i))
+    assert [f for f, _ in hits] == ["pd_abi.cu"], hits
