@@ -171,8 +171,8 @@ void pd_set_tuning(const pd_tuning* in); /* NULL restores the values read from t
 /* ------------------------------------------------------------------------------------------------
  * Verification of the integrator's "plane geometry does not vary along x" promise (HotPathMixin.disp_rowwise,
  * INTEGRATION.md): compares every element of a [B,N,H,W] tensor with column 0 of its row and adds the number of
- * rows that differ to *violations (a device-accessible int32: device memory or pinned host memory, which lets the
- * host poll it without a synchronisation).  One streaming pass over the tensor; enqueue it on first use of a buffer.
+ * rows that differ to *violations (an int32 in device memory; the Python boundary copies it to pinned host memory on the
+ * same stream and polls it on its next call, so nothing synchronises).  One streaming pass over the tensor.
  * ---------------------------------------------------------------------------------------------- */
 int pd_x_constant_check(const void* data, int32_t dtype /* pd_mask_dtype: PD_MASK_F32 | PD_MASK_U8 */, const pd_strides4* strides,
                         int32_t B, int32_t N, int32_t H, int32_t W, int32_t* violations, pd_stream_t stream);

@@ -17,8 +17,8 @@ detached copies for inspection; no live reference code path consumes them — ``
 is broken upstream).  ``outputs[("rgb_rec", side)]`` is always produced and is
 differentiable (``log_img`` and the perceptual term read it).
 
-What stays PyTorch (out of scope): the perceptual network, the smoothness term, the
-self-distillation |disp - disp_pp| term and the tiny 3x3 pose / homography algebra.
+What stays PyTorch (out of scope): the perceptual network's convolutions (scheduled by
+``perceptual.py``), the self-distillation |disp - disp_pp| term and the tiny 3x3 pose / homography algebra.
 """
 from __future__ import annotations
 
@@ -119,13 +119,74 @@ class HotPathMixin:
     #: expand of depth_decoder.py:156): a dense disparity takes the per-pixel kernels, a dense mask is streamed next to
     #: the logits (the forward pass keeps a row summary so that the backward pass can leave all-ones rows in HBM).
     disp_rowwise: bool = False
+    #: How the ``disp_rowwise`` promise is verified (pd_x_constant_check: one streaming pass that compares every element with
+    #: column 0 of its row, asynchronous, no host synchronisation): "first" = the first ``verify_rowwise_calls`` uses of
+    #: each (shape, strides, dtype) — the promise is a property of the decoder's construction, not of the data —
+    #: "always" = every call (+N*X1 of reads per tensor), "never" = trust.  A violation raises
+    #: ``PlaneDepthLibraryError`` (PD_ERR_ARG) from the next call into the boundary, or from ``check_promises()``.
+    verify_rowwise: str = "first"
+    verify_rowwise_calls: int = 2
+    #: compute_losses: the reference raises when ``pc_net`` or ``outputs["disp"]`` is missing (trainer.py:746, 768); so does
+    #: this mixin unless the carrier opts out explicitly (tests / bench time the photometric path alone)
+    skip_missing_terms: bool = False
     #: photometric term: None = reference behaviour (mixture NLL if opt.use_mixture_loss else L1);
     #: "ssim_l1" = 0.85*SSIM + 0.15*L1 (compute_reprojection_loss, trainer.py:687-699) on the novel view
     photometric: Optional[str] = None
 
     # ------------------------------------------------------------------------------------------
+    def _promise_state(self):
+        st = self.__dict__.get("_pd_promise_state")
+        if st is None:
+            st = self.__dict__["_pd_promise_state"] = {"seen": {}, "dev": None, "host": None, "what": []}
+        return st
+
+    def check_promises(self, synchronize: bool = True) -> None:
+        """Raise if an earlier asynchronous verification of the ``disp_rowwise`` promise found x-varying plane geometry.
+        ``synchronize=False`` only looks at results that have already arrived (what every boundary call does on entry)."""
+        st = self._promise_state()
+        if st["host"] is None:
+            return
+        if synchronize:
+            torch.cuda.synchronize()
+        n = int(st["host"][0])
+        if n:
+            raise L.PlaneDepthLibraryError(
+                "disp_rowwise promise violated (pd_status %d PD_ERR_ARG): %d row(s) of %s vary along x; unset disp_rowwise "
+                "(yz planes / per-pixel disparities take the per-pixel kernels)" % (1, n, " / ".join(sorted(set(st["what"])))))
+
+    def _verify_x_constant(self, t: torch.Tensor, what: str) -> None:
+        """Enqueue pd_x_constant_check for a dense tensor the caller promised to be x-constant (policy: verify_rowwise)."""
+        import ctypes as C
+
+        from .functional import _stream, _strides4
+
+        mode = self.verify_rowwise
+        if mode == "never" or not t.is_cuda:
+            return
+        st = self._promise_state()
+        key = (what, tuple(t.shape), tuple(t.stride()), t.dtype)
+        count = st["seen"].get(key, 0)
+        if mode != "always" and (count >= self.verify_rowwise_calls or torch.cuda.is_current_stream_capturing()):
+            return
+        st["seen"][key] = count + 1
+        if st["dev"] is None or st["dev"].device != t.device:
+            st["dev"] = torch.zeros(1, dtype=torch.int32, device=t.device)
+            st["host"] = torch.zeros(1, dtype=torch.int32).pin_memory()
+        td = t.detach()
+        if td.dtype == torch.bool:
+            td = td.view(torch.uint8)
+        elif td.dtype not in (torch.float32, torch.uint8):
+            td = td.float()
+        dtype = L.PD_MASK_F32 if td.dtype == torch.float32 else L.PD_MASK_U8
+        B, N, H, W = td.shape
+        strides = _strides4(td)
+        L.check(L.lib().pd_x_constant_check(td.data_ptr(), dtype, C.byref(strides), B, N, H, W, st["dev"].data_ptr(), _stream()), "pd_x_constant_check")
+        st["host"].copy_(st["dev"], non_blocking=True)
+        st["what"].append(what)
+
     def pred_novel_images(self, inputs: Dict, outputs: Dict) -> None:
         opt = self.opt
+        self.check_promises(synchronize=False)
         B, N, H, W = outputs["probability"].shape
         color = "color_aug" if _flag(opt, "match_aug", False) else "color"
         src = inputs[(color, "l")]
@@ -144,8 +205,10 @@ class HotPathMixin:
                 mask = outputs["padding_mask"]
                 sign = 1.0 if side == "r" else (-1.0 if side == "l" else 0.0)
                 if self.disp_rowwise and disp.dim() == 4 and disp.stride(3) != 0 and disp.shape[3] > 1:
+                    self._verify_x_constant(disp, "disp_layered")
                     disp = rowwise_view(disp)
                 if self.disp_rowwise and torch.is_tensor(mask) and mask.dim() == 4 and mask.stride(3) != 0 and mask.shape[3] > 1:
+                    self._verify_x_constant(mask, "padding_mask")
                     mask = mask.detach()[..., :1].expand(-1, -1, -1, mask.shape[3])  # zero x stride: one value per row
             elif wt == "homography_warp":
                 hmat, cam = homography_params(outputs["distance"], outputs["norm"], outputs[("Rt", side)], inputs["K"], inputs["inv_K"])
@@ -199,6 +262,12 @@ class HotPathMixin:
         if mode == L.PD_LOSS_MIXTURE and not _flag(opt, "use_mixture_loss", False):
             raise ValueError("photometric='mixture' needs opt.use_mixture_loss (sigma channel)")
         pc_net = getattr(self, "pc_net", None)
+        if not self.skip_missing_terms:
+            if pc_net is None:
+                raise AttributeError("compute_losses: self.pc_net is missing (trainer.py:746 always evaluates the perceptual term); "
+                                     "set skip_missing_terms=True to time the photometric path alone")
+            if "disp" not in outputs:
+                raise KeyError("disp")  # trainer.py:768 reads outputs["disp"] unconditionally
         # trainer.py:717-766 accumulates into zero-initialised entries and divides every entry by len(target_sides)
         # in place; the same values are formed here without the no-op kernels (0 + x, x / 1): at B200 speeds each
         # tiny elementwise launch costs as much as 1 % of the whole step
@@ -247,7 +316,9 @@ class HotPathMixin:
         batch ``cat([img, img.flip(-1)])`` (``probability``, ``logits``, ``disp_layered``, ``disp``).  Returns
         ``(disp_pp, mask_novel)``, both detached, like the reference."""
         disp_layered = outputs["disp_layered"]
+        self.check_promises(synchronize=False)
         if self.disp_rowwise and disp_layered.dim() == 4 and disp_layered.stride(3) != 0 and disp_layered.shape[3] > 1:
+            self._verify_x_constant(disp_layered, "disp_layered")
             disp_layered = disp_layered.detach()[..., :1].expand(-1, -1, -1, disp_layered.shape[3])
         disp_pp, mask_novel, _, _ = occlusion_masks(outputs["logits"], outputs["probability"], disp_layered, outputs["disp"],
                                                     exact_coords=bool(self.exact_coords))
@@ -301,7 +372,7 @@ class HotPath(HotPathMixin):
     and smoke() instantiate instead of the full Trainer, whose constructor needs NCCL + KITTI)."""
 
     def __init__(self, opt, target_sides=None, pc_net=None, photometric: Optional[str] = None, materialize_layered: bool = False,
-                 exact_coords: bool = False, disp_rowwise: bool = False):
+                 exact_coords: bool = False, disp_rowwise: bool = False, verify_rowwise: str = "first", skip_missing_terms: bool = True):
         self.opt = opt
         if target_sides is None:
             target_sides = ([] if _flag(opt, "no_stereo", False) else ["r"]) + list(_flag(opt, "novel_frame_ids", []))
@@ -311,6 +382,8 @@ class HotPath(HotPathMixin):
         self.materialize_layered = materialize_layered
         self.exact_coords = exact_coords
         self.disp_rowwise = disp_rowwise
+        self.verify_rowwise = verify_rowwise
+        self.skip_missing_terms = skip_missing_terms
 
     def process(self, inputs, outputs):
         self.pred_novel_images(inputs, outputs)

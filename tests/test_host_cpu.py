@@ -87,3 +87,28 @@ def test_homography_params_match_the_reference_formula():
     vv = (q[:, 1] / q[:, 2].clamp_min(1e-7)).reshape(B, N, H, W)
     sane = u.abs() < 1e4
     assert torch.allclose(uu[sane], u[sane], rtol=1e-4, atol=2e-3) and torch.allclose(vv[sane], v[sane], rtol=1e-4, atol=2e-3)
+
+
+def test_compute_losses_raises_on_missing_terms_like_the_reference():
+    """ADVICE r1: a mis-wired integration (no pc_net, no outputs["disp"]) must not silently train on a different total loss;
+    the stand-alone HotPath carrier opts out explicitly."""
+    from types import SimpleNamespace
+
+    import pytest
+    import torch
+
+    from planedepth_b200.boundary import HotPath, HotPathMixin
+
+    class Carrier(HotPathMixin):
+        pass
+
+    c = Carrier()
+    c.opt = SimpleNamespace(warp_type="disp_warp")
+    c.target_sides = ["r"]
+    outputs = {"probability": torch.zeros(1, 2, 4, 8)}
+    with pytest.raises(AttributeError, match="pc_net"):
+        c.compute_losses({}, outputs)
+    c.pc_net = lambda x: [x, x, x]
+    with pytest.raises(KeyError, match="disp"):
+        c.compute_losses({}, outputs)
+    assert HotPath(c.opt, ["r"]).skip_missing_terms is True and HotPathMixin.skip_missing_terms is False
