@@ -16,6 +16,36 @@ from . import _lib as L
 #: when set to a list, every C-ABI call appends (name, start_event, end_event) recorded on the launch stream
 KERNEL_TIMELINE = None
 
+#: Fold pd_photometric_bwd into the prologue of pd_warp_composite_bwd (pd_warp_grad_out's fused form): the photometric
+#: node's backward hands its operands (d loss / d ph_sum, the unit gradient saved by the forward, the perceptual term's
+#: gradient) to the warp node that produced its input instead of launching a kernel and writing g_rgb_rec to HBM.
+FUSE_PHOTOMETRIC_BWD = True
+
+
+class _Link:
+    """Side channel between the autograd node that produced ``rgb_rec`` (_WarpComposite) and the photometric node that
+    consumes it: autograd runs the consumer's backward first; it parks its operands here."""
+
+    __slots__ = ("pending",)
+
+    def __init__(self):
+        self.pending = None
+
+
+_PLACEHOLDER = {}
+
+
+def _placeholder(shape, device):
+    """Stride-0 zero standing in for a gradient whose value travels through a _Link (no kernel, no memory)."""
+    z = _PLACEHOLDER.get(device)
+    if z is None:
+        z = _PLACEHOLDER[device] = torch.zeros((), device=device)
+    return z.expand(shape)
+
+
+def _is_placeholder(g) -> bool:
+    return g is not None and g.numel() > 1 and all(st == 0 for st in g.stride())
+
 
 def _call(name, fn, *args):
     """Invoke one C-ABI entry point, optionally bracketed by CUDA events on the current stream."""
@@ -88,8 +118,9 @@ class _WarpComposite(torch.autograd.Function):
     """pd_warp_composite_fwd / _bwd: trainer.py:533-603 for one target side."""
 
     @staticmethod
-    def forward(ctx, cfg: WarpConfig, src, tgt, logits, sigma, disp, mask, hmat, cam):
+    def forward(ctx, cfg: WarpConfig, link, src, tgt, logits, sigma, disp, mask, hmat, cam):
         lib = L.lib()
+        ctx.link = link
         B, N, H, W = cfg.shape
         dev = logits.device
         desc = L.WarpDesc(B=B, N=N, H=H, W=W, warp_type=cfg.warp_type, mixture=int(cfg.mixture), automask=int(cfg.automask),
@@ -145,8 +176,17 @@ class _WarpComposite(torch.autograd.Function):
         B, N, H, W = cfg.shape
         src, tgt, logits, sigma, disp, mask, hmat, cam, rgb_rec, stats = ctx.saved_tensors
         dev = logits.device
-        need = ctx.needs_input_grad  # (cfg, src, tgt, logits, sigma, disp, mask, hmat, cam)
-        g_rgb = torch.zeros_like(rgb_rec) if g_rgb is None else _f32c(g_rgb, "grad rgb_rec")
+        need = ctx.needs_input_grad[1:]  # (cfg, src, tgt, logits, sigma, disp, mask, hmat, cam)
+        fused = ctx.link.pending if ctx.link is not None else None
+        if ctx.link is not None:
+            ctx.link.pending = None
+        if fused is not None:
+            # the photometric node parked its operands: placeholders carry no value, anything else is a genuine extra gradient
+            g_rgb = None if (g_rgb is None or _is_placeholder(g_rgb)) else _f32c(g_rgb, "grad rgb_rec")
+            if g_nll is not None and (_is_placeholder(g_nll) or not g_nll.numel()):
+                g_nll = None
+        else:
+            g_rgb = torch.zeros_like(rgb_rec) if g_rgb is None else _f32c(g_rgb, "grad rgb_rec")
         if cfg.mixture and g_nll is not None and g_nll.numel():
             g_nll = _f32c(g_nll, "grad nll")
         else:
@@ -155,6 +195,10 @@ class _WarpComposite(torch.autograd.Function):
                        hmat=_ptr(hmat), cam=_ptr(cam))
         saved = L.WarpOut(rgb_rec=_ptr(rgb_rec), stats=_ptr(stats))
         gout = L.WarpGradOut(g_rgb_rec=_ptr(g_rgb), g_nll=_ptr(g_nll))
+        if fused is not None:
+            gout.g_ph_sum, gout.ph_scale = _ptr(fused["g_ph_sum"]), float(fused["ph_scale"])
+            gout.g_unit, gout.g_unit_nll = _ptr(fused["g_unit"]), _ptr(fused["g_unit_nll"])
+            gout.g_pred, gout.mask_novel = _ptr(fused["g_pred"]), _ptr(fused["mask_novel"])
         g_logits = torch.empty_like(logits) if need[3] else None
         g_sigma = torch.empty_like(sigma) if (cfg.mixture and sigma is not None and need[4]) else None
         g_disp = g_hmat = None
@@ -180,7 +224,7 @@ class _WarpComposite(torch.autograd.Function):
             g_hmat = torch.cat([g9, torch.zeros(B * N, 3, device=dev)], 1)
         if g_disp is not None and tuple(g_disp.shape) != tuple(disp.shape):
             g_disp = (g_disp / spread if spread > 1 else g_disp).expand(disp.shape)
-        return (None, None, None, g_logits, g_sigma, g_disp, None, g_hmat, None)
+        return (None, None, None, None, g_logits, g_sigma, g_disp, None, g_hmat, None)
 
 
 def warp_composite(cfg: WarpConfig, src, tgt, logits, sigma=None, disp=None, mask=None, hmat=None, cam=None):
@@ -205,8 +249,13 @@ def warp_composite(cfg: WarpConfig, src, tgt, logits, sigma=None, disp=None, mas
         hmat = _f32c(hmat, "hmat")
     if cam is not None:
         cam = _f32c(cam, "cam").detach()
-    outs = _WarpComposite.apply(cfg, src.detach(), None if tgt is None else tgt.detach(), logits, sigma, disp, mask, hmat, cam)
+    link = _Link()
+    outs = _WarpComposite.apply(cfg, link, src.detach(), None if tgt is None else tgt.detach(), logits, sigma, disp, mask, hmat, cam)
     rgb_rec, nll, nll_auto = outs[:3]
+    # photometric_loss() finds the producer through these attributes (the dict contract hands the same objects over)
+    rgb_rec._pd_link = link
+    if cfg.mixture:
+        nll._pd_link = link
     layered = None
     if cfg.layered:
         names = ["rgb_rec_layered", "logit_rec", "probability_rec"] + (["sigma_rec", "pi_rec"] if cfg.mixture else [])
@@ -220,8 +269,10 @@ class _Photometric(torch.autograd.Function):
     is a streaming scale-and-add."""
 
     @staticmethod
-    def forward(ctx, mode: int, automask: bool, want_map: bool, scale: float, rgb_rec, tgt, src, mask_novel, nll, nll_auto):
+    def forward(ctx, mode: int, automask: bool, want_map: bool, scale: float, link, rgb_rec, tgt, src, mask_novel, nll, nll_auto):
         lib = L.lib()
+        ctx.link = link
+        ctx.scale = float(scale)
         B, _, H, W = rgb_rec.shape
         dev = rgb_rec.device
         mixture = mode == L.PD_LOSS_MIXTURE
@@ -242,7 +293,12 @@ class _Photometric(torch.autograd.Function):
         ctx.mixture = mixture
         ctx.shape = (B, H, W)
         ctx.save_for_backward(mask_novel, g_unit, g_unit_nll)
-        outs = (ph_sum, pred if pred is not None else torch.empty(0, device=dev), ph_map if ph_map is not None else torch.empty(0, device=dev))
+        if pred is None:
+            # without the mask_novel blend pred IS rgb_rec; with a link it is still handed out as an output of this node (an
+            # alias, no copy) so that the perceptual term's gradient arrives here and rgb_rec keeps a single consumer
+            pred = rgb_rec.detach() if link is not None else torch.empty(0, device=dev)
+            ctx.has_pred = link is not None
+        outs = (ph_sum, pred, ph_map if ph_map is not None else torch.empty(0, device=dev))
         ctx.mark_non_differentiable(outs[2])
         return outs
 
@@ -254,6 +310,12 @@ class _Photometric(torch.autograd.Function):
         dev = (g_unit if g_unit is not None else g_unit_nll).device
         g_sum = torch.zeros((), device=dev) if g_sum is None else _f32c(g_sum, "grad ph_sum")
         g_pred = _f32c(g_pred, "grad pred") if (ctx.has_pred and g_pred is not None) else None
+        if ctx.link is not None:
+            # fused: the warp node's backward kernel forms g_ph_sum * unit + g_pred * mask_novel in its prologue
+            ctx.link.pending = {"g_ph_sum": g_sum, "ph_scale": ctx.scale, "g_unit": g_unit, "g_unit_nll": g_unit_nll, "g_pred": g_pred,
+                                "mask_novel": mask_novel}
+            return (None, None, None, None, None, _placeholder((B, 3, H, W), dev), None, None, None,
+                    _placeholder((B, 1, H, W), dev) if ctx.mixture else None, None)
         tin = L.LossIn(mask_novel=_ptr(mask_novel))
         saved = L.LossOut(g_unit=_ptr(g_unit), g_unit_nll=_ptr(g_unit_nll))
         g_rgb = torch.empty(B, 3, H, W, device=dev, dtype=torch.float32)
@@ -262,7 +324,7 @@ class _Photometric(torch.autograd.Function):
         gin = L.LossGradIn(g_rgb_rec=_ptr(g_rgb), g_nll=_ptr(g_nll))
         _call("pd_photometric_bwd", lib.pd_photometric_bwd, C.byref(ctx.desc), C.byref(tin), C.byref(saved), C.byref(gout), C.byref(gin), None,
               _stream())
-        return (None, None, None, None, g_rgb, None, None, None, g_nll, None)
+        return (None, None, None, None, None, g_rgb, None, None, None, g_nll, None)
 
 
 def photometric_loss(mode: int, automask: bool, rgb_rec, tgt, src=None, mask_novel=None, nll=None, nll_auto=None, want_map=False,
@@ -279,8 +341,12 @@ def photometric_loss(mode: int, automask: bool, rgb_rec, tgt, src=None, mask_nov
         nll_auto = _f32c(nll_auto, "nll_auto").detach() if automask else None
     else:
         nll = nll_auto = None
-    ph_sum, pred, ph_map = _Photometric.apply(mode, automask, want_map, float(scale), rgb_rec, tgt, src, mask_novel, nll, nll_auto)
-    return ph_sum, (pred if mask_novel is not None else rgb_rec), (ph_map if want_map else None)
+    # fuse with the producing warp node when rgb_rec (and, in mixture mode, nll) come straight from it
+    link = getattr(rgb_rec, "_pd_link", None) if FUSE_PHOTOMETRIC_BWD else None
+    if link is not None and mode == L.PD_LOSS_MIXTURE and getattr(nll, "_pd_link", None) is not link:
+        link = None
+    ph_sum, pred, ph_map = _Photometric.apply(mode, automask, want_map, float(scale), link, rgb_rec, tgt, src, mask_novel, nll, nll_auto)
+    return ph_sum, (pred if (mask_novel is not None or link is not None) else rgb_rec), (ph_map if want_map else None)
 
 
 def occlusion_masks(logits, probability, disp_layered, disp, exact_coords: bool = False):

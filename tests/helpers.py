@@ -114,23 +114,27 @@ def error_stats(got, want, atol):
     err = np.abs(g - w)
     bad = err > atol
     st = {"max_err": float(err.max()) if err.size else 0.0, "atol": float(atol), "frac_bad": float(bad.mean()) if err.size else 0.0,
-          "n": int(err.size), "worst_row_frac": 0.0}
-    if err.ndim >= 2 and err.shape[-1] >= 8 and bad.any():
-        st["worst_row_frac"] = float(bad.reshape(-1, err.shape[-1]).mean(1).max())
+          "n": int(err.size), "worst_row_frac": 0.0, "worst_col_frac": 0.0, "finite": bool(np.isfinite(g).all())}
+    if err.ndim >= 2 and err.shape[-1] >= 8 and err.shape[-2] >= 8 and bad.any():
+        b3 = bad.reshape(-1, err.shape[-2], err.shape[-1])
+        st["worst_row_frac"] = float(b3.mean(2).max())
+        st["worst_col_frac"] = float(b3.mean(1).max())
     return st
 
 
-def bounded_check(got, want, atol, what, allow_frac=0.0, cap=100.0, row_frac=0.5):
-    """|got - want| <= atol except for a fraction `allow_frac` of knife-edge elements (clamp / min / floor decisions that flip
-    under 1-ulp CPU-GPU differences).  The exempt elements are bounded as well: none may be off by more than cap * atol
-    (1e-2 of the scale at the 1e-4 gate), and they may not fill more than `row_frac` of any row — a wrong row or column
-    of a large tensor stays below any fraction gate, a border / pad bug does not stay below these two."""
+def bounded_check(got, want, atol, what, allow_frac=0.0, cap=100.0, line_frac=0.5):
+    """|got - want| <= atol except for a fraction `allow_frac` of knife-edge elements (|x| sign kinks, clamp / min / floor
+    decisions that flip under rounding-level differences).  The exemptions are bounded too: no element may be off by more
+    than cap * atol, and the exempt elements may not fill more than `line_frac` of any image row or column — a wrong row
+    or column of a large tensor stays below any fraction gate, a border / pad / ring-phase bug does not stay below these."""
     st = error_stats(got, want, atol)
     if os.environ.get("PD_TEST_REPORT"):
         REPORT.append((what, st))
         return st
+    assert st["finite"], "%s: non-finite values" % what
     assert st["frac_bad"] <= allow_frac, "%s: %.3g of %d elements off by more than %.1e (max err %.3e)" % (
         what, st["frac_bad"], st["n"], atol, st["max_err"])
     assert st["max_err"] <= cap * atol, "%s: an exempt element is off by %.3e > %g x tolerance %.1e" % (what, st["max_err"], cap, atol)
-    assert st["worst_row_frac"] <= row_frac, "%s: %.0f%% of one row is beyond tolerance" % (what, 100 * st["worst_row_frac"])
+    assert st["worst_row_frac"] <= line_frac, "%s: %.0f%% of one row is beyond tolerance" % (what, 100 * st["worst_row_frac"])
+    assert st["worst_col_frac"] <= line_frac, "%s: %.0f%% of one column is beyond tolerance" % (what, 100 * st["worst_col_frac"])
     return st

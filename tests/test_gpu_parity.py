@@ -263,6 +263,48 @@ def test_rowwise_promise_on_dense_cat_layout(idx, mode):
         check(cg.leaves[k].grad, leaf.grad, grad_tol(k) * scale, "grad_" + k, allow_frac=2e-3)
 
 
+@pytest.mark.parametrize("idx", [0, 1, 2, 5, 7, 15])
+def test_unfused_photometric_backward_matches_oracle(idx):
+    """The default path folds pd_photometric_bwd into the warp backward's prologue (pd_warp_grad_out's fused form); the
+    stand-alone entry point stays part of the ABI and must give the same gradients."""
+    from planedepth_b200 import functional
+
+    cfg = CONFIGS[idx]
+    cc = build_on("cpu", cfg, seed=700 + idx)
+    cg = build_on("cuda", cfg, seed=700 + idx)
+    lo = O.hot_path(cc.opt, cc.target_sides, cc.inputs, cc.outputs, pyramid_features)
+    lo["loss/total_loss"].backward()
+    functional.FUSE_PHOTOMETRIC_BWD = False
+    try:
+        functional.KERNEL_TIMELINE = []
+        lg = run_cuda(cg, None, "fused")
+        names = [n for n, _, _ in functional.KERNEL_TIMELINE]
+    finally:
+        functional.FUSE_PHOTOMETRIC_BWD = True
+        functional.KERNEL_TIMELINE = None
+    assert "pd_photometric_bwd" in names
+    for k in lo:
+        check(lg[k], lo[k], TOL, k)
+    for k, leaf in cc.leaves.items():
+        if leaf.grad is None:
+            continue
+        scale = float(leaf.grad.abs().max()) + 1e-12
+        check(cg.leaves[k].grad, leaf.grad, grad_tol(k) * scale, "grad_" + k, allow_frac=2e-3)
+    # ... and the fused default launches no photometric backward kernel
+    cg2 = build_on("cuda", cfg, seed=700 + idx)
+    functional.KERNEL_TIMELINE = []
+    try:
+        run_cuda(cg2, None, "fused")
+        names = [n for n, _, _ in functional.KERNEL_TIMELINE]
+    finally:
+        functional.KERNEL_TIMELINE = None
+    assert "pd_photometric_bwd" not in names and "pd_warp_composite_bwd" in names
+    for k, leaf in cg.leaves.items():
+        if leaf.grad is not None:
+            scale = float(leaf.grad.abs().max()) + 1e-12
+            check(cg2.leaves[k].grad, leaf.grad, 1e-5 * scale, "fused vs unfused grad_" + k, allow_frac=1e-4)
+
+
 def test_rowwise_promise_is_verified_not_trusted():
     """x-varying plane geometry handed over WITH the promise must not silently read column 0.  The
     asynchronous pd_x_constant_check flags it; the next boundary call (or check_promises()) raises PD_ERR_ARG."""
