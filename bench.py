@@ -173,38 +173,15 @@ def algorithmic_bytes(B, N, H, W, mixture):
 # --------------------------------------------------------------------------------------------------
 # reference / CPU arm
 # --------------------------------------------------------------------------------------------------
-def load_reference():
-    """The unmodified reference through an import shim, if baseline/_ref travelled with the snapshot."""
-    ref = os.path.join(ROOT, "baseline", "_ref")
-    if not os.path.exists(os.path.join(ref, "trainer.py")):
-        return None
+def load_reference(cpu_only=True):
+    """The unmodified reference through the import shim (baseline/shim.py), if baseline/_ref travelled with the snapshot.
+    Returns (trainer module, layers module) or None."""
     try:
-        import types
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import shim
 
-        import torch.nn as nn
-
-        for name in ["tensorboardX", "IPython", "skimage", "skimage.transform", "matplotlib"]:
-            sys.modules.setdefault(name, types.ModuleType(name))
-        sys.modules["tensorboardX"].SummaryWriter = object
-        sys.modules["IPython"].embed = lambda *a, **k: None
-        sys.modules["matplotlib"].scale = None
-        sys.modules["skimage"].transform = sys.modules["skimage.transform"]
-        six = types.ModuleType("torch._six")
-        six.string_classes = (str, bytes)
-        sys.modules["torch._six"] = six
-        torch._six = six
-        # the reference calls .cuda() on helper tensors; this arm is the CPU path
-        torch.Tensor.cuda = lambda self, *a, **k: self
-        nn.Module.cuda = lambda self, *a, **k: self
-        import PIL.Image
-
-        if not hasattr(PIL.Image, "ANTIALIAS"):
-            PIL.Image.ANTIALIAS = PIL.Image.LANCZOS
-        sys.path.insert(0, ref)
-        import layers as ref_layers
-        import trainer as ref_trainer
-
-        return ref_trainer, ref_layers
+        mods = shim.load(cpu_only=cpu_only)
+        return None if mods is None else (mods[0], mods[1])
     except Exception as e:  # pragma: no cover
         sys.stderr.write("reference import failed (%s); using the oracle port\n" % e)
         return None
@@ -318,186 +295,379 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if ws > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION/INFO
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("PD_BENCH_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        # NCCL_DEBUG is left as the launcher set it (its INFO lines carry the rank / transport evidence); protect_stdout()
+        # keeps fd 1 to the one JSON line whatever NCCL prints
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = _lib.lib()
-    B, H, W, over, photometric, desc = CONFIGS[args.config]
-    opt = make_opt(**over)
-    mnov = opt.self_distillation > 0  # the SD stage hands over outputs["mask_novel"] (trainer.py:404-466)
-    opt.self_distillation = 0.0      # its |disp - disp_pp| term belongs to the decoder tail, not to this path
-    seed = D.shard_seed(1234, rank)
-    batch = make_batch(B, H, W, opt, seed=seed, device="cpu", layout=args.layout, mask_novel=mnov)
-    N = batch.shape[1]
+    if args.no_fuse_bwd:
+        functional.FUSE_PHOTOMETRIC_BWD = False
     dev = torch.device("cuda", local_rank)
-    # static device buffers: network outputs live on the device; the `inputs` dict comes from the host
-    host_inputs = {k: v.pin_memory() for k, v in batch.inputs.items()}
-    batch_gpu = make_batch(B, H, W, opt, seed=seed, device=dev, layout=args.layout, mask_novel=mnov)
-    outputs, leaves_map = batch_gpu.outputs, batch_gpu.leaves
-    inputs = batch_gpu.inputs
-    leaves = list(leaves_map.values())
-    # the integration patch promises x-constant disparities whenever the decoder has no yz planes
-    hp = HotPath(opt, batch.target_sides, pc_net=None, photometric=photometric, disp_rowwise=(getattr(opt, "yz_levels", 0) == 0) and not args.no_rowwise)
-    step = make_step(hp, inputs, outputs, leaves, batch_gpu.attach)
-    if args.no_graph:
-        class _Eager:
-            result = None
 
-            def replay(self):
-                self.result = step()
-                return self.result
+    def measure(cfg_name, steps, warmup, main):
+        B, H, W, over, photometric, desc = CONFIGS[cfg_name]
+        opt = make_opt(**over)
+        mnov = opt.self_distillation > 0  # the SD stage hands over outputs["mask_novel"] (trainer.py:404-466)
+        opt.self_distillation = 0.0      # its |disp - disp_pp| term belongs to the decoder tail, not to this path
+        seed = D.shard_seed(1234, rank)
+        batch = make_batch(B, H, W, opt, seed=seed, device="cpu", layout=args.layout, mask_novel=mnov)
+        N = batch.shape[1]
+        dev = torch.device("cuda", local_rank)
+        # static device buffers: network outputs live on the device; the `inputs` dict comes from the host
+        host_inputs = {k: v.pin_memory() for k, v in batch.inputs.items()}
+        batch_gpu = make_batch(B, H, W, opt, seed=seed, device=dev, layout=args.layout, mask_novel=mnov)
+        outputs, leaves_map = batch_gpu.outputs, batch_gpu.leaves
+        inputs = batch_gpu.inputs
+        leaves = list(leaves_map.values())
+        # the integration patch promises x-constant disparities whenever the decoder has no yz planes
+        hp = HotPath(opt, batch.target_sides, pc_net=None, photometric=photometric, disp_rowwise=(getattr(opt, "yz_levels", 0) == 0) and not args.no_rowwise)
+        step = make_step(hp, inputs, outputs, leaves, batch_gpu.attach)
+        if args.no_graph:
+            class _Eager:
+                result = None
 
-        graphed = _Eager()
-        graphed.replay()
-    else:
-        graphed = GraphedStep(step, warmup=3)
+                def replay(self):
+                    self.result = step()
+                    return self.result
 
-    def barrier():
-        D.barrier(ws, cuda=True)
+            graphed = _Eager()
+            graphed.replay()
+        else:
+            graphed = GraphedStep(step, warmup=3)
 
-    # ---------------- value: inputs resident in HBM, CUDA-graph replay -------------------------
-    for _ in range(args.warmup):
-        graphed.replay()
-    clocks = ClockSampler(local_rank)
-    barrier()
-    lib.pd_reset_launch_count()
-    probe = step()  # one eager step to count the library launches a step performs
-    launches_per_step = lib.pd_launch_count()
-    del probe
-    barrier()
+        def barrier():
+            D.barrier(ws, cuda=True)
+
+        # ---------------- value: inputs resident in HBM, CUDA-graph replay -------------------------
+        for _ in range(warmup):
+            graphed.replay()
+        clocks = ClockSampler(local_rank)
+        barrier()
+        lib.pd_reset_launch_count()
+        probe = step()  # one eager step to count the library launches a step performs
+        launches_per_step = lib.pd_launch_count()
+        del probe
+        barrier()
+        if rank == 0:
+            clocks.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            graphed.replay()
+        ev1.record()
+        if rank == 0:
+            clocks.sample_until(ev1)  # the queued steps are still running: these samples are under load
+        barrier()
+        ms_step = D.max_over_ranks(ev0.elapsed_time(ev1), ws, dev) / steps
+        loss_val = float(graphed.result["loss"].item())
+
+        # ---------------- e2e: the path's host-born inputs from pinned host memory each step ---------
+        # The tensors of the `inputs` dict this path reads (source + target colours; K / inv_K / Rt for the
+        # homography warp) start every step in pinned HOST memory, as they do when they come out of the data loader
+        # (trainer.py:328-329 copies them with .to(device)); logits / sigma / plane geometry are network outputs and are
+        # device-born in the reference too.  The H2D copy of step i+1 runs on a copy stream while step i computes
+        # (one staging set, events both ways); the loss comes back to the host every step.
+        color = "color"
+        read_keys = [(color, "l")] + [(color, sd) for sd in batch.target_sides]
+        if opt.warp_type != "disp_warp":
+            read_keys += ["K", "inv_K"] + [("Rt", sd) for sd in batch.target_sides]
+        read_keys = [k for k in dict.fromkeys(read_keys) if k in host_inputs]
+        host_sel = {k: host_inputs[k] for k in read_keys}
+        staging = {k: torch.empty_like(inputs[k]) for k in read_keys}
+        loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+        h2d = sum(v.numel() * v.element_size() for v in host_sel.values())
+        copy_stream = torch.cuda.Stream()
+        copied, consumed = torch.cuda.Event(), torch.cuda.Event()
+
+        def enqueue_h2d():
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed)
+                for k, v in host_sel.items():
+                    staging[k].copy_(v, non_blocking=True)
+                copied.record(copy_stream)
+
+        consumed.record()
+        enqueue_h2d()
+
+        def e2e_step():
+            main = torch.cuda.current_stream()
+            main.wait_event(copied)
+            for k in read_keys:
+                inputs[k].copy_(staging[k], non_blocking=True)
+            consumed.record(main)
+            enqueue_h2d()  # next step's inputs travel while this step computes
+            res = graphed.replay()
+            loss_host.copy_(res["loss"], non_blocking=True)
+            main.synchronize()
+            return float(loss_host)
+
+        for _ in range(warmup):
+            e2e_step()
+        barrier()
+        ev0.record()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            e2e_step()
+        ev1.record()
+        barrier()
+        e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
+        e2e_ms_step = D.max_over_ranks(e2e_ms, ws, dev) / steps
+        copy_stream.synchronize()
+        clk = clocks.stop() if rank == 0 else None
+
+        # ---------------- roofline: per-kernel CUDA events on the launch stream (eager pass) --------
+        functional.KERNEL_TIMELINE = []
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        functional.KERNEL_TIMELINE = []
+        n_roof = max(3, min(steps, 10))
+        for _ in range(n_roof):
+            step()
+        torch.cuda.synchronize()
+        per = {}
+        for name, s, e in functional.KERNEL_TIMELINE:
+            per.setdefault(name, []).append(s.elapsed_time(e))
+        functional.KERNEL_TIMELINE = None
+        avg_ms = {k: sum(v) / len(v) for k, v in per.items()}
+        dom = max(avg_ms, key=avg_ms.get)
+        alg = algorithmic_bytes(B, N, H, W, opt.use_mixture_loss)  # per launch (= per target side)
+        n_calls = {k: len(v) / n_roof for k, v in per.items()}  # launches per step
+        peak, peak_src = peaks()
+        achieved = alg[dom] / (avg_ms[dom] * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                key = cfg_name + ("_compact" if args.layout == "compact" else ("_nopromise" if args.no_rowwise else ""))
+                traffic = tj.get(key, {}).get(dom)
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "frac_of_spec_8TBs": achieved / 8000.0, "algorithmic_bytes": alg[dom], "kernel_ms": avg_ms[dom],
+                    "all_kernels_ms": avg_ms,
+                    "all_kernels_frac": {k: alg[k] / (avg_ms[k] * 1e-3) / 1e9 / peak for k in avg_ms},
+                    "launches_per_step": n_calls,
+                    "step_frac": sum(alg[k] * n_calls.get(k, 0) for k in alg) / (ms_step * 1e-3) / 1e9 / peak}
+
+        e2e_scope = ("per step: H2D of the path's host-born inputs (%s) from pinned memory on a copy stream overlapped with the previous "
+                     "step, D2H of the loss; logits/sigma/plane geometry are network outputs (device-born)" % ", ".join(str(k) for k in read_keys))
+        if rank != 0:
+            return None
+        cpu = None
+        if ws == 1 and main and not args.no_cpu_baseline:
+            # bounded sample of the same workload on the host cores: ~10-20 s of CPU work (26 steps of B=4 images at ~0.35 s)
+            cpu, _ = time_cpu(cfg_name, min(B, 4), 24, 2)
+        return {
+            "metric": METRIC, "value": D.aggregate_throughput(B, ws, ms_step), "unit": UNIT, "n_gpus": ws, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * ws, "planes": N, "height": H, "width": W,
+                       "photometric": photometric or ("mixture" if opt.use_mixture_loss else "l1"), "layout": args.layout,
+                       "rowwise_promise": bool((getattr(opt, "yz_levels", 0) == 0) and not args.no_rowwise),
+                       "parallelism": "dp%d (independent shards; the path itself has no collective - see the ddp leg)" % ws,
+                       "launch": "eager" if args.no_graph else "cuda_graph replay",
+                       "l2": "no flush: per-step working set (logits %.0f MB + grads %.0f MB) exceeds the 126 MB L2" % (
+                           B * N * H * W * 4 / 1e6, B * N * H * W * 4 / 1e6),
+                       "e2e_scope": e2e_scope},
+            "e2e": {"value": D.aggregate_throughput(B, ws, e2e_ms_step), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms_step},
+            "gpu_launches": int(launches_per_step) * steps,
+            "gpu_launches_per_step": int(launches_per_step),
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "loss": loss_val,
+        }
+
+    line = measure(args.config, args.steps, args.warmup, main=True)
+    extras = {}
+    # the multi-GPU BASELINE configs on the GPU counts they are quoted on (configs[3]: 4 GPUs, configs[4]: 8 GPUs)
+    if ws == 4 and args.config == "cfg2":
+        extras["cfg4_dp4"] = brief(measure("cfg4", 30, 5, main=False))
+    if ws == 8 and args.config == "cfg2":
+        extras["cfg5_dp8"] = brief(measure("cfg5", 20, 5, main=False))
+    if not args.no_ddp_leg:
+        extras["ddp"] = ddp_leg(args, rank, local_rank, ws, dev)
+    if ws == 1 and not args.no_reference_gpu:
+        extras["reference_gpu"] = reference_gpu_leg(args.config)
     if rank == 0:
-        clocks.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        graphed.replay()
-    ev1.record()
-    if rank == 0:
-        clocks.sample_until(ev1)  # the queued steps are still running: these samples are under load
-    barrier()
-    ms_step = D.max_over_ranks(ev0.elapsed_time(ev1), ws, dev) / args.steps
-    loss_val = float(graphed.result["loss"].item())
-
-    # ---------------- e2e: the path's host-born inputs from pinned host memory each step ---------
-    # The tensors of the `inputs` dict this path reads (source + target colours; K / inv_K / Rt for the
-    # homography warp) start every step in pinned HOST memory, as they do when they come out of the data loader
-    # (trainer.py:328-329 copies them with .to(device)); logits / sigma / plane geometry are network outputs and are
-    # device-born in the reference too.  The H2D copy of step i+1 runs on a copy stream while step i computes
-    # (one staging set, events both ways); the loss comes back to the host every step.
-    color = "color"
-    read_keys = [(color, "l")] + [(color, sd) for sd in batch.target_sides]
-    if opt.warp_type != "disp_warp":
-        read_keys += ["K", "inv_K"] + [("Rt", sd) for sd in batch.target_sides]
-    read_keys = [k for k in dict.fromkeys(read_keys) if k in host_inputs]
-    host_sel = {k: host_inputs[k] for k in read_keys}
-    staging = {k: torch.empty_like(inputs[k]) for k in read_keys}
-    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-    h2d = sum(v.numel() * v.element_size() for v in host_sel.values())
-    copy_stream = torch.cuda.Stream()
-    copied, consumed = torch.cuda.Event(), torch.cuda.Event()
-
-    def enqueue_h2d():
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed)
-            for k, v in host_sel.items():
-                staging[k].copy_(v, non_blocking=True)
-            copied.record(copy_stream)
-
-    consumed.record()
-    enqueue_h2d()
-
-    def e2e_step():
-        main = torch.cuda.current_stream()
-        main.wait_event(copied)
-        for k in read_keys:
-            inputs[k].copy_(staging[k], non_blocking=True)
-        consumed.record(main)
-        enqueue_h2d()  # next step's inputs travel while this step computes
-        res = graphed.replay()
-        loss_host.copy_(res["loss"], non_blocking=True)
-        main.synchronize()
-        return float(loss_host)
-
-    for _ in range(args.warmup):
-        e2e_step()
-    barrier()
-    ev0.record()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    ev1.record()
-    barrier()
-    e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
-    e2e_ms_step = D.max_over_ranks(e2e_ms, ws, dev) / args.steps
-    copy_stream.synchronize()
-    clk = clocks.stop() if rank == 0 else None
-
-    # ---------------- roofline: per-kernel CUDA events on the launch stream (eager pass) --------
-    functional.KERNEL_TIMELINE = []
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
-    functional.KERNEL_TIMELINE = []
-    n_roof = max(3, min(args.steps, 10))
-    for _ in range(n_roof):
-        step()
-    torch.cuda.synchronize()
-    per = {}
-    for name, s, e in functional.KERNEL_TIMELINE:
-        per.setdefault(name, []).append(s.elapsed_time(e))
-    functional.KERNEL_TIMELINE = None
-    avg_ms = {k: sum(v) / len(v) for k, v in per.items()}
-    dom = max(avg_ms, key=avg_ms.get)
-    alg = algorithmic_bytes(B, N, H, W, opt.use_mixture_loss)  # per launch (= per target side)
-    n_calls = {k: len(v) / n_roof for k, v in per.items()}  # launches per step
-    peak, peak_src = peaks()
-    achieved = alg[dom] / (avg_ms[dom] * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            tj = json.load(open(tp))
-            key = args.config + ("_compact" if args.layout == "compact" else ("_nopromise" if args.no_rowwise else ""))
-            traffic = tj.get(key, {}).get(dom)
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "frac_of_spec_8TBs": achieved / 8000.0, "algorithmic_bytes": alg[dom], "kernel_ms": avg_ms[dom],
-                "all_kernels_ms": avg_ms,
-                "all_kernels_frac": {k: alg[k] / (avg_ms[k] * 1e-3) / 1e9 / peak for k in avg_ms},
-                "launches_per_step": n_calls,
-                "step_frac": sum(alg[k] * n_calls.get(k, 0) for k in alg) / (ms_step * 1e-3) / 1e9 / peak}
-
-    if rank != 0:
-        if ws > 1:
-            dist.destroy_process_group()
-        return
-    cpu = None
-    if ws == 1 and not args.no_cpu_baseline:
-        # bounded sample of the same workload on the host cores: ~10-20 s of CPU work (26 steps of B=4 images at ~0.35 s)
-        cpu, _ = time_cpu(args.config, min(B, 4), 24, 2)
-    line = {
-        "metric": METRIC, "value": D.aggregate_throughput(B, ws, ms_step), "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * ws, "planes": N, "height": H, "width": W,
-                   "photometric": photometric or ("mixture" if opt.use_mixture_loss else "l1"), "layout": args.layout,
-                   "rowwise_promise": bool((getattr(opt, "yz_levels", 0) == 0) and not args.no_rowwise),
-                   "parallelism": "dp%d (independent shards, no data-path collective)" % ws, "launch": "eager" if args.no_graph else "cuda_graph replay",
-                   "l2": "no flush: per-step working set (logits %.0f MB + grads %.0f MB) exceeds the 126 MB L2" % (
-                       B * N * H * W * 4 / 1e6, B * N * H * W * 4 / 1e6),
-                   "e2e_scope": "per step: H2D of the path's host-born inputs (%s) from pinned memory on a copy stream overlapped with the previous step, "
-                                "D2H of the loss; logits/sigma/plane geometry are network outputs (device-born)" % ", ".join(str(k) for k in read_keys)},
-        "e2e": {"value": D.aggregate_throughput(B, ws, e2e_ms_step), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": e2e_ms_step},
-        "gpu_launches": int(launches_per_step) * args.steps,
-        "gpu_launches_per_step": int(launches_per_step),
-        "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "loss": loss_val,
-    }
-    emit(line)
+        line.update(extras)
+        emit(line)
     if ws > 1:
         dist.destroy_process_group()
+
+
+def ddp_leg(args, rank, local_rank, ws, dev):
+    """The data-parallel TRAINING step north_star describes: a producer network (the reference's own seeded ResNet-18
+    encoder + DepthDecoder from baseline/_ref; a built-in convolutional head of the same gradient size when that tree did not
+    travel) feeds the hot path, its backward feeds DistributedDataParallel, whose bucketed NCCL all-reduce (sum / world
+    over NVLink) overlaps the remaining backward — the only cross-device traffic (no SyncBatchNorm).  cfg2 shape, eager
+    launches, device-timed, max over ranks.  At N = 1 the same step runs without the wrapper: the per-N values of this leg
+    are what a DDP scaling efficiency is computed from."""
+    import torch.distributed as dist
+    import torch.nn as nn
+
+    from planedepth_b200 import dist as D
+    from planedepth_b200.boundary import HotPath
+    from planedepth_b200.synthetic import make_batch, make_opt
+
+    B, H, W, over, photometric, desc = CONFIGS["cfg2"]
+    opt = make_opt(**over)
+    batch = make_batch(B, H, W, opt, seed=D.shard_seed(4321, rank), device=dev, requires_grad=False)
+    inputs = batch.inputs
+    N = batch.shape[1]
+    producer = None
+    kind = "builtin conv head"
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import shim
+
+        if shim.available() and shim.load() is not None:
+            ropt = shim.default_options(num_layers=18, height=H, width=W, xz_levels=0, novel_frame_ids=[])
+            models = shim.build_models(ropt, dev, seed=7)
+
+            class RefProducer(nn.Module):
+                def __init__(self):
+                    super().__init__()
+                    self.encoder, self.depth = models["encoder"], models["depth"]
+
+                def forward(self, img, grid):
+                    return self.depth(self.encoder(img), grid)
+
+            producer = RefProducer().to(dev)
+            kind = "reference ResnetEncoder(18) + DepthDecoder (baseline/_ref, seeded random weights)"
+    except Exception as e:  # pragma: no cover
+        sys.stderr.write("ddp leg: reference networks unavailable (%s); built-in head\n" % e)
+        producer = None
+    if producer is None:
+        torch.manual_seed(7)
+
+        class Head(nn.Module):
+            def __init__(self):
+                super().__init__()
+                ch = [3, 64, 128, 256, 512]
+                down = []
+                for i in range(4):
+                    down += [nn.Conv2d(ch[i], ch[i + 1], 3, 2, 1), nn.ELU(inplace=True)]
+                mid = []
+                for _ in range(5):
+                    mid += [nn.Conv2d(512, 512, 3, 1, 1), nn.ELU(inplace=True)]
+                self.down, self.mid = nn.Sequential(*down), nn.Sequential(*mid)
+                self.out = nn.Conv2d(512, N, 3, 1, 1)
+
+            def forward(self, img, grid):
+                x = self.out(self.mid(self.down(img)))
+                logits = nn.functional.interpolate(x, size=img.shape[-2:], mode="bilinear", align_corners=False)
+                return {"logits": logits, "probability": logits.detach(), "disp": logits[:, :1].abs() + 1.0}
+
+        producer = Head().to(dev)
+    n_params = sum(p.numel() for p in producer.parameters())
+    model = producer
+    if ws > 1:
+        model = nn.parallel.DistributedDataParallel(producer, device_ids=[local_rank], output_device=local_rank, gradient_as_bucket_view=True)
+    hp = HotPath(opt, batch.target_sides, pc_net=None, photometric=photometric, disp_rowwise=True)
+    params = [p for p in producer.parameters() if p.requires_grad]
+
+    def step():
+        out = model(inputs[("color_aug", "l")], inputs["grid"])
+        for k in ("disp_layered", "padding_mask", "distance", "norm"):
+            out.setdefault(k, batch.outputs[k])
+        out[("Rt", "r")] = inputs[("Rt", "r")]
+        losses = hp.process(inputs, out)
+        for p in params:
+            p.grad = None
+        losses["loss/total_loss"].backward()
+        return losses["loss/total_loss"].detach()
+
+    steps = max(5, min(args.steps, 30))
+    for _ in range(5):
+        step()
+    D.barrier(ws, cuda=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    D.barrier(ws, cuda=True)
+    ms = D.max_over_ranks(e0.elapsed_time(e1), ws, dev) / steps
+    return {"value": D.aggregate_throughput(B, ws, ms), "unit": UNIT, "ms_per_step": ms, "steps": steps, "n_gpus": ws, "producer": kind,
+            "parameters": n_params, "gradient_bytes_allreduced_per_step": (n_params * 4 if ws > 1 else 0),
+            "collective": ("DistributedDataParallel bucketed NCCL all-reduce, overlapped with backward" if ws > 1 else "none (N = 1)"),
+            "workload": "producer fwd + " + desc + " + producer bwd", "loss": float(loss)}
+
+
+def reference_gpu_leg(cfg_name):
+    """BASELINE.md row G, the denominator of north_star's '>= 10x the reference GPU grid_sample + SSIM path': the UNMODIFIED
+    reference code (baseline/_ref; F.grid_sample + autograd) doing the work of one bench step — pred_novel_images + the
+    photometric term, forward + backward — on the same synthetic batch on this GPU.  3 warm-up + 10 timed steps."""
+    import torch.nn as nn
+
+    from planedepth_b200.synthetic import make_batch, make_opt
+
+    ref = load_reference(cpu_only=False)
+    if ref is None:
+        return {"unavailable": "baseline/_ref did not travel with the snapshot"}
+    tr, layers = ref
+    from types import SimpleNamespace
+
+    B, H, W, over, photometric, desc = CONFIGS[cfg_name]
+    opt = make_opt(**over)
+    mnov = opt.self_distillation > 0
+    opt.self_distillation = 0.0
+    try:
+        batch = make_batch(B, H, W, opt, seed=1234, device="cuda", layout="reference", mask_novel=mnov)
+        leaves = list(batch.leaves.values())
+        t = object.__new__(tr.Trainer)
+        t.opt = SimpleNamespace(**vars(opt))
+        t.opt.use_ssim = photometric == "ssim_l1"
+        t.target_sides = batch.target_sides
+        t.softmax = nn.Softmax(1)
+        t.ssim = layers.SSIM().cuda()
+        t.homography_warp = layers.HomographyWarp(H, W)
+        t.backproject_depth = layers.BackprojectDepth(H, W)
+        t.project_3d = layers.Project3D(H, W)
+
+        def step():
+            out = batch.attach(dict(batch.outputs))
+            tr.Trainer.pred_novel_images(t, batch.inputs, out)
+            total = 0
+            for s in batch.target_sides:
+                if photometric == "ssim_l1":
+                    total = total + tr.Trainer.compute_reprojection_loss(t, out[("rgb_rec", s)], batch.inputs[("color", s)]).mean()
+                elif opt.use_mixture_loss:
+                    err = torch.abs(out[("rgb_rec_layered", s)] - batch.inputs[("color", s)][:, None]).mean(2)
+                    total = total + layers.multimodal_loss(err, out[("sigma_rec", s)], out[("pi_rec", s)], dist="lap").mean()
+                else:
+                    total = total + torch.abs(out[("rgb_rec", s)] - batch.inputs[("color", s)]).mean()
+            torch.autograd.grad(total, leaves, allow_unused=True)
+            return total
+
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            loss = step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 10
+        res = {"value": B / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "steps": 10, "warmup": 3, "loss": float(loss),
+               "what": "unmodified reference Trainer.pred_novel_images + photometric term (F.grid_sample, autograd), fwd+bwd, same batch, this GPU",
+               "warped_images_per_s": B * batch.shape[1] * len(batch.target_sides) / ms * 1e3}
+        del batch, leaves, t
+        torch.cuda.empty_cache()
+        return res
+    except Exception as e:  # pragma: no cover
+        return {"unavailable": "reference GPU run failed: %s" % (str(e)[:200],)}
+
+
+def brief(line):
+    if line is None:
+        return None
+    keep = ("value", "unit", "n_gpus", "ms_per_step", "steps", "e2e", "loss", "gpu_launches_per_step")
+    out = {k: line[k] for k in keep}
+    out["workload"] = line["config"]["workload"]
+    out["roofline_frac"] = line["roofline"]["frac"]
+    out["roofline_kernel"] = line["roofline"]["kernel"]
+    return out
 
 
 _JSON_FD = None
@@ -535,6 +705,9 @@ def main():
                     help="withhold the integrator's promise that plane geometry is x-constant (yz_levels == 0): dense masks are streamed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-fuse-bwd", action="store_true", help="keep pd_photometric_bwd as its own launch (diagnostic)")
+    ap.add_argument("--no-ddp-leg", action="store_true", help="skip the producer + DistributedDataParallel training-step leg")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip timing the unmodified reference on this GPU (N = 1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -1,4 +1,5 @@
 // Translation unit: TMA-streamed backward row kernels (pd_warp_stream.cuh, rows_bwd_stream instantiations).
+#define PD_TS_BWD_ONLY
 #include "pd_warp_stream.cuh"
 
 namespace pd {

@@ -1,4 +1,5 @@
 // Translation unit: TMA-streamed forward row kernels (pd_warp_stream.cuh, rows_fwd_stream instantiations).
+#define PD_TS_FWD_ONLY
 #include "pd_warp_stream.cuh"
 
 namespace pd {

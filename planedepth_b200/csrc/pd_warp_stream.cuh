@@ -30,13 +30,14 @@ namespace ts {
 constexpr int PAD = 12;  // zero floats on both sides of every shared-memory row (>= window size)
 
 struct __align__(16) PlaneCoef {
-    int k0;          // floor(sign * disparity), clamped so that x + k0 cannot overflow
+    // first 16 bytes: everything the backward's gather phase needs (one 128-bit broadcast load)
+    int k4;          // 4 * k0, k0 = floor(sign * disparity) clamped so that x + k0 cannot overflow: the shift in bytes
     float wc0, wc1;  // (1 - frac) * m, frac * m           (colour / sigma taps, gradient gather)
     float wl0;       // wc0 * log2(e)                       (logit taps, softmax in base 2)
     float wl1;       // wc1 * log2(e)
     float m;         // row mask value (1 when the mask is dense or absent)
-    int k4;          // k0 * 4: the shift in bytes
     float skip;      // SMASK_SUMMARY (backward): != 0 when the row summary says the mask row is all ones, so it is not read
+    int pad;
 };
 
 struct StreamCfg {
@@ -63,6 +64,9 @@ enum { SMASK_ROW = 0, SMASK_DENSE = 1, SMASK_SUMMARY = 2 };
 // mbarrier / TMA primitives (PTX; SASS: SYNCS / UBLKCP)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
+// suspend-time hint of mbarrier.try_wait: a waiting thread is parked by the hardware until the phase completes (or this many
+// ns pass) instead of spinning through try_wait / branch pairs that compete with the working warps for issue slots
+constexpr uint32_t kSuspendHintNs = 20000u;
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -81,11 +85,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(kSuspendHintNs)
         : "memory");
     return ok != 0;
 }
@@ -99,11 +103,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs)
         : "memory");
     return ok != 0;
 }
@@ -247,7 +251,8 @@ __device__ __forceinline__ void stage_coef(const WarpParams& p, const StreamCfg&
         const int r = idx / N, n = idx - r * N;
         const int row = g * c.rpc + r;
         PlaneCoef k;
-        k.k0 = W + 16, k.wc0 = k.wc1 = k.wl0 = k.wl1 = 0.0f, k.m = 0.0f, k.skip = 0.0f;
+        int k0 = W + 16;
+        k.wc0 = k.wc1 = k.wl0 = k.wl1 = 0.0f, k.m = 0.0f, k.skip = 0.0f, k.pad = 0;
         if (row < rows_total) {
             const int b = row / H, y = row - b * H;
             const float d = __ldg(p.in.disp + soff(p.d.disp_stride, b, n, y, 0));
@@ -260,14 +265,14 @@ __device__ __forceinline__ void stage_coef(const WarpParams& p, const StreamCfg&
                 // set bit n = some pixel of the plane's mask row differs from 1.0
                 if (!((__ldg(p.mask_rows + row) >> n) & 1ull)) k.skip = 1.0f;
             }
-            k.k0 = sane ? (int)kf : W + 16;
+            k0 = sane ? (int)kf : W + 16;
             k.m = m;
             k.wc1 = w1 * m;
             k.wc0 = (1.0f - w1) * m;
             k.wl0 = k.wc0 * kLog2e;
             k.wl1 = k.wc1 * kLog2e;
         }
-        k.k4 = k.k0 * 4;
+        k.k4 = k0 * 4;
         coef[idx] = k;
     }
 }
@@ -331,8 +336,13 @@ __device__ __forceinline__ PlaneCoef load_coef(uint32_t a32) {
     const float4 a = lds128(a32);
     const float4 b = lds128(a32 + 16);
     PlaneCoef k;
-    k.k0 = __float_as_int(a.x), k.wc0 = a.y, k.wc1 = a.z, k.wl0 = a.w, k.wl1 = b.x, k.m = b.y, k.k4 = __float_as_int(b.z), k.skip = b.w;
+    k.k4 = __float_as_int(a.x), k.wc0 = a.y, k.wc1 = a.z, k.wl0 = a.w, k.wl1 = b.x, k.m = b.y, k.skip = b.z, k.pad = 0;
     return k;
+}
+// the gather phase of the backward: shift and the two colour-domain weights only
+__device__ __forceinline__ void load_coef_gather(uint32_t a32, int& k4, float& wc0, float& wc1) {
+    const float4 a = lds128(a32);
+    k4 = __float_as_int(a.x), wc0 = a.y, wc1 = a.z;
 }
 
 // byte offset (multiple of 16, clamped into the zero pads) of the window holding the taps that start at byte
@@ -612,7 +622,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
 // ------------------------------------------------------------------------------------------------
 template <bool MIX, int PX>
 struct BwdCtx {
-    float g0[PX], g1[PX], g2[PX], Gbar[PX], Ml2[PX], invS[PX];
+    float g0[PX], g1[PX], g2[PX], nGbar[PX], Ml2[PX];  // nGbar = -sum_c g_c rgb_rec_c; Ml2 = reference logit * log2(e) + log2(sum exp)
     float tr[MIX ? PX : 1], tg[MIX ? PX : 1], tb[MIX ? PX : 1], Zinv[MIX ? PX : 1], gD[MIX ? PX : 1], gDD[MIX ? PX : 1];
 };
 
@@ -633,7 +643,7 @@ __device__ __forceinline__ float bwd_plane(uint32_t srow, uint32_t lrow, uint32_
         float t;
         if (PERPIX) t = fmaf(fmaf(k.wl0, v[R + i], k.wl1 * v[R + i + 1]), mm[i], -c.Ml2[i]);
         else t = fmaf(k.wl0, v[R + i], fmaf(k.wl1, v[R + i + 1], -c.Ml2[i]));
-        pi[i] = fast_exp2(t) * c.invS[i];
+        pi[i] = fast_exp2(t);  // softmax probability: 1 / S sits in the reference (Ml2 + log2 S)
         if (WANT_DISP) dlu[i] = v[R + i + 1] - v[R + i];
     }
     float cr[PX], cg[PX], cb[PX], dr[WANT_DISP ? PX : 1], dg[WANT_DISP ? PX : 1], db[WANT_DISP ? PX : 1];
@@ -657,13 +667,13 @@ __device__ __forceinline__ float bwd_plane(uint32_t srow, uint32_t lrow, uint32_
         cb[i] = fmaf(k.wc0, v[R + i], k.wc1 * v[R + i + 1]);
         if (PERPIX) cb[i] *= mm[i];
         if (WANT_DISP) db[i] = v[R + i + 1] - v[R + i];
-        Gn[i] = c.g0[i] * cr[i] + c.g1[i] * cg[i] + c.g2[i] * cb[i];
+        Gn[i] = fmaf(c.g0[i], cr[i], fmaf(c.g1[i], cg[i], fmaf(c.g2[i], cb[i], c.nGbar[i])));  // sum_c g_c colour_c - Gbar
     }
     float dl[PX], ds[MIX ? PX : 1];
     if constexpr (!MIX) {
 #pragma unroll
         for (int i = 0; i < PX; ++i) {
-            dl[i] = pi[i] * (Gn[i] - c.Gbar[i]);
+            dl[i] = pi[i] * Gn[i];
             if (WANT_DISP) gx[i] = fmaf(dl[i], dlu[i], pi[i] * (c.g0[i] * dr[i] + c.g1[i] * dg[i] + c.g2[i] * db[i]));
         }
     } else {
@@ -677,7 +687,7 @@ __device__ __forceinline__ float bwd_plane(uint32_t srow, uint32_t lrow, uint32_
             // with a = 1/sigma, w = pi a / Z (compositing weight), q = gD pi lap (the plane's share of dL/dD):
             //   dL/dlogit = w dG + q - pi gDD,  dL/dsigma = a (q a (err - sigma) - w dG),  dL/dcolour = w g -+ q a / 3
             const float w = pi[i] * inv * c.Zinv[i];
-            const float dG = Gn[i] - c.Gbar[i];
+            const float dG = Gn[i];
             const float err = (fabsf(cr[i] - c.tr[i]) + fabsf(cg[i] - c.tg[i]) + fabsf(cb[i] - c.tb[i])) * (1.0f / 3.0f);
             const float ea = err * inv;
             const float q = c.gD[i] * pi[i] * (0.5f * inv) * fast_exp2(-ea * kLog2e);
@@ -815,8 +825,8 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
             load_px_global<PX>(st + p.hw, Sv);
 #pragma unroll
             for (int i = 0; i < PX; ++i) {
-                c.Gbar[i] = c.g0[i] * ra[i] + c.g1[i] * rb[i] + c.g2[i] * rc[i];
-                c.invS[i] = 1.0f / Sv[i];
+                c.nGbar[i] = -(c.g0[i] * ra[i] + c.g1[i] * rb[i] + c.g2[i] * rc[i]);
+                c.Ml2[i] += log2f(Sv[i]);
             }
             if constexpr (MIX) {
                 const float* tp = p.in.tgt + (int64_t)b * p.chw3 + rem;
@@ -896,16 +906,18 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
                 uint32_t drow = dblk;
                 int64_t o = (((int64_t)b * N + n0) * H + y) * W + x0;
                 for (int q = 0; q < np; ++q, coef_a += (uint32_t)sizeof(PlaneCoef), drow += NE * rowpitch4, o += p.hw) {
-                    const PlaneCoef k = load_coef(coef_a);
+                    int k4;
+                    float wc0, wc1;
+                    load_coef_gather(coef_a, k4, wc0, wc1);
                     // with a dense mask the per-pixel mask is already folded into the exchange rows (k.m == 1)
-                    const int at4 = x04 - k.k4 - 4;
+                    const int at4 = x04 - k4 - 4;
                     float gg[PX];
                     if (p.gin.g_logits) {
-                        gather_any<PX>(drow, at4, W4, k.wc0, k.wc1, gg);
+                        gather_any<PX>(drow, at4, W4, wc0, wc1, gg);
                         store_px_stream<PX>(p.gin.g_logits + o, gg);
                     }
                     if constexpr (MIX) if (p.gin.g_sigma) {
-                        gather_any<PX>(drow + rowpitch4, at4, W4, k.wc0, k.wc1, gg);
+                        gather_any<PX>(drow + rowpitch4, at4, W4, wc0, wc1, gg);
                         store_px_stream<PX>(p.gin.g_sigma + o, gg);
                     }
                 }
@@ -965,9 +977,11 @@ inline StreamCfg stream_cfg(const WarpParams& p, bool mix, bool dense, int ne_bw
     c.pitch = p.d.W + 2 * PAD;
     c.nc = ((c.rpc * c.tpr + 31) / 32) * 32;
     const pd_tuning& tn = tuning();  // clamped when it was set: hs >= 1, 1 <= nst <= MAX_STAGES
-    c.hs = tn.stream_hs > 0 ? tn.stream_hs : 4;
+    // measured (profiles/r2c_*): the narrow plain backward prefers fewer, longer blocks (a consumer barrier per block)
+    const bool narrow_plain_bwd = ne_bwd > 0 && !mix && c.nc <= 160;
+    c.hs = tn.stream_hs > 0 ? tn.stream_hs : (narrow_plain_bwd ? 5 : 4);
     if (c.hs > p.d.N) c.hs = p.d.N;
-    c.nst = tn.stream_nst > 0 ? tn.stream_nst : 3;
+    c.nst = tn.stream_nst > 0 ? tn.stream_nst : (narrow_plain_bwd ? 2 : 3);
     if (c.nst > MAX_STAGES) c.nst = MAX_STAGES;
     // shrink the pipeline until the CTA fits the shared-memory budget (default: three CTAs per SM)
     // (three CTAs of <= 192 threads per SM, two of the 352-thread CTAs that wide rows need)
@@ -998,6 +1012,9 @@ inline int stream_grid(int ngroups, int threads, size_t smem, const void* kernel
     return (int)(g < ngroups ? g : ngroups);
 }
 
+// The two translation units that include this header define PD_TS_FWD_ONLY / PD_TS_BWD_ONLY so that each instantiates one
+// kernel family only (non-template inline launchers would instantiate every kernel they mention in both).
+#ifndef PD_TS_BWD_ONLY
 // THREADS = consumer threads the row groups are packed into + the producer warp
 template <bool MIX, int MASKMODE, int PX, int THREADS, int MINB>
 inline bool launch_fwd_stream_t(const WarpParams& p, cudaStream_t st, bool dry) {
@@ -1013,6 +1030,9 @@ inline bool launch_fwd_stream_t(const WarpParams& p, cudaStream_t st, bool dry) 
     return true;
 }
 
+#endif  // PD_TS_BWD_ONLY
+
+#ifndef PD_TS_FWD_ONLY
 template <bool MIX, int MASKMODE, bool WANT_DISP, int PX, int THREADS, int MINB>
 inline bool launch_bwd_stream_t(const WarpParams& p, cudaStream_t st, bool dry) {
     const StreamCfg c = stream_cfg<PX, THREADS - 32>(p, MIX, MASKMODE == SMASK_DENSE, MIX ? 2 : 1, WANT_DISP);
@@ -1027,6 +1047,9 @@ inline bool launch_bwd_stream_t(const WarpParams& p, cudaStream_t st, bool dry) 
     return true;
 }
 
+#endif  // PD_TS_FWD_ONLY
+
+#ifndef PD_TS_BWD_ONLY
 template <bool MIX, int MASKMODE>
 inline bool launch_fwd_stream_m(const WarpParams& p, cudaStream_t st, bool dry) {
     const int W = p.d.W;
@@ -1042,6 +1065,9 @@ inline bool launch_fwd_stream(const WarpParams& p, cudaStream_t st, bool dry = f
     return mm == SMASK_ROW ? launch_fwd_stream_m<false, SMASK_ROW>(p, st, dry) : launch_fwd_stream_m<false, SMASK_DENSE>(p, st, dry);
 }
 
+#endif  // PD_TS_BWD_ONLY
+
+#ifndef PD_TS_FWD_ONLY
 template <bool MIX, int MASKMODE, bool WANT_DISP>
 inline bool launch_bwd_stream_w(const WarpParams& p, cudaStream_t st, bool dry) {
     const int W = p.d.W;
@@ -1067,6 +1093,7 @@ inline bool launch_bwd_stream(const WarpParams& p, cudaStream_t st, bool dry = f
     if (mm == SMASK_SUMMARY) return launch_bwd_stream_m<false, SMASK_SUMMARY>(p, st, dry);
     return mm == SMASK_ROW ? launch_bwd_stream_m<false, SMASK_ROW>(p, st, dry) : launch_bwd_stream_m<false, SMASK_DENSE>(p, st, dry);
 }
+#endif  // PD_TS_FWD_ONLY
 
 }  // namespace ts
 }  // namespace pd

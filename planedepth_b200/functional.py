@@ -121,6 +121,7 @@ class _WarpComposite(torch.autograd.Function):
     def forward(ctx, cfg: WarpConfig, link, src, tgt, logits, sigma, disp, mask, hmat, cam):
         lib = L.lib()
         ctx.link = link
+        ctx.set_materialize_grads(False)  # an unused output's gradient arrives as None, not as a zero-filled tensor
         B, N, H, W = cfg.shape
         dev = logits.device
         desc = L.WarpDesc(B=B, N=N, H=H, W=W, warp_type=cfg.warp_type, mixture=int(cfg.mixture), automask=int(cfg.automask),
@@ -272,6 +273,7 @@ class _Photometric(torch.autograd.Function):
     def forward(ctx, mode: int, automask: bool, want_map: bool, scale: float, link, rgb_rec, tgt, src, mask_novel, nll, nll_auto):
         lib = L.lib()
         ctx.link = link
+        ctx.set_materialize_grads(False)  # pred without a consumer (no perceptual term): g_pred is None, no fill, no read
         ctx.scale = float(scale)
         B, _, H, W = rgb_rec.shape
         dev = rgb_rec.device

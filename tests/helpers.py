@@ -114,19 +114,23 @@ def error_stats(got, want, atol):
     err = np.abs(g - w)
     bad = err > atol
     st = {"max_err": float(err.max()) if err.size else 0.0, "atol": float(atol), "frac_bad": float(bad.mean()) if err.size else 0.0,
-          "n": int(err.size), "worst_row_frac": 0.0, "worst_col_frac": 0.0, "finite": bool(np.isfinite(g).all())}
+          "n": int(err.size), "worst_row_frac": 0.0, "worst_col_frac": 0.0, "bad_lines": 0, "finite": bool(np.isfinite(g).all())}
     if err.ndim >= 2 and err.shape[-1] >= 8 and err.shape[-2] >= 8 and bad.any():
         b3 = bad.reshape(-1, err.shape[-2], err.shape[-1])
-        st["worst_row_frac"] = float(b3.mean(2).max())
-        st["worst_col_frac"] = float(b3.mean(1).max())
+        rows, cols = b3.mean(2), b3.mean(1)
+        st["worst_row_frac"] = float(rows.max())
+        st["worst_col_frac"] = float(cols.max())
+        st["bad_lines"] = int((rows > 0.5).sum() + (cols > 0.5).sum())  # image rows / columns that are mostly wrong
     return st
 
 
-def bounded_check(got, want, atol, what, allow_frac=0.0, cap=100.0, line_frac=0.5):
+def bounded_check(got, want, atol, what, allow_frac=0.0, cap=100.0, max_bad_lines=0):
     """|got - want| <= atol except for a fraction `allow_frac` of knife-edge elements (|x| sign kinks, clamp / min / floor
     decisions that flip under rounding-level differences).  The exemptions are bounded too: no element may be off by more
-    than cap * atol, and the exempt elements may not fill more than `line_frac` of any image row or column — a wrong row
-    or column of a large tensor stays below any fraction gate, a border / pad / ring-phase bug does not stay below these."""
+    than cap * atol, and at most `max_bad_lines` image rows / columns of the whole tensor may be mostly (> 50 %) beyond
+    tolerance — a wrong row or column of a large tensor stays below any fraction gate; a border / pad / ring-phase bug
+    hits a line of EVERY plane and image, far more than the one or two lines a legitimate knife edge can touch (a plane
+    whose border tap weight is ~1e-4, so that the sigma clamp gate of its border column hinges on the position noise)."""
     st = error_stats(got, want, atol)
     if os.environ.get("PD_TEST_REPORT"):
         REPORT.append((what, st))
@@ -135,6 +139,6 @@ def bounded_check(got, want, atol, what, allow_frac=0.0, cap=100.0, line_frac=0.
     assert st["frac_bad"] <= allow_frac, "%s: %.3g of %d elements off by more than %.1e (max err %.3e)" % (
         what, st["frac_bad"], st["n"], atol, st["max_err"])
     assert st["max_err"] <= cap * atol, "%s: an exempt element is off by %.3e > %g x tolerance %.1e" % (what, st["max_err"], cap, atol)
-    assert st["worst_row_frac"] <= line_frac, "%s: %.0f%% of one row is beyond tolerance" % (what, 100 * st["worst_row_frac"])
-    assert st["worst_col_frac"] <= line_frac, "%s: %.0f%% of one column is beyond tolerance" % (what, 100 * st["worst_col_frac"])
+    assert st["bad_lines"] <= max_bad_lines, "%s: %d image rows / columns are mostly beyond tolerance (worst row %.0f%%, worst column %.0f%%)" % (
+        what, st["bad_lines"], 100 * st["worst_row_frac"], 100 * st["worst_col_frac"])
     return st

@@ -23,8 +23,9 @@ trip, DESIGN.md deviations: <= 6e-5 px at W = 640, 1.2e-4 px at W = 1280).  On t
 position noise meets the steepest possible fields (colour slope up to 1 / px, logit slope ~ 2 / px, sigma down to 0.01):
 forward 1e-4 on all but 1e-4 of the pixels (none beyond 1e-3), per-pixel NLL within delta_u * slope / sigma_min = 2e-2,
 gradients 1e-4 of their maximum on all but 1e-4 of the elements, plane-parameter gradients (sums over every pixel, the
-1/sigma-amplified ones included) 5e-3; measured values are in profiles/r2_parity_fullsize.json.  On smooth fields the default
-kernels meet the EXACT gates."""
+1/sigma-amplified ones included) 5e-3; measured values are in profiles/r2_parity_fullsize.json.  On smooth (network-like)
+fields the default kernels meet the EXACT gates except where 1/sigma amplifies the position noise: per-pixel NLL 1e-3
+(sigma_min = 0.01 turns 1.2e-4 px x slope 0.05 into 6e-4), plane-parameter gradients 5e-4."""
 import json
 import os
 
@@ -136,14 +137,15 @@ REDUCED = ("disp_base", "xz_h")  # plane-parameter gradients: sums over all H*W 
 
 
 def compare(tag, want, got, exact, noise=True):
-    """`exact`: EXACT-class gates; otherwise DEFAULT-class gates (iid noise) — see the module docstring.  `noise=False`
-    (smooth fields): EXACT-class gates whatever the kernel."""
+    """`exact`: EXACT-class gates; otherwise DEFAULT-class gates on iid noise (`noise`) or on smooth fields."""
     strict = exact or not noise
+    nll_tol = TOL if exact else (2e-2 if noise else 1e-3)
+    red_tol = TOL if exact else (5e-3 if noise else 5e-4)
     for s in want["sides"]:
         if ("rgb_rec", s) in got:
             bounded_check(got[("rgb_rec", s)], want[("rgb_rec", s)], TOL, "%s rgb_rec@%s" % (tag, s), allow_frac=(1e-5 if strict else 1e-4), cap=10)
         if ("nll", s) in want and ("nll", s) in got:
-            bounded_check(got[("nll", s)], want[("nll", s)], TOL if strict else 2e-2, "%s nll@%s" % (tag, s), allow_frac=0.0)
+            bounded_check(got[("nll", s)], want[("nll", s)], nll_tol, "%s nll@%s" % (tag, s), allow_frac=0.0)
     for k, v in got["losses"].items():
         bounded_check(torch.tensor(v), torch.tensor(want["losses"][k]), 1e-5, "%s %s" % (tag, k))
     for k, gw in want["grads"].items():
@@ -153,9 +155,10 @@ def compare(tag, want, got, exact, noise=True):
         assert gg is not None, "%s: no CUDA gradient for %s" % (tag, k)
         scale = float(gw.abs().max()) + 1e-12
         if k in REDUCED:
-            bounded_check(gg, gw, (TOL if strict else 5e-3) * scale, "%s grad_%s" % (tag, k))
+            bounded_check(gg, gw, red_tol * scale, "%s grad_%s" % (tag, k))
         else:
-            bounded_check(gg, gw, TOL * scale, "%s grad_%s" % (tag, k), allow_frac=(1e-5 if strict else 1e-4), cap=2.5 / TOL)
+            bounded_check(gg, gw, TOL * scale, "%s grad_%s" % (tag, k), allow_frac=(1e-5 if strict else 1e-4), cap=2.5 / TOL,
+                          max_bad_lines=(0 if exact else 2))
 
 
 @pytest.fixture(scope="module", autouse=True)
