@@ -47,6 +47,7 @@ CONFIGS = {
     "dbg_res": (4, 384, 1280, dict(plane_residual=True), None, "debug: residual only"),
     "dbg_w": (4, 384, 1280, dict(), None, "debug: 1280 wide L1"),
 }
+RAW_H, RAW_W = 375, 1242  # a KITTI raw frame (the reference's dataset), what a decoder hands to the loader
 METRIC = "training images/sec (49-plane warp+SSIM hot path, fwd+bwd)"
 UNIT = "images/s"
 
@@ -153,6 +154,30 @@ class ClockSampler:
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm), "source": "nvidia-smi -lms 20"}
+
+
+def gpu_cpu_affinity(index):
+    """CPUs NVML reports as local to the GPU (its NUMA node), or None.  Pinned staging buffers are first-touched by the thread
+    that allocates them: allocating from a CPU of the GPU's node keeps the H2D DMA off the inter-socket link."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = index
+        if vis:
+            try:
+                idx = int(vis.split(",")[index])
+            except Exception:
+                idx = index
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {w * 64 + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        return cpus or None
+    except Exception:
+        return None
 
 
 def algorithmic_bytes(B, N, H, W, mixture):
@@ -312,7 +337,11 @@ def run_ours(args):
         batch = make_batch(B, H, W, opt, seed=seed, device="cpu", layout=args.layout, mask_novel=mnov)
         N = batch.shape[1]
         dev = torch.device("cuda", local_rank)
-        # static device buffers: network outputs live on the device; the `inputs` dict comes from the host
+        # static device buffers: network outputs live on the device; the `inputs` dict comes from the host.  The pinned staging
+        # buffers are allocated (first-touched) from a CPU of the GPU's NUMA node
+        old_aff, local_cpus = os.sched_getaffinity(0), (None if args.no_numa_pin else gpu_cpu_affinity(local_rank))
+        if local_cpus:
+            os.sched_setaffinity(0, local_cpus)
         host_inputs = {k: v.pin_memory() for k, v in batch.inputs.items()}
         batch_gpu = make_batch(B, H, W, opt, seed=seed, device=dev, layout=args.layout, mask_novel=mnov)
         outputs, leaves_map = batch_gpu.outputs, batch_gpu.leaves
@@ -371,47 +400,69 @@ def run_ours(args):
         if opt.warp_type != "disp_warp":
             read_keys += ["K", "inv_K"] + [("Rt", sd) for sd in batch.target_sides]
         read_keys = [k for k in dict.fromkeys(read_keys) if k in host_inputs]
-        host_sel = {k: host_inputs[k] for k in read_keys}
-        staging = {k: torch.empty_like(inputs[k]) for k in read_keys}
         loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-        h2d = sum(v.numel() * v.element_size() for v in host_sel.values())
         copy_stream = torch.cuda.Stream()
-        copied, consumed = torch.cuda.Event(), torch.cuda.Event()
 
-        def enqueue_h2d():
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed)
-                for k, v in host_sel.items():
-                    staging[k].copy_(v, non_blocking=True)
-                copied.record(copy_stream)
-
-        consumed.record()
-        enqueue_h2d()
-
-        def e2e_step():
-            main = torch.cuda.current_stream()
-            main.wait_event(copied)
+        def run_e2e(u8):
+            """u8: the colour frames start as RAW uint8 frames of the dataset's size (KITTI: 375 x 1242 x 3, interleaved, as a
+            decoder leaves them) and are converted / resized / clamped on the device (pd_resize_bicubic_u8)
+            — what the reference's loader does per sample on the CPU (pair_transforms.py:63-78) before shipping fp32 tensors.
+            Otherwise: the fp32 tensors of the `inputs` dict travel, as in the reference (trainer.py:328-329)."""
+            host_sel = {}
             for k in read_keys:
-                inputs[k].copy_(staging[k], non_blocking=True)
-            consumed.record(main)
-            enqueue_h2d()  # next step's inputs travel while this step computes
-            res = graphed.replay()
-            loss_host.copy_(res["loss"], non_blocking=True)
-            main.synchronize()
-            return float(loss_host)
+                if u8 and isinstance(k, tuple) and k[0] == color:
+                    gg = torch.Generator().manual_seed(seed + 17 + len(host_sel))
+                    host_sel[k] = torch.randint(0, 256, (B, RAW_H, RAW_W, 3), generator=gg, dtype=torch.uint8).pin_memory()
+                else:
+                    host_sel[k] = host_inputs[k]
+            staging = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host_sel.items()}
+            nbytes = sum(v.numel() * v.element_size() for v in host_sel.values())
+            copied, consumed = torch.cuda.Event(), torch.cuda.Event()
 
-        for _ in range(warmup):
-            e2e_step()
-        barrier()
-        ev0.record()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            e2e_step()
-        ev1.record()
-        barrier()
-        e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
-        e2e_ms_step = D.max_over_ranks(e2e_ms, ws, dev) / steps
-        copy_stream.synchronize()
+            def enqueue_h2d():
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed)
+                    for k, v in host_sel.items():
+                        staging[k].copy_(v, non_blocking=True)
+                    copied.record(copy_stream)
+
+            consumed.record()
+            enqueue_h2d()
+
+            def e2e_step():
+                main = torch.cuda.current_stream()
+                main.wait_event(copied)
+                for k in read_keys:
+                    if staging[k].dtype == torch.uint8:
+                        functional.resize_frames_u8(staging[k], (H, W), out=inputs[k])
+                    else:
+                        inputs[k].copy_(staging[k], non_blocking=True)
+                consumed.record(main)
+                enqueue_h2d()  # next step's inputs travel while this step computes
+                res = graphed.replay()
+                loss_host.copy_(res["loss"], non_blocking=True)
+                main.synchronize()
+                return float(loss_host)
+
+            for _ in range(warmup):
+                e2e_step()
+            barrier()
+            ev0.record()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                e2e_step()
+            ev1.record()
+            barrier()
+            ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
+            ms = D.max_over_ranks(ms, ws, dev) / steps
+            copy_stream.synchronize()
+            return ms, nbytes
+
+        e2e_ms_step, h2d = run_e2e(u8=not args.e2e_fp32)
+        e2e_alt_ms, h2d_alt = run_e2e(u8=args.e2e_fp32)
+        # restore the resident inputs for the roofline pass below
+        for k in read_keys:
+            inputs[k].copy_(host_inputs[k].to(dev))
         clk = clocks.stop() if rank == 0 else None
 
         # ---------------- roofline: per-kernel CUDA events on the launch stream (eager pass) --------
@@ -450,8 +501,13 @@ def run_ours(args):
                     "launches_per_step": n_calls,
                     "step_frac": sum(alg[k] * n_calls.get(k, 0) for k in alg) / (ms_step * 1e-3) / 1e9 / peak}
 
+        if local_cpus:
+            os.sched_setaffinity(0, old_aff)
+        fmt = {True: "raw uint8 frames %dx%dx3 converted / bicubic-resized / clamped on the device (pd_resize_bicubic_u8)" % (RAW_H, RAW_W),
+               False: "fp32 tensors of the inputs dict (the reference's transport, trainer.py:328-329)"}
         e2e_scope = ("per step: H2D of the path's host-born inputs (%s) from pinned memory on a copy stream overlapped with the previous "
-                     "step, D2H of the loss; logits/sigma/plane geometry are network outputs (device-born)" % ", ".join(str(k) for k in read_keys))
+                     "step [colour frames: %s], D2H of the loss; logits/sigma/plane geometry are network outputs (device-born)" % (
+                         ", ".join(str(k) for k in read_keys), fmt[not args.e2e_fp32]))
         if rank != 0:
             return None
         cpu = None
@@ -470,7 +526,10 @@ def run_ours(args):
                            B * N * H * W * 4 / 1e6, B * N * H * W * 4 / 1e6),
                        "e2e_scope": e2e_scope},
             "e2e": {"value": D.aggregate_throughput(B, ws, e2e_ms_step), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": e2e_ms_step},
+                    "ms_per_step": e2e_ms_step, "h2d_GBps": h2d / (e2e_ms_step * 1e-3) / 1e9,
+                    "numa_pinned_cpus": (len(local_cpus) if local_cpus else 0), "colour_transport": "fp32" if args.e2e_fp32 else "uint8 raw frames",
+                    "other_transport": {"colour_transport": "uint8 raw frames" if args.e2e_fp32 else "fp32",
+                                        "value": D.aggregate_throughput(B, ws, e2e_alt_ms), "ms_per_step": e2e_alt_ms, "h2d_bytes_per_step": h2d_alt}},
             "gpu_launches": int(launches_per_step) * steps,
             "gpu_launches_per_step": int(launches_per_step),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "loss": loss_val,
@@ -706,6 +765,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-fuse-bwd", action="store_true", help="keep pd_photometric_bwd as its own launch (diagnostic)")
+    ap.add_argument("--e2e-fp32", action="store_true", help="headline e2e ships fp32 colour tensors (the reference's transport) instead of raw uint8 frames")
+    ap.add_argument("--no-numa-pin", action="store_true", help="do not move the process to the GPU's NUMA node for the e2e leg")
     ap.add_argument("--no-ddp-leg", action="store_true", help="skip the producer + DistributedDataParallel training-step leg")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip timing the unmodified reference on this GPU (N = 1 only)")
     args = ap.parse_args()

@@ -351,6 +351,21 @@ size_t pd_occlusion_masks_workspace_bytes(const pd_occl_desc* desc); /* one [B,N
 int pd_occlusion_masks_fwd(const pd_occl_desc* desc, const pd_occl_in* in, pd_occl_out* out, void* workspace,
                            pd_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Device-side input staging: replaces the per-sample CPU float resize of the reference's loader
+ * (datasets/pair_transforms.py:63-78 Resize, :28-48 RandomResizeCrop) + the fp32 H2D copy of trainer.py:328-329.  The raw
+ * uint8 frame crosses PCIe; one kernel does ToTensor (/255), F.interpolate(mode="bicubic", align_corners=True) to
+ * [Hf, Wf], the crop [y0 : y0+H, x0 : x0+W] and .clamp(0, 1) into the fp32 [B,3,H,W] tensor the path reads.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pd_resize_desc {
+    int32_t B, Hs, Ws;   /* frames, source size */
+    int32_t Hf, Wf;      /* size of the full resized frame (0 = H, W: plain Resize) */
+    int32_t y0, x0;      /* crop offset inside the resized frame */
+    int32_t H, W;        /* output size */
+    int32_t src_layout;  /* 0 = [B,Hs,Ws,3] interleaved (a decoder's output), 1 = [B,3,Hs,Ws] planar */
+} pd_resize_desc;
+int pd_resize_bicubic_u8(const pd_resize_desc* desc, const unsigned char* src, float* dst, pd_stream_t stream);
+
 /* Introspection for tests / bench: number of kernels the library has launched in this process since
  * the last pd_reset_launch_count() (bench.py reports it as gpu_launches). */
 int64_t pd_launch_count(void);

@@ -438,3 +438,45 @@ def decoder_tail(logits_raw, sigma_raw, padding_mask, disp_layered, mixture: boo
     out["disp"] = (out["probability"] * disp_layered).sum(1, True)  # :288
     out["depth"] = 0.1 * 0.58 * W / out["disp"]  # :290
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# input staging: the loader's float resize, datasets/pair_transforms.py:28-48, 63-78
+# --------------------------------------------------------------------------------------------
+
+
+def _cubic_weights(t):
+    """ATen cubic_convolution1 / cubic_convolution2 with A = -0.75 (UpSample.h get_cubic_upsample_coefficients)."""
+    A = -0.75
+    x0, x2, x3 = t + 1.0, 1.0 - t, 2.0 - t
+    w0 = ((A * x0 - 5.0 * A) * x0 + 8.0 * A) * x0 - 4.0 * A
+    w1 = ((A + 2.0) * t - (A + 3.0)) * t * t + 1.0
+    w2 = ((A + 2.0) * x2 - (A + 3.0)) * x2 * x2 + 1.0
+    w3 = ((A * x3 - 5.0 * A) * x3 + 8.0 * A) * x3 - 4.0 * A
+    return [w0, w1, w2, w3]
+
+
+def resize_frames_u8(frames_u8, size, full_size=None, crop=(0, 0)):
+    """What the reference's loader does to one decoded frame, restated with explicit gathers: ``ToTensor`` (uint8 / 255),
+    ``F.interpolate(x, full_size, mode="bicubic", align_corners=True)`` (third-party: ATen upsample_bicubic2d — source
+    coordinate ``o * (in - 1) / (out - 1)``, taps floor - 1 .. floor + 2 clamped to the image, A = -0.75), the crop window of
+    RandomResizeCrop and ``.clamp(0, 1)``.  ``frames_u8``: [B,3,Hs,Ws] uint8 -> fp32 [B,3,H,W]."""
+    x = frames_u8.to(torch.float32) / 255.0
+    B, C, Hs, Ws = x.shape
+    H, W = size
+    Hf, Wf = (H, W) if full_size is None else full_size
+    sy = torch.tensor((Hs - 1) / (Hf - 1) if Hf > 1 else 0.0, dtype=torch.float32)
+    sx = torch.tensor((Ws - 1) / (Wf - 1) if Wf > 1 else 0.0, dtype=torch.float32)
+    fy = sy * (torch.arange(H, dtype=torch.float32) + crop[0])
+    fx = sx * (torch.arange(W, dtype=torch.float32) + crop[1])
+    iy, ix = fy.floor(), fx.floor()
+    wy, wx = _cubic_weights(fy - iy), _cubic_weights(fx - ix)
+    iy, ix = iy.long(), ix.long()
+    out = torch.zeros(B, C, H, W, dtype=torch.float32)
+    for j in range(4):
+        rows = x[:, :, (iy - 1 + j).clamp(0, Hs - 1), :]  # [B,C,H,Ws]
+        acc = torch.zeros(B, C, H, W, dtype=torch.float32)
+        for k in range(4):
+            acc = acc + rows[:, :, :, (ix - 1 + k).clamp(0, Ws - 1)] * wx[k][None, None, None, :]
+        out = out + acc * wy[j][None, None, :, None]
+    return out.clamp(0.0, 1.0)

@@ -32,7 +32,7 @@ EXPORTS = [
     "pd_occlusion_masks_workspace_bytes", "pd_occlusion_masks_fwd",
     "pd_smooth_loss_workspace_bytes", "pd_smooth_loss_fwd", "pd_smooth_loss_bwd",
     "pd_plane_tail_fwd", "pd_plane_tail_bwd",
-    "pd_get_tuning", "pd_set_tuning", "pd_x_constant_check",
+    "pd_get_tuning", "pd_set_tuning", "pd_x_constant_check", "pd_resize_bicubic_u8",
 ]
 
 
@@ -108,6 +108,10 @@ class OcclIn(C.Structure):
 
 class OcclOut(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("o_l", "o_fr", "mask_novel", "disp_pp")]
+
+
+class ResizeDesc(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("B", "Hs", "Ws", "Hf", "Wf", "y0", "x0", "H", "W", "src_layout")]
 
 
 class LossDesc(C.Structure):
@@ -311,6 +315,8 @@ def lib() -> C.CDLL:
     L.pd_set_tuning.argtypes = [C.POINTER(Tuning)]
     L.pd_x_constant_check.restype = C.c_int
     L.pd_x_constant_check.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Strides4), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    L.pd_resize_bicubic_u8.restype = C.c_int
+    L.pd_resize_bicubic_u8.argtypes = [C.POINTER(ResizeDesc), C.c_void_p, C.c_void_p, C.c_void_p]
     L.pd_debug_roundtrip.restype = C.c_int
     L.pd_debug_roundtrip.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     if L.pd_version() != ABI_VERSION:

@@ -234,18 +234,29 @@ class HotPathMixin:
     generate_images_pred = pred_novel_images
 
     # ------------------------------------------------------------------------------------------
+    #: how the perceptual term is scheduled (perceptual.py): "reference" = trainer.py:672-685 as written (three fp32 passes
+    #: per side); "scheduled" = constant passes batched under no_grad and cached per step, channels_last (fp32 values
+    #: unchanged); "scheduled_bf16" = the same with the feature network under bf16 autocast, fp32 reductions
+    perceptual_mode: str = "scheduled"
+
+    def _perceptual_schedule(self):
+        from .perceptual import PerceptualSchedule
+
+        sched = self.__dict__.get("_pd_pc_schedule")
+        mode = self.perceptual_mode
+        if sched is None or sched.pc_net is not self.pc_net or sched.mode != mode:
+            sched = PerceptualSchedule(self.pc_net, dtype=(torch.bfloat16 if mode == "scheduled_bf16" else None))
+            sched.mode = mode
+            self.__dict__["_pd_pc_schedule"] = sched
+        return sched
+
     def perceptual_loss(self, pred, target, source=None):
-        """trainer.py:672-685 — stays PyTorch (the feature network is cuDNN territory)."""
-        pv, tv = self.pc_net(pred), self.pc_net(target)
-        sv = self.pc_net(source) if source is not None else None
-        total = 0
-        for i in range(3):
-            lp = ((pv[i] - tv[i]) ** 2).mean(1, True)
-            if sv is not None:
-                la = ((sv[i] - tv[i]) ** 2).mean(1, True)
-                lp, _ = torch.cat([lp, la], dim=1).min(1, True)
-            total = total + lp.mean()
-        return total
+        """trainer.py:672-685.  The feature network's convolutions stay PyTorch / cuDNN; perceptual.py schedules them."""
+        if self.perceptual_mode == "reference":
+            from .perceptual import reference_perceptual_loss
+
+            return reference_perceptual_loss(self.pc_net, pred, target, source)
+        return self._perceptual_schedule()(pred, target, source)
 
     def _photometric_mode(self) -> int:
         mode = self.photometric
@@ -279,6 +290,8 @@ class HotPathMixin:
         src = inputs[(color, "l")]
         mask_novel = outputs.get("mask_novel")
         inv_count = 1.0 / float(B * H * W)
+        if pc_net is not None and self.perceptual_mode != "reference":
+            self._perceptual_schedule().new_batch()  # feature cache lives for one step: source features are shared by the sides
         for side in self.target_sides:
             target = inputs[(color, side)]
             # ph_loss.mean() (trainer.py:742): the 1/(B*H*W) is folded into the kernel's reduction
@@ -372,7 +385,8 @@ class HotPath(HotPathMixin):
     and smoke() instantiate instead of the full Trainer, whose constructor needs NCCL + KITTI)."""
 
     def __init__(self, opt, target_sides=None, pc_net=None, photometric: Optional[str] = None, materialize_layered: bool = False,
-                 exact_coords: bool = False, disp_rowwise: bool = False, verify_rowwise: str = "first", skip_missing_terms: bool = True):
+                 exact_coords: bool = False, disp_rowwise: bool = False, verify_rowwise: str = "first", skip_missing_terms: bool = True,
+                 perceptual_mode: str = "scheduled"):
         self.opt = opt
         if target_sides is None:
             target_sides = ([] if _flag(opt, "no_stereo", False) else ["r"]) + list(_flag(opt, "novel_frame_ids", []))
@@ -384,6 +398,7 @@ class HotPath(HotPathMixin):
         self.disp_rowwise = disp_rowwise
         self.verify_rowwise = verify_rowwise
         self.skip_missing_terms = skip_missing_terms
+        self.perceptual_mode = perceptual_mode
 
     def process(self, inputs, outputs):
         self.pred_novel_images(inputs, outputs)

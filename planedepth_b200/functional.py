@@ -378,6 +378,28 @@ def occlusion_masks(logits, probability, disp_layered, disp, exact_coords: bool 
     return disp_pp, mask_novel, o_l, o_fr
 
 
+def resize_frames_u8(frames: torch.Tensor, size, full_size=None, crop=(0, 0), out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """pd_resize_bicubic_u8: raw uint8 frames ([B,Hs,Ws,3] interleaved or [B,3,Hs,Ws] planar, on the device) ->
+    fp32 [B,3,H,W] = ``F.interpolate(frames / 255, full_size, mode="bicubic", align_corners=True)[..., crop window].clamp(0, 1)``
+    (datasets/pair_transforms.py:63-78; with ``full_size`` / ``crop``: RandomResizeCrop, :28-48).  No gradients (data)."""
+    lib = L.lib()
+    if frames.device.type != "cuda":
+        raise L.PlaneDepthLibraryError("frames must be a CUDA tensor (planedepth_b200 has no CPU path)")
+    if frames.dtype != torch.uint8 or frames.dim() != 4:
+        raise ValueError("frames must be uint8 [B,Hs,Ws,3] or [B,3,Hs,Ws]")
+    hwc = frames.shape[-1] == 3 and frames.shape[1] != 3
+    frames = frames.contiguous()
+    B = frames.shape[0]
+    Hs, Ws = (frames.shape[1], frames.shape[2]) if hwc else (frames.shape[2], frames.shape[3])
+    H, W = int(size[0]), int(size[1])
+    Hf, Wf = (H, W) if full_size is None else (int(full_size[0]), int(full_size[1]))
+    if out is None:
+        out = torch.empty(B, 3, H, W, device=frames.device, dtype=torch.float32)
+    desc = L.ResizeDesc(B=B, Hs=Hs, Ws=Ws, Hf=Hf, Wf=Wf, y0=int(crop[0]), x0=int(crop[1]), H=H, W=W, src_layout=0 if hwc else 1)
+    _call("pd_resize_bicubic_u8", lib.pd_resize_bicubic_u8, C.byref(desc), frames.data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
 class _SmoothLoss(torch.autograd.Function):
     """pd_smooth_loss_fwd / _bwd: get_smooth_loss_disp (layers.py:243-256) on the crop [..., x0:] (trainer.py:768-771)."""
 
