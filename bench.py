@@ -416,6 +416,9 @@ def run_ours(args):
                 else:
                     host_sel[k] = host_inputs[k]
             staging = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host_sel.items()}
+            # uint8 frames are converted on the COPY stream, right behind their H2D, into fp32 staging: the conversion of step
+            # i+1 overlaps step i like the transfer does, and the main stream sees fp32 staging in both modes
+            ready = {k: (torch.empty_like(inputs[k]) if v.dtype == torch.uint8 else staging[k]) for k, v in host_sel.items()}
             nbytes = sum(v.numel() * v.element_size() for v in host_sel.values())
             copied, consumed = torch.cuda.Event(), torch.cuda.Event()
 
@@ -424,6 +427,8 @@ def run_ours(args):
                     copy_stream.wait_event(consumed)
                     for k, v in host_sel.items():
                         staging[k].copy_(v, non_blocking=True)
+                        if v.dtype == torch.uint8:
+                            functional.resize_frames_u8(staging[k], (H, W), out=ready[k])
                     copied.record(copy_stream)
 
             consumed.record()
@@ -433,12 +438,9 @@ def run_ours(args):
                 main = torch.cuda.current_stream()
                 main.wait_event(copied)
                 for k in read_keys:
-                    if staging[k].dtype == torch.uint8:
-                        functional.resize_frames_u8(staging[k], (H, W), out=inputs[k])
-                    else:
-                        inputs[k].copy_(staging[k], non_blocking=True)
+                    inputs[k].copy_(ready[k], non_blocking=True)
                 consumed.record(main)
-                enqueue_h2d()  # next step's inputs travel while this step computes
+                enqueue_h2d()  # next step's inputs travel (and are converted) while this step computes
                 res = graphed.replay()
                 loss_host.copy_(res["loss"], non_blocking=True)
                 main.synchronize()
