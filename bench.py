@@ -619,23 +619,35 @@ def ddp_leg(args, rank, local_rank, ws, dev):
                 return {"logits": logits, "probability": logits.detach(), "disp": logits[:, :1].abs() + 1.0}
 
         producer = Head().to(dev)
-    n_params = sum(p.numel() for p in producer.parameters())
-    model = producer
-    if ws > 1:
-        model = nn.parallel.DistributedDataParallel(producer, device_ids=[local_rank], output_device=local_rank, gradient_as_bucket_view=True)
     hp = HotPath(opt, batch.target_sides, pc_net=None, photometric=photometric, disp_rowwise=True)
-    params = [p for p in producer.parameters() if p.requires_grad]
 
-    def step():
-        out = model(inputs[("color_aug", "l")], inputs["grid"])
+    def run_step(net):
+        out = net(inputs[("color_aug", "l")], inputs["grid"])
         for k in ("disp_layered", "padding_mask", "distance", "norm"):
             out.setdefault(k, batch.outputs[k])
         out[("Rt", "r")] = inputs[("Rt", "r")]
-        losses = hp.process(inputs, out)
+        return hp.process(inputs, out)["loss/total_loss"]
+
+    # parameters the step never touches (the ResNet's classifier head: the reference copes with
+    # find_unused_parameters=True, trainer.py:99, a per-step graph traversal) are frozen once, found by a dry run: DDP then
+    # runs with its static bucket plan
+    run_step(producer).backward()
+    for prm in producer.parameters():
+        if prm.grad is None:
+            prm.requires_grad_(False)
+        prm.grad = None
+    n_params = sum(p.numel() for p in producer.parameters() if p.requires_grad)
+    model = producer
+    if ws > 1:
+        model = nn.parallel.DistributedDataParallel(producer, device_ids=[local_rank], output_device=local_rank, gradient_as_bucket_view=True)
+    params = [p for p in producer.parameters() if p.requires_grad]
+
+    def step():
+        loss = run_step(model)
         for p in params:
             p.grad = None
-        losses["loss/total_loss"].backward()
-        return losses["loss/total_loss"].detach()
+        loss.backward()
+        return loss.detach()
 
     steps = max(5, min(args.steps, 30))
     for _ in range(5):

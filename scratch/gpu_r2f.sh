@@ -5,10 +5,10 @@ O=gpurun_out
 mkdir -p $O
 NCCL_DEBUG=INFO python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 5 > $O/${TAG}_bench_2gpu.json 2> $O/${TAG}_bench_2gpu.err; echo "2gpu rc=$?"
 wc -l $O/${TAG}_bench_2gpu.json; grep -c "NCCL INFO" $O/${TAG}_bench_2gpu.err; grep -m3 "comm 0x.*rank .* nranks" $O/${TAG}_bench_2gpu.err
-CUDA_VISIBLE_DEVICES=0 python bench.py --no-cpu-baseline --steps 100 > $O/${TAG}_bench_1gpu.json 2> $O/${TAG}_bench_1gpu.err; echo "1gpu rc=$?"
+echo skip-1gpu
 python - <<'PY'
 import json
-for f in ["gpurun_out/r2f_bench_1gpu.json","gpurun_out/r2f_bench_2gpu.json"]:
+for f in ["gpurun_out/r2f_bench_2gpu.json"]:
     d=json.loads(open(f).read().strip().splitlines()[-1])
     print(f, d["n_gpus"], "%.4f ms  %.0f img/s"%(d["ms_per_step"], d["value"]))
     print("   e2e", d["e2e"])
