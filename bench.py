@@ -415,32 +415,42 @@ def run_ours(args):
                     host_sel[k] = torch.randint(0, 256, (B, RAW_H, RAW_W, 3), generator=gg, dtype=torch.uint8).pin_memory()
                 else:
                     host_sel[k] = host_inputs[k]
-            staging = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host_sel.items()}
-            # uint8 frames are converted on the COPY stream, right behind their H2D, into fp32 staging: the conversion of step
-            # i+1 overlaps step i like the transfer does, and the main stream sees fp32 staging in both modes
-            ready = {k: (torch.empty_like(inputs[k]) if v.dtype == torch.uint8 else staging[k]) for k, v in host_sel.items()}
+            # two staging sets: the H2D of step i+1 only waits for the consumer of step i-1 (uint8 frames are converted /
+            # resized by a kernel on the main stream; with one set the next transfer would idle for that kernel's duration.
+            # Converting on the copy stream instead was measured and dropped: its CTAs only find SMs between the persistent
+            # kernels of the step, 1.7 ms per step instead of 0.7)
+            staging = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host_sel.items()} for _ in range(2)]
             nbytes = sum(v.numel() * v.element_size() for v in host_sel.values())
-            copied, consumed = torch.cuda.Event(), torch.cuda.Event()
+            copied = [torch.cuda.Event(), torch.cuda.Event()]
+            consumed = [torch.cuda.Event(), torch.cuda.Event()]
+            state = {"next_h2d": 0, "next_use": 0}
 
             def enqueue_h2d():
+                i = state["next_h2d"]
                 with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(consumed)
+                    copy_stream.wait_event(consumed[i])
                     for k, v in host_sel.items():
-                        staging[k].copy_(v, non_blocking=True)
-                        if v.dtype == torch.uint8:
-                            functional.resize_frames_u8(staging[k], (H, W), out=ready[k])
-                    copied.record(copy_stream)
+                        staging[i][k].copy_(v, non_blocking=True)
+                    copied[i].record(copy_stream)
+                state["next_h2d"] = i ^ 1
 
-            consumed.record()
+            for ev in consumed:
+                ev.record()
+            enqueue_h2d()
             enqueue_h2d()
 
             def e2e_step():
                 main = torch.cuda.current_stream()
-                main.wait_event(copied)
+                i = state["next_use"]
+                main.wait_event(copied[i])
                 for k in read_keys:
-                    inputs[k].copy_(ready[k], non_blocking=True)
-                consumed.record(main)
-                enqueue_h2d()  # next step's inputs travel (and are converted) while this step computes
+                    if staging[i][k].dtype == torch.uint8:
+                        functional.resize_frames_u8(staging[i][k], (H, W), out=inputs[k])
+                    else:
+                        inputs[k].copy_(staging[i][k], non_blocking=True)
+                consumed[i].record(main)
+                state["next_use"] = i ^ 1
+                enqueue_h2d()  # refill the set just consumed: travels while this step (and the next) compute
                 res = graphed.replay()
                 loss_host.copy_(res["loss"], non_blocking=True)
                 main.synchronize()
@@ -631,11 +641,7 @@ def ddp_leg(args, rank, local_rank, ws, dev):
     # parameters the step never touches (the ResNet's classifier head: the reference copes with
     # find_unused_parameters=True, trainer.py:99, a per-step graph traversal) are frozen once, found by a dry run: DDP then
     # runs with its static bucket plan
-    run_step(producer).backward()
-    for prm in producer.parameters():
-        if prm.grad is None:
-            prm.requires_grad_(False)
-        prm.grad = None
+    D.freeze_unused_parameters(producer, lambda: run_step(producer))
     n_params = sum(p.numel() for p in producer.parameters() if p.requires_grad)
     model = producer
     if ws > 1:

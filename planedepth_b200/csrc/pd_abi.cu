@@ -39,6 +39,7 @@ pd_tuning sanitize(pd_tuning t) {
     t.stream_px8 = t.stream_px8 != 0;
     t.ssim_tiles = t.ssim_tiles != 0;
     t.homo_tiles = clampi(t.homo_tiles, -1, 1);
+    t.stream_fwd_minb = (t.stream_fwd_minb == 5 || t.stream_fwd_minb == 6) ? t.stream_fwd_minb : 0;
     return t;
 }
 
@@ -58,6 +59,7 @@ pd_tuning tuning_from_env() {
     t.stream_px8 = env_int("PD_STREAM_PX8");
     t.ssim_tiles = env_int("PD_SSIM_TILES");
     t.homo_tiles = env_int("PD_HOMO_TILES");
+    t.stream_fwd_minb = env_int("PD_STREAM_FWD_MINB");
     return sanitize(t);
 }
 

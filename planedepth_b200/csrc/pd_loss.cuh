@@ -13,6 +13,8 @@
 // (already gated by the automask min and scaled by 0.85/3), stage 3 gathers the 9 centres around every
 // tile pixel with the reflect-padding multiplicities.
 #pragma once
+#include <type_traits>
+
 #include "pd_device.cuh"
 
 namespace pd {
@@ -359,22 +361,30 @@ __global__ void __launch_bounds__(SW_THREADS, 2) ssim_l1_stream_kernel(const Los
         float wxp = (x + 1 >= W) ? 0.0f : 1.0f + ((x == W - 2) ? 1.0f : 0.0f);
         if (x == 1) wxm += 1.0f;  // centre 0 sees column 1 a second time as the reflected column -1
 
-        float H1[3][5], H2[3][5], S1[3][3], S2[3][3];      // horizontal sums of the two previous rows
-        float ap[3], bp[3], sp[3], app[3], bpp[3];          // values one / two rows back
-        float C1[3][3], C2[3][3];                           // column-summed coefficients of the two previous centre rows
-        float gate_p = 0.0f, m_p = 1.0f, m_pp = 1.0f;
+        // Two-row histories live in ping-pong slots: at row i slot [i & 1] holds the values of two rows back (it is consumed
+        // and then overwritten by the current row), slot [(i + 1) & 1] the previous row.  The loop body is instantiated for
+        // both parities, so the slot indices are compile-time constants and no register is moved between rows.
+        float Hh[2][3][5], Sh[2][3][3];     // horizontal sums of the two previous rows (prediction / target; source)
+        float av[2][3], bv[2][3], sv[2][3]; // values of the two previous rows
+        float Ch[2][3][3];                  // column-summed derivative coefficients of the two previous centre rows
+        float gatev[2] = {0.0f, 0.0f}, mv[2] = {1.0f, 1.0f};
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
+        for (int q = 0; q < 2; ++q)
 #pragma unroll
-            for (int k = 0; k < 5; ++k) H1[c][k] = H2[c][k] = 0.0f;
+            for (int c = 0; c < 3; ++c) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) S1[c][k] = S2[c][k] = C1[c][k] = C2[c][k] = 0.0f;
-            ap[c] = bp[c] = sp[c] = app[c] = bpp[c] = 0.0f;
-        }
+                for (int k = 0; k < 5; ++k) Hh[q][c][k] = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) Sh[q][c][k] = Ch[q][c][k] = 0.0f;
+                av[q][c] = bv[q][c] = sv[q][c] = 0.0f;
+            }
         SsimRow nxt;
         ssim_load_row<AUTO, HASMASK>(p, b, ys - 2, xv, nxt);
         const int iters = rs + 4;  // rows past ye (last segment of an image) are walked with clamped loads and masked stores
-        for (int i = 0; i < iters; ++i) {
+
+        auto row_step = [&](const int i, auto parity) {
+            constexpr int O = decltype(parity)::value;  // slot of two rows back (overwritten at the end), 1 - O: previous row
+            constexpr int P = 1 - O;
             const int y = ys - 2 + i;  // value row of this iteration; centre row y-1; gradient row y-2
             const SsimRow cur = nxt;
             if (i + 1 < iters) ssim_load_row<AUTO, HASMASK>(p, b, y + 1, xv, nxt);
@@ -397,10 +407,10 @@ __global__ void __launch_bounds__(SW_THREADS, 2) ssim_l1_stream_kernel(const Los
                 hc[2] = fmaf(al, al, fmaf(ar, ar, a * a)), hc[3] = fmaf(tl, tl, fmaf(tr, tr, t * t));
                 hc[4] = fmaf(al, tl, fmaf(ar, tr, a * t));
                 WinStats w;
-                w.mx = (H2[c][0] + H1[c][0] + hc[0]) * k9, w.my = (H2[c][1] + H1[c][1] + hc[1]) * k9;
-                w.sx = (H2[c][2] + H1[c][2] + hc[2]) * k9 - w.mx * w.mx;
-                w.sy = (H2[c][3] + H1[c][3] + hc[3]) * k9 - w.my * w.my;
-                w.sxy = (H2[c][4] + H1[c][4] + hc[4]) * k9 - w.mx * w.my;
+                w.mx = (Hh[O][c][0] + Hh[P][c][0] + hc[0]) * k9, w.my = (Hh[O][c][1] + Hh[P][c][1] + hc[1]) * k9;
+                w.sx = (Hh[O][c][2] + Hh[P][c][2] + hc[2]) * k9 - w.mx * w.mx;
+                w.sy = (Hh[O][c][3] + Hh[P][c][3] + hc[3]) * k9 - w.my * w.my;
+                w.sxy = (Hh[O][c][4] + Hh[P][c][4] + hc[4]) * k9 - w.mx * w.my;
                 const float a1c = 2.0f * w.mx * w.my + kC1, a2c = 2.0f * w.sxy + kC2;
                 const float b1c = w.mx * w.mx + w.my * w.my + kC1, b2c = w.sx + w.sy + kC2;
                 const float n = a1c * a2c, d = b1c * b2c;
@@ -409,7 +419,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2) ssim_l1_stream_kernel(const Los
                 const float v = (1.0f - __fdiv_rn(n, d)) * 0.5f;
                 const float id = __fdividef(1.0f, d);
                 ss += fminf(fmaxf(v, 0.0f), 1.0f);
-                l1 += fabsf(ap[c] - bp[c]);
+                l1 += fabsf(av[P][c] - bv[P][c]);
                 ca[c] = cb[c] = cc[c] = 0.0f;
                 if (WANT_G && v >= 0.0f && v <= 1.0f) {  // clamp backward
                     const float nd2 = n * id * id;
@@ -423,18 +433,18 @@ __global__ void __launch_bounds__(SW_THREADS, 2) ssim_l1_stream_kernel(const Los
                     float hs[3];
                     hs[0] = sl + s + sr, hs[1] = fmaf(sl, sl, fmaf(sr, sr, s * s)), hs[2] = fmaf(sl, tl, fmaf(sr, tr, s * t));
                     WinStats u;
-                    u.mx = (S2[c][0] + S1[c][0] + hs[0]) * k9, u.my = w.my;
-                    u.sx = (S2[c][1] + S1[c][1] + hs[1]) * k9 - u.mx * u.mx;
+                    u.mx = (Sh[O][c][0] + Sh[P][c][0] + hs[0]) * k9, u.my = w.my;
+                    u.sx = (Sh[O][c][1] + Sh[P][c][1] + hs[1]) * k9 - u.mx * u.mx;
                     u.sy = w.sy;
-                    u.sxy = (S2[c][2] + S1[c][2] + hs[2]) * k9 - u.mx * u.my;
+                    u.sxy = (Sh[O][c][2] + Sh[P][c][2] + hs[2]) * k9 - u.mx * u.my;
                     float na, da;
                     ssa += fminf(fmaxf(ssim_val(u, na, da), 0.0f), 1.0f);
-                    l1a += fabsf(sp[c] - bp[c]);
+                    l1a += fabsf(sv[P][c] - bv[P][c]);
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) S2[c][k] = S1[c][k], S1[c][k] = hs[k];
+                    for (int k = 0; k < 3; ++k) Sh[O][c][k] = hs[k];
                 }
 #pragma unroll
-                for (int k = 0; k < 5; ++k) H2[c][k] = H1[c][k], H1[c][k] = hc[k];
+                for (int k = 0; k < 5; ++k) Hh[O][c][k] = hc[k];
             }
             float ph = 0.85f * (ss * k3) + 0.15f * (l1 * k3);
             float gate = inside ? 1.0f : 0.0f;
@@ -462,22 +472,27 @@ __global__ void __launch_bounds__(SW_THREADS, 2) ssim_l1_stream_kernel(const Los
                     h[1] = fmaf(wxm, __shfl_up_sync(0xffffffffu, zb, 1), fmaf(wxp, __shfl_down_sync(0xffffffffu, zb, 1), zb));
                     h[2] = fmaf(wxm, __shfl_up_sync(0xffffffffu, zc, 1), fmaf(wxp, __shfl_down_sync(0xffffffffu, zc, 1), zc));
                     if (store) {
-                        const float sa = fmaf(wym, C2[c][0], fmaf(wyp, h[0], C1[c][0]));
-                        const float sb = fmaf(wym, C2[c][1], fmaf(wyp, h[1], C1[c][1]));
-                        const float sc = fmaf(wym, C2[c][2], fmaf(wyp, h[2], C1[c][2]));
-                        const float pr = app[c], tg = bpp[c];
-                        float g = gate_p * (0.15f * k3) * sgnf(pr - tg) + sa + sb * pr + sc * tg;
-                        if (HASMASK) g *= m_pp;
+                        // Ch[O]: centre row py-1 (two back), Ch[P]: centre row py, h: centre row py+1
+                        const float sa = fmaf(wym, Ch[O][c][0], fmaf(wyp, h[0], Ch[P][c][0]));
+                        const float sb = fmaf(wym, Ch[O][c][1], fmaf(wyp, h[1], Ch[P][c][1]));
+                        const float sc = fmaf(wym, Ch[O][c][2], fmaf(wyp, h[2], Ch[P][c][2]));
+                        const float pr = av[O][c], tg = bv[O][c];  // values of row py (two back)
+                        float g = gatev[P] * (0.15f * k3) * sgnf(pr - tg) + sa + sb * pr + sc * tg;
+                        if (HASMASK) g *= mv[O];
                         p.out.g_unit[((int64_t)b * 3 + c) * p.hw + (int64_t)py * W + x] = g;
                     }
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) C2[c][k] = C1[c][k], C1[c][k] = h[k];
+                    for (int k = 0; k < 3; ++k) Ch[O][c][k] = h[k];
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) app[c] = ap[c], bpp[c] = bp[c], ap[c] = cur.a[c], bp[c] = cur.b[c], sp[c] = cur.s[c];
-            m_pp = m_p, m_p = cur.m;
-            gate_p = gate;
+            for (int c = 0; c < 3; ++c) av[O][c] = cur.a[c], bv[O][c] = cur.b[c], sv[O][c] = cur.s[c];
+            mv[O] = cur.m;
+            gatev[O] = gate;
+        };
+        for (int i = 0; i < iters; i += 2) {
+            row_step(i, std::integral_constant<int, 0>{});
+            if (i + 1 < iters) row_step(i + 1, std::integral_constant<int, 1>{});
         }
     }
     ph_acc = warp_sum(ph_acc);

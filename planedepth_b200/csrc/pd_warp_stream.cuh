@@ -968,7 +968,7 @@ inline bool stream_path_supported(const WarpParams& p) {
 }
 
 template <int PX, int THREADS>
-inline StreamCfg stream_cfg(const WarpParams& p, bool mix, bool dense, int ne_bwd, bool want_disp) {
+inline StreamCfg stream_cfg(const WarpParams& p, bool mix, bool dense, int ne_bwd, bool want_disp, int budget_kb = 0) {
     StreamCfg c;
     c.tpr = p.d.W / PX;
     c.rpc = THREADS / c.tpr;
@@ -987,7 +987,7 @@ inline StreamCfg stream_cfg(const WarpParams& p, bool mix, bool dense, int ne_bw
     // (three CTAs of <= 192 threads per SM, two of the 352-thread CTAs that wide rows need)
     // (the wide mixture backward runs one CTA per SM on registers anyway: it gets a deep ring instead, cfg3 0.82 -> 0.69 ms)
     const int dflt_kb = c.nc > 160 ? ((mix && ne_bwd > 0) ? 200 : 110) : 72;
-    const size_t budget = (size_t)(tn.stream_smem_kb > 0 ? tn.stream_smem_kb : dflt_kb) * 1024;
+    const size_t budget = (size_t)(budget_kb > 0 ? budget_kb : (tn.stream_smem_kb > 0 ? tn.stream_smem_kb : dflt_kb)) * 1024;
     while (stream_smem_bytes(c, p.d.N, mix, dense, ne_bwd, want_disp) > budget) {
         if (c.nst > 2) --c.nst;
         else if (c.hs > 1) --c.hs;
@@ -1018,7 +1018,8 @@ inline int stream_grid(int ngroups, int threads, size_t smem, const void* kernel
 // THREADS = consumer threads the row groups are packed into + the producer warp
 template <bool MIX, int MASKMODE, int PX, int THREADS, int MINB>
 inline bool launch_fwd_stream_t(const WarpParams& p, cudaStream_t st, bool dry) {
-    const StreamCfg c = stream_cfg<PX, THREADS - 32>(p, MIX, MASKMODE == SMASK_DENSE, 0, false);
+    // more than four resident CTAs only fit with a shallower ring: 220 KB / MINB each
+    const StreamCfg c = stream_cfg<PX, THREADS - 32>(p, MIX, MASKMODE == SMASK_DENSE, 0, false, MINB > 4 ? 220 / MINB : 0);
     const int threads = c.nc + 32;
     if (threads > THREADS) return false;
     const size_t smem = stream_smem_bytes(c, p.d.N, MIX, MASKMODE == SMASK_DENSE, 0, false);
@@ -1054,6 +1055,10 @@ template <bool MIX, int MASKMODE>
 inline bool launch_fwd_stream_m(const WarpParams& p, cudaStream_t st, bool dry) {
     const int W = p.d.W;
     if (W % 8 == 0 && W / 8 <= 160 && tuning().stream_px8) return launch_fwd_stream_t<MIX, MASKMODE, 8, 192, 2>(p, st, dry);
+    if constexpr (!MIX && MASKMODE == SMASK_ROW) {  // occupancy experiments (pd_tuning.stream_fwd_minb): fewer registers, shallower ring
+        if (W / 4 <= 160 && tuning().stream_fwd_minb == 5) return launch_fwd_stream_t<MIX, MASKMODE, 4, 192, 5>(p, st, dry);
+        if (W / 4 <= 160 && tuning().stream_fwd_minb == 6) return launch_fwd_stream_t<MIX, MASKMODE, 4, 192, 6>(p, st, dry);
+    }
     if (W / 4 <= 160) return launch_fwd_stream_t<MIX, MASKMODE, 4, 192, MIX ? 2 : 4>(p, st, dry);
     if (W / 4 <= 320) return launch_fwd_stream_t<MIX, MASKMODE, 4, 352, MIX ? 2 : 2>(p, st, dry);
     return false;

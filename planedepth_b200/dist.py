@@ -63,3 +63,21 @@ def global_mean_loss(local_sum: torch.Tensor, local_count: int, world_size: int)
 def aggregate_throughput(units_per_rank: int, world_size: int, ms_per_step: float) -> float:
     """Whole-job units/s (weak scaling: every rank processes units_per_rank per step)."""
     return units_per_rank * world_size / (ms_per_step * 1e-3)
+
+
+def freeze_unused_parameters(module: torch.nn.Module, dry_run_loss) -> int:
+    """Freeze the parameters a training step never touches, found by one dry run (``dry_run_loss()`` returns the step's
+    loss for the un-wrapped ``module``).  The reference wraps its networks with ``find_unused_parameters=True``
+    (trainer.py:99) because the ResNet encoder's classifier head never contributes to the loss: a graph traversal and a
+    bitmap all-reduce every step.  With the dead parameters frozen once, DistributedDataParallel keeps a static bucket
+    plan and only the gradient buckets cross devices.  Returns the number of parameters frozen."""
+    for p in module.parameters():
+        p.grad = None
+    dry_run_loss().backward()
+    frozen = 0
+    for p in module.parameters():
+        if p.requires_grad and p.grad is None:
+            p.requires_grad_(False)
+            frozen += p.numel()
+        p.grad = None
+    return frozen

@@ -113,7 +113,7 @@ def test_tuning_block_is_clamped_and_restorable():
     """pd_set_tuning replaces the per-call getenv knobs of round 1: values are clamped when they are set (a zero or negative
     ring depth can no longer reach a division), NULL restores what the environment said at load."""
     lib = L.lib()
-    t = L.Tuning(stream_ctas_per_sm=-3, stream_hs=-1, stream_nst=99, stream_smem_kb=10 ** 6, stream_px8=7, ssim_tiles=-2, homo_tiles=5)
+    t = L.Tuning(stream_ctas_per_sm=-3, stream_hs=-1, stream_nst=99, stream_smem_kb=10 ** 6, stream_px8=7, ssim_tiles=-2, homo_tiles=5, stream_fwd_minb=7)
     lib.pd_set_tuning(C.byref(t))
     got = L.Tuning()
     lib.pd_get_tuning(C.byref(got))

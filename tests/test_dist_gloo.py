@@ -73,6 +73,63 @@ def test_two_rank_gloo_sharding_and_reductions():
     assert abs(got[0][4] - got[1][4]) < 1e-9
 
 
+def _ddp_worker(rank, ws, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(ws), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    import torch.nn as nn
+
+    from planedepth_b200 import dist as D
+
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        torch.manual_seed(0)  # identical replicas
+
+        class Net(nn.Module):  # a used trunk and a never-used head, like the ResNet encoder's fc layer
+            def __init__(self):
+                super().__init__()
+                self.trunk = nn.Conv2d(3, 4, 3, padding=1)
+                self.fc = nn.Linear(4, 10)
+
+            def forward(self, x):
+                return self.trunk(x)
+
+        net = Net()
+        g = torch.Generator().manual_seed(100 + rank)  # distinct shard per rank
+        x = torch.rand(2, 3, 8, 8, generator=g)
+        frozen = D.freeze_unused_parameters(net, lambda: net(x).square().mean())
+        assert frozen == 4 * 10 + 10 and not net.fc.weight.requires_grad and net.trunk.weight.requires_grad
+        ddp = nn.parallel.DistributedDataParallel(net)  # no find_unused_parameters: the static plan must hold for several steps
+        for _ in range(3):
+            for p in net.parameters():
+                p.grad = None
+            ddp(x).square().mean().backward()
+        # the all-reduce averaged the per-rank gradients: identical on both ranks, equal to the mean of the local ones
+        gsum = net.trunk.weight.grad.clone()
+        ref = [torch.zeros_like(gsum) for _ in range(ws)]
+        dist.all_gather(ref, gsum)
+        assert all(torch.equal(r, ref[0]) for r in ref)
+        q.put((rank, float(gsum.abs().sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_ddp_with_frozen_unused_parameters():
+    """The bench's ddp leg on CPU: DistributedDataParallel over gloo, world size 2, with the never-used parameters frozen by
+    dist.freeze_unused_parameters instead of find_unused_parameters=True."""
+    ws, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0, "rank exited with %s" % p.exitcode
+    got = sorted(q.get(timeout=5) for _ in range(ws))
+    assert abs(got[0][1] - got[1][1]) < 1e-12 and got[0][1] > 0
+
+
 def test_shard_range_partitions_exactly():
     from planedepth_b200.dist import aggregate_throughput, shard_range
 
