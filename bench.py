@@ -485,8 +485,12 @@ def run_ours(args):
         functional.KERNEL_TIMELINE = []
         n_roof = max(3, min(steps, 10))
         for _ in range(n_roof):
+            # The launches of an eager step are issued by Python far slower than the GPU executes them: an event pair
+            # around a call would also time the idle GPU waiting for the host to reach the launch.  A short device-side
+            # delay lets the host queue the whole step first, so every event pair brackets nothing but its kernels.
+            torch.cuda._sleep(4_000_000)  # ~2 ms at 1.97 GHz
             step()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
         per = {}
         for name, s, e in functional.KERNEL_TIMELINE:
             per.setdefault(name, []).append(s.elapsed_time(e))
