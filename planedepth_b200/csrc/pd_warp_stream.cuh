@@ -49,6 +49,7 @@ struct StreamCfg {
     int nblk;     // blocks per row group = ceil(N / hs)
     int ngroups;  // ceil(B * H / rpc)
     int nc;       // consumer threads (multiple of 32); the CTA has nc + 32 threads, the last warp produces
+    int l2_hint;  // streamed rows carry the L2 evict-first policy
 };
 
 constexpr int MAX_STAGES = 8;
@@ -119,6 +120,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tma_row(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// The [B,N,H,W] streams (logits, sigma, dense mask: 289 MB each at cfg 2) pass through the chip exactly once per kernel while
+// the per-pixel context around them (source colour, rgb_rec, statistics, upstream / unit gradients: ~100 MB) is produced by
+// one kernel of the step and consumed by the next.  The streamed rows therefore travel with an L2 evict-first policy, which
+// leaves the 126 MB L2 to the context.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_row_hint(float* dst, const float* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                  : "memory");
 }
 
@@ -289,6 +306,8 @@ __device__ __forceinline__ void producer_loop(const WarpParams& p, const StreamC
     const int W = p.d.W, H = p.d.H, N = p.d.N, rows_total = p.d.B * H;
     const uint32_t rowbytes = (uint32_t)(W * sizeof(float));
     const int streams = 1 + (MIX ? 1 : 0) + (DENSE ? 1 : 0);
+    const uint64_t pol = l2_evict_first_policy();
+    const bool hint = c.l2_hint != 0;
     int stage = 0, use = 0;  // use = how many times the ring wrapped
     for (int it = 0; it < nit; ++it) {
         const int g = blockIdx.x + it * gridDim.x;
@@ -319,9 +338,15 @@ __device__ __forceinline__ void producer_loop(const WarpParams& p, const StreamC
                     int64_t off = (((int64_t)b * N + n0) * H + y) * W;
                     size_t slot = ((size_t)(stage * c.hs) * c.rpc + r) * c.pitch + PAD;
                     for (int n = n0; n < n1; ++n) {
-                        tma_row(s.lring + slot, p.in.logits + off, rowbytes, bar);
-                        if (MIX) tma_row(s.sring + slot, p.in.sigma + off, rowbytes, bar);
-                        if (DENSE) tma_row(s.mring + slot, reinterpret_cast<const float*>(p.in.mask) + soff(p.d.mask_stride, b, n, y, 0), rowbytes, bar);
+                        if (hint) {
+                            tma_row_hint(s.lring + slot, p.in.logits + off, rowbytes, bar, pol);
+                            if (MIX) tma_row_hint(s.sring + slot, p.in.sigma + off, rowbytes, bar, pol);
+                            if (DENSE) tma_row_hint(s.mring + slot, reinterpret_cast<const float*>(p.in.mask) + soff(p.d.mask_stride, b, n, y, 0), rowbytes, bar, pol);
+                        } else {
+                            tma_row(s.lring + slot, p.in.logits + off, rowbytes, bar);
+                            if (MIX) tma_row(s.sring + slot, p.in.sigma + off, rowbytes, bar);
+                            if (DENSE) tma_row(s.mring + slot, reinterpret_cast<const float*>(p.in.mask) + soff(p.d.mask_stride, b, n, y, 0), rowbytes, bar);
+                        }
                         off += p.hw;
                         slot += (size_t)c.rpc * c.pitch;
                     }
@@ -996,6 +1021,7 @@ inline StreamCfg stream_cfg(const WarpParams& p, bool mix, bool dense, int ne_bw
     c.nblk = (p.d.N + c.hs - 1) / c.hs;
     if (c.nst > c.nblk) c.nst = c.nblk;  // reuse of the per-group buffers relies on nst <= nblk (see producer_loop)
     c.ngroups = (p.d.B * p.d.H + c.rpc - 1) / c.rpc;
+    c.l2_hint = tn.stream_no_l2_hint ? 0 : 1;
     return c;
 }
 
