@@ -103,6 +103,6 @@ if __name__ == "__main__":
     tag = sys.argv[1]
     launches(tag)
     full(tag)
-    for sfx in ("_cfg3", "_cfg4"):
+    for sfx in ("_cfg3", "_cfg4", "_resize"):
         full(tag, sfx)
     print("wrote profiles/%s_*" % tag)
