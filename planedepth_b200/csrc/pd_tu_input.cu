@@ -6,6 +6,11 @@
 // uint8 frame crosses PCIe (1.4 MB per KITTI frame whatever the training resolution; 4x fewer bytes than fp32 at 1280x384)
 // and one kernel does /255 + bicubic resize (+ crop) + clamp into the fp32 NCHW tensor the path reads.
 //
+// One thread per output pixel, 48 byte taps through L1.  A shared-memory tile variant (64 x 4 output pixels per CTA, source
+// window staged as floats, interleaved and channel-planar layouts) was built and measured in round 2: 31.5 / 43 us against
+// 33 us for this kernel at [12,3,192,640] <- 375 x 1242 — at a 2x reduction a 4-row tile needs 12 source rows, so staging
+// converts almost as many elements as the taps read — and was dropped.
+//
 // Arithmetic = ATen upsample_bicubic2d with align_corners=True: source coordinate s = o * (in - 1) / (out - 1) (scale formed
 // in fp32), cubic-convolution weights with A = -0.75, taps at floor(s) - 1 .. floor(s) + 2 with indices clamped to the image,
 // rows interpolated along x first, then along y.
@@ -79,72 +84,6 @@ __global__ void __launch_bounds__(256) resize_bicubic_u8_kernel(const ResizePara
     }
 }
 
-// Tile variant: a CTA produces a 64 x 4 output tile; the source window it needs (<= ~130 x 12 pixels at a 2x reduction) is
-// brought in once with coalesced byte loads, converted to float (/255) into shared memory, and the 16 taps per pixel are read
-// from there.  Same arithmetic and association as the direct kernel above.
-constexpr int RT_W = 64, RT_H = 4, RT_THREADS = RT_W * RT_H;
-
-template <bool HWC>
-__global__ void __launch_bounds__(RT_THREADS) resize_bicubic_u8_tile_kernel(const ResizeParams p, int Cmax) {
-    extern __shared__ float tile[];  // [R][Cmax * 3], pixel-interleaved
-    const int W = p.d.W, H = p.d.H, Hs = p.d.Hs, Ws = p.d.Ws;
-    const int b = blockIdx.z, X0 = blockIdx.x * RT_W, Y0 = blockIdx.y * RT_H;
-    const int xl = min(X0 + RT_W - 1, W - 1), yl = min(Y0 + RT_H - 1, H - 1);
-    // source window of the tile (taps floor - 1 .. floor + 2, clamped to the image like the taps themselves)
-    const int r_lo = min(max((int)floorf(p.sy * (float)(Y0 + p.d.y0)) - 1, 0), Hs - 1);
-    const int r_hi = min(max((int)floorf(p.sy * (float)(yl + p.d.y0)) + 2, 0), Hs - 1);
-    const int c_lo = min(max((int)floorf(p.sx * (float)(X0 + p.d.x0)) - 1, 0), Ws - 1);
-    const int c_hi = min(max((int)floorf(p.sx * (float)(xl + p.d.x0)) + 2, 0), Ws - 1);
-    const int R = r_hi - r_lo + 1, C3 = (c_hi - c_lo + 1) * 3, pitch = Cmax * 3;
-    const float k255 = 1.0f / 255.0f;
-    const int64_t img = (int64_t)b * 3 * Hs * Ws;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int r = wid; r < R; r += RT_THREADS / 32) {
-        const int ys = r_lo + r;
-        for (int q = lane; q < C3; q += 32) {
-            int64_t o;
-            if (HWC) {
-                o = img + ((int64_t)ys * Ws + c_lo) * 3 + q;
-            } else {
-                const int px = q / 3, ch = q - px * 3;
-                o = img + ((int64_t)ch * Hs + ys) * Ws + c_lo + px;
-            }
-            tile[r * pitch + q] = (float)__ldg(p.src + o) * k255;  // ToTensor: uint8 / 255
-        }
-    }
-    __syncthreads();
-    const int x = X0 + (threadIdx.x & (RT_W - 1)), y = Y0 + (threadIdx.x / RT_W);
-    if (x >= W || y >= H) return;
-    const float fy = p.sy * (float)(y + p.d.y0), fx = p.sx * (float)(x + p.d.x0);
-    const float fy0 = floorf(fy), fx0 = floorf(fx);
-    const int iy = (int)fy0, ix = (int)fx0;
-    float wy[4], wx[4];
-    cubic_weights(fy - fy0, wy);
-    cubic_weights(fx - fx0, wx);
-    int ro[4], co[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        ro[k] = (min(max(iy - 1 + k, 0), Hs - 1) - r_lo) * pitch;
-        co[k] = (min(max(ix - 1 + k, 0), Ws - 1) - c_lo) * 3;
-    }
-    float acc[3] = {0.0f, 0.0f, 0.0f};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float row[3] = {0.0f, 0.0f, 0.0f};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float* t = tile + ro[j] + co[k];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) row[c] = (k == 0) ? t[c] * wx[0] : fmaf(t[c], wx[k], row[c]);
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) acc[c] = (j == 0) ? row[c] * wy[0] : fmaf(row[c], wy[j], acc[c]);
-    }
-    const int64_t hw = (int64_t)H * W;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) p.dst[((int64_t)b * 3 + c) * hw + (int64_t)y * W + x] = fminf(fmaxf(acc[c], 0.0f), 1.0f);  // .clamp(0, 1)
-}
-
 }  // namespace
 
 extern "C" {
@@ -165,15 +104,6 @@ int pd_resize_bicubic_u8(const pd_resize_desc* d, const unsigned char* src, floa
     // ATen area_pixel_compute_scale(align_corners=True): (in - 1) / (out - 1) in fp32, 0 when out == 1
     p.sy = Hf > 1 ? (float)(d->Hs - 1) / (float)(Hf - 1) : 0.0f;
     p.sx = Wf > 1 ? (float)(d->Ws - 1) / (float)(Wf - 1) : 0.0f;
-    // tile kernel when the source window of a 64 x 4 output tile fits a modest shared-memory buffer (any usual loader scale)
-    const int Rmax = (int)(p.sy * (float)(RT_H - 1)) + 6, Cmax = (int)(p.sx * (float)(RT_W - 1)) + 6;
-    const size_t smem = (size_t)Rmax * Cmax * 3 * sizeof(float);
-    if (smem <= 40 * 1024 && d->B <= 65535 && !pd::tuning().resize_direct) {
-        const dim3 grid((d->W + RT_W - 1) / RT_W, (d->H + RT_H - 1) / RT_H, d->B);
-        if (d->src_layout == 0) resize_bicubic_u8_tile_kernel<true><<<grid, RT_THREADS, smem, (cudaStream_t)stream>>>(p, Cmax);
-        else resize_bicubic_u8_tile_kernel<false><<<grid, RT_THREADS, smem, (cudaStream_t)stream>>>(p, Cmax);
-        return check_launch("resize_bicubic_u8_tile");
-    }
     const int64_t total = (int64_t)d->B * d->H * d->W;
     const int64_t want = (total + 255) / 256, cap = (int64_t)pd::sm_count() * 16;
     const unsigned grid = (unsigned)(want < cap ? want : cap);

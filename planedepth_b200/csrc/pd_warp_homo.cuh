@@ -266,7 +266,10 @@ __device__ __forceinline__ float warp_reduce_scatter8(const float (&v)[8]) {
     return d;  // value index = 4*bit4 + 2*bit3 + bit2 of the lane
 }
 
-template <bool MIX>
+// FUSED: the upstream gradients arrive in pd_warp_grad_out's fused form (formed here from the photometric forward's unit
+// gradient); otherwise the prologue is the plain load of g_rgb_rec / g_nll.  Two instantiations: the generic prologue
+// (pointer tests, 64-bit offsets kept live) changed the register allocation of the plane loop and cost 10 % at cfg 4.
+template <bool MIX, bool FUSED>
 __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const float4* __restrict__ rgbx, float rcp_w, float rcp_h) {
     extern __shared__ __align__(16) float sh[];  // [N][12] parameters, then [N][9] dL/dH accumulators of the CTA
     const int N = p.d.N, W = p.d.W, H = p.d.H;
@@ -286,9 +289,34 @@ __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const 
     const float ry = fmaf(__ldg(ik + 4), fy, __ldg(ik + 3) * fx) + __ldg(ik + 5);
     const float rz = fmaf(__ldg(ik + 7), fy, __ldg(ik + 6) * fx) + __ldg(ik + 8);
 
-    const float gph = upstream_scale(p);
-    const int64_t gi = (int64_t)b * p.chw3 + rem;
-    const float g0 = upstream_rgb(p, gph, gi, pix), g1 = upstream_rgb(p, gph, gi + p.hw, pix), g2 = upstream_rgb(p, gph, gi + 2 * p.hw, pix);
+    float g0, g1, g2, gn_up = 0.0f;
+    if (FUSED) {
+        // common case first, shaped like the plain prologue: three loads of the unit gradient times one scalar; the optional
+        // extra terms (perceptual gradient, a genuine g_rgb_rec / g_nll on top) sit behind one uniform branch
+        const float gph = upstream_scale(p);
+        g0 = g1 = g2 = 0.0f;
+        if (p.gout.g_unit) {
+            const float* gp = p.gout.g_unit + (int64_t)b * p.chw3 + rem;
+            g0 = gph * __ldg(gp), g1 = gph * __ldg(gp + p.hw), g2 = gph * __ldg(gp + 2 * p.hw);
+        }
+        if (MIX && p.gout.g_unit_nll) gn_up = gph * __ldg(p.gout.g_unit_nll + pix);
+        if (p.gout.g_pred || p.gout.g_rgb_rec || p.gout.g_nll) {
+            const int64_t gi = (int64_t)b * p.chw3 + rem;
+            if (p.gout.g_pred) {
+                const float m = p.gout.mask_novel ? __ldg(p.gout.mask_novel + pix) : 1.0f;
+                g0 = fmaf(__ldg(p.gout.g_pred + gi), m, g0), g1 = fmaf(__ldg(p.gout.g_pred + gi + p.hw), m, g1);
+                g2 = fmaf(__ldg(p.gout.g_pred + gi + 2 * p.hw), m, g2);
+            }
+            if (p.gout.g_rgb_rec) {
+                g0 += __ldg(p.gout.g_rgb_rec + gi), g1 += __ldg(p.gout.g_rgb_rec + gi + p.hw), g2 += __ldg(p.gout.g_rgb_rec + gi + 2 * p.hw);
+            }
+            if (MIX && p.gout.g_nll) gn_up += __ldg(p.gout.g_nll + pix);
+        }
+    } else {
+        const float* gp = p.gout.g_rgb_rec + (int64_t)b * p.chw3 + rem;
+        g0 = __ldg(gp), g1 = __ldg(gp + p.hw), g2 = __ldg(gp + 2 * p.hw);
+        if (MIX) gn_up = p.gout.g_nll ? __ldg(p.gout.g_nll + pix) : 0.0f;
+    }
     const float* rp = p.out.rgb_rec + (int64_t)b * p.chw3 + rem;
     const float Gbar = g0 * __ldg(rp) + g1 * __ldg(rp + p.hw) + g2 * __ldg(rp + 2 * p.hw);
     const float* st = p.out.stats + (int64_t)b * (MIX ? PD_STATS_MIXTURE : PD_STATS_PLAIN) * p.hw + rem;
@@ -299,7 +327,7 @@ __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const 
         tr = __ldg(tp), tg = __ldg(tp + p.hw), tb = __ldg(tp + 2 * p.hw);
         Zinv = Sv / __ldg(st + 2 * p.hw);  // 1/Z, Z = sum pi/sigma = A/S
         const float D = __ldg(st + 3 * p.hw);
-        const float gn = upstream_nll(p, gph, pix);
+        const float gn = gn_up;
         gD = -gn / D;            // d loss / d D,  nll = -log D
         gDD = gD * (D - 1e-7f);  // = sum_k pi_k P_k
     }
@@ -423,8 +451,14 @@ inline void launch_homo_bwd(const WarpParams& p, const float4* rgbx, cudaStream_
     const unsigned grid = (unsigned)((int64_t)p.d.B * p.hw / HT);
     const size_t smem = (size_t)p.d.N * 21 * sizeof(float);
     const float rw = rows_rcp(p.d.W), rh = rows_rcp(p.d.H);
-    if (p.d.mixture) homo_bwd_kernel<true><<<grid, HT, smem, st>>>(p, rgbx, rw, rh);
-    else homo_bwd_kernel<false><<<grid, HT, smem, st>>>(p, rgbx, rw, rh);
+    const bool fused = p.gout.g_ph_sum != nullptr;
+    if (p.d.mixture) {
+        if (fused) homo_bwd_kernel<true, true><<<grid, HT, smem, st>>>(p, rgbx, rw, rh);
+        else homo_bwd_kernel<true, false><<<grid, HT, smem, st>>>(p, rgbx, rw, rh);
+    } else {
+        if (fused) homo_bwd_kernel<false, true><<<grid, HT, smem, st>>>(p, rgbx, rw, rh);
+        else homo_bwd_kernel<false, false><<<grid, HT, smem, st>>>(p, rgbx, rw, rh);
+    }
 }
 
 }  // namespace hm

@@ -19,6 +19,7 @@ KERNEL_TIMELINE = None
 #: Fold pd_photometric_bwd into the prologue of pd_warp_composite_bwd (pd_warp_grad_out's fused form): the photometric
 #: node's backward hands its operands (d loss / d ph_sum, the unit gradient saved by the forward, the perceptual term's
 #: gradient) to the warp node that produced its input instead of launching a kernel and writing g_rgb_rec to HBM.
+#: True: for the stereo (disp_warp) kernels; "all": every warp type (the ABI supports it everywhere; tests); False: never.
 FUSE_PHOTOMETRIC_BWD = True
 
 
@@ -250,13 +251,16 @@ def warp_composite(cfg: WarpConfig, src, tgt, logits, sigma=None, disp=None, mas
         hmat = _f32c(hmat, "hmat")
     if cam is not None:
         cam = _f32c(cam, "cam").detach()
-    link = _Link()
+    # the side channel to the photometric node exists for the stereo kernels only: their row prologue absorbs the fused form
+    # for free, while the thread-per-pixel homography / general backward kernels lose 10 % to it (measured, cfg 4)
+    link = _Link() if (cfg.warp_type == L.PD_WARP_DISP or FUSE_PHOTOMETRIC_BWD == "all") else None
     outs = _WarpComposite.apply(cfg, link, src.detach(), None if tgt is None else tgt.detach(), logits, sigma, disp, mask, hmat, cam)
     rgb_rec, nll, nll_auto = outs[:3]
     # photometric_loss() finds the producer through these attributes (the dict contract hands the same objects over)
-    rgb_rec._pd_link = link
-    if cfg.mixture:
-        nll._pd_link = link
+    if link is not None:
+        rgb_rec._pd_link = link
+        if cfg.mixture:
+            nll._pd_link = link
     layered = None
     if cfg.layered:
         names = ["rgb_rec_layered", "logit_rec", "probability_rec"] + (["sigma_rec", "pi_rec"] if cfg.mixture else [])

@@ -298,11 +298,41 @@ def test_unfused_photometric_backward_matches_oracle(idx):
         names = [n for n, _, _ in functional.KERNEL_TIMELINE]
     finally:
         functional.KERNEL_TIMELINE = None
-    assert "pd_photometric_bwd" not in names and "pd_warp_composite_bwd" in names
+    # only the stereo kernels absorb the fused form (the thread-per-pixel kernels lose 10 % to it: functional.warp_composite)
+    assert ("pd_photometric_bwd" not in names) == (cfg[4] == "disp_warp") and "pd_warp_composite_bwd" in names
     for k, leaf in cg.leaves.items():
         if leaf.grad is not None:
             scale = float(leaf.grad.abs().max()) + 1e-12
             check(cg2.leaves[k].grad, leaf.grad, 1e-5 * scale, "fused vs unfused grad_" + k, allow_frac=1e-4)
+
+
+@pytest.mark.parametrize("idx", [4, 5, 6, 7, 3])
+def test_fused_upstream_form_on_every_kernel_family(idx):
+    """pd_warp_grad_out's fused fields are part of the ABI for every warp type (homography fast path, general kernels for
+    depth_warp / dense disparities), although the Python boundary only uses them for disp_warp."""
+    from planedepth_b200 import functional
+
+    cfg = CONFIGS[idx]
+    cc = build_on("cpu", cfg, seed=800 + idx)
+    cg = build_on("cuda", cfg, seed=800 + idx)
+    lo = O.hot_path(cc.opt, cc.target_sides, cc.inputs, cc.outputs, pyramid_features)
+    lo["loss/total_loss"].backward()
+    functional.FUSE_PHOTOMETRIC_BWD = "all"
+    try:
+        functional.KERNEL_TIMELINE = []
+        lg = run_cuda(cg, None, "fused")
+        names = [n for n, _, _ in functional.KERNEL_TIMELINE]
+    finally:
+        functional.FUSE_PHOTOMETRIC_BWD = True
+        functional.KERNEL_TIMELINE = None
+    assert "pd_photometric_bwd" not in names
+    for k in lo:
+        check(lg[k], lo[k], TOL, k)
+    for k, leaf in cc.leaves.items():
+        if leaf.grad is None:
+            continue
+        scale = float(leaf.grad.abs().max()) + 1e-12
+        check(cg.leaves[k].grad, leaf.grad, grad_tol(k) * scale, "grad_" + k, allow_frac=2e-3)
 
 
 def test_rowwise_promise_is_verified_not_trusted():

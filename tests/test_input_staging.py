@@ -37,13 +37,9 @@ def test_oracle_resize_matches_torch_interpolate(case):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("direct", [False, True])
 @pytest.mark.parametrize("layout", ["hwc", "chw"])
 @pytest.mark.parametrize("case", CASES)
-def test_cuda_resize_matches_oracle(case, layout, direct):
-    """Both kernels: the shared-memory tile kernel (default) and the one-thread-per-pixel kernel (large reductions, or
-    pd_tuning.resize_direct)."""
-    from planedepth_b200 import _lib
+def test_cuda_resize_matches_oracle(case, layout):
     from planedepth_b200.functional import resize_frames_u8
 
     Hs, Ws, size, full, crop = case
@@ -53,8 +49,7 @@ def test_cuda_resize_matches_oracle(case, layout, direct):
     dev = frames.cuda()
     if layout == "hwc":
         dev = dev.permute(0, 2, 3, 1).contiguous()
-    with _lib.tuned(resize_direct=int(direct)):
-        got = resize_frames_u8(dev, size, full, crop)
+    got = resize_frames_u8(dev, size, full, crop)
     assert got.shape == want.shape and got.dtype == torch.float32
     err = (got.cpu() - want).abs().max().item()
     assert err <= 1e-5, err  # fp32 sums of 16 taps in a different association; values in [0, 1]
