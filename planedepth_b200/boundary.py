@@ -93,6 +93,10 @@ class _RowwiseView(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        if g.stride(3) == 0:
+            # the kernels hand the x-reduced gradient back already spread evenly over x (a stride-0 view): sum / w of equal
+            # values is the value itself, no [B,N,H,W] reduction needed
+            return g
         return (g.sum(3, keepdim=True) / ctx.w).expand(-1, -1, -1, ctx.w)
 
 
