@@ -70,6 +70,8 @@ def _stream() -> int:
 
 
 def _f32c(t: torch.Tensor, what: str) -> torch.Tensor:
+    """fp32, contiguous, on the device.  Other dtypes (e.g. bf16 network outputs under autocast) are UPCAST here with torch: a
+    convenience at the boundary, not a storage format — the kernels compute and stream fp32 only."""
     if t.device.type != "cuda":
         raise L.PlaneDepthLibraryError("%s must be a CUDA tensor (planedepth_b200 has no CPU path)" % what)
     if t.dtype != torch.float32:

@@ -526,11 +526,12 @@ def test_smooth_loss_matches_oracle(shape, x0, gamma):
 
 
 # ------------------------------------------------------------------------------------------------
-# bf16 storage of the network outputs (BASELINE.md parity gate: <= 2e-2): the boundary accepts bf16 logits / sigma,
-# computes in fp32 and hands bf16 gradients back
+# bf16 network outputs at the boundary (BASELINE.md parity gate: <= 2e-2).  This is an INPUT CONVENIENCE, not a storage format:
+# functional._f32c upcasts bf16 logits / sigma with torch before the fp32 kernels run and autograd casts the gradients back; the
+# kernels never read or write bf16 (DESIGN.md section 8 says why a bf16 stream would not make the issue-bound kernels faster)
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("idx", [0, 2])
-def test_bf16_storage_within_2e_2(idx):
+def test_bf16_inputs_are_upcast_within_2e_2(idx):
     cfg = CONFIGS[idx]
     cc = build_on("cpu", cfg, seed=500 + idx)
     cg = build_on("cuda", cfg, seed=500 + idx)
@@ -542,12 +543,12 @@ def test_bf16_storage_within_2e_2(idx):
             leaves16[k] = cg.outputs[k].detach().to(torch.bfloat16).requires_grad_(True)
             cg.outputs[k] = leaves16[k]
     lg = run_cuda(cg, None, "fused")
-    check(cg.outputs[("rgb_rec", "r")], cc.outputs[("rgb_rec", "r")], 2e-2, "rgb_rec (bf16 storage)")
-    check(lg["loss/total_loss"], lo["loss/total_loss"], 2e-2, "total loss (bf16 storage)")
+    check(cg.outputs[("rgb_rec", "r")], cc.outputs[("rgb_rec", "r")], 2e-2, "rgb_rec (bf16 inputs)")
+    check(lg["loss/total_loss"], lo["loss/total_loss"], 2e-2, "total loss (bf16 inputs)")
     for k, leaf in leaves16.items():
         assert leaf.grad is not None and leaf.grad.dtype == torch.bfloat16
         want = cc.leaves[k].grad
-        check(leaf.grad.float(), want, 2e-2 * float(want.abs().max()), "grad_%s (bf16 storage)" % k, allow_frac=2e-3)
+        check(leaf.grad.float(), want, 2e-2 * float(want.abs().max()), "grad_%s (bf16 inputs)" % k, allow_frac=2e-3)
 
 
 # ------------------------------------------------------------------------------------------------
