@@ -180,16 +180,17 @@ def gpu_cpu_affinity(index):
         return None
 
 
-def algorithmic_bytes(B, N, H, W, mixture):
-    """SURVEY.md §8(d) per image per target frame, fp32; X1 = H*W*4.
+def algorithmic_bytes(B, N, H, W, mixture, elem=4):
+    """SURVEY.md §8(d) per image per target frame; X1 = H*W*4; `elem` = bytes per stored logit / sigma / gradient element
+    (4, or 2 with bf16 storage, which halves the N-terms).
     warp fwd: N(1+m) logits/sigma + 3 src + 3 rgb_rec (+3 tgt, +1 nll with mixture)
     warp bwd: 2N(1+m) (re-read, write grads) + 3 src + 3 g_rgb_rec + 3 rgb_rec/tgt
     loss fwd: 3 rgb_rec + 3 tgt (+1 ph map) ; loss bwd: 3 rgb_rec + 3 tgt + 3 g_rgb_rec."""
     x1 = H * W * 4
     m = 1 if mixture else 0
     return {
-        "pd_warp_composite_fwd": B * x1 * (N * (1 + m) + 6 + 4 * m),
-        "pd_warp_composite_bwd": B * x1 * (2 * N * (1 + m) + 9),
+        "pd_warp_composite_fwd": B * x1 * (N * (1 + m) * elem / 4 + 6 + 4 * m),
+        "pd_warp_composite_bwd": B * x1 * (2 * N * (1 + m) * elem / 4 + 9),
         "pd_photometric_fwd": B * x1 * 6,
         "pd_photometric_bwd": B * x1 * 9,
     }
@@ -346,6 +347,13 @@ def run_ours(args):
         batch_gpu = make_batch(B, H, W, opt, seed=seed, device=dev, layout=args.layout, mask_novel=mnov)
         outputs, leaves_map = batch_gpu.outputs, batch_gpu.leaves
         inputs = batch_gpu.inputs
+        if args.storage == "bf16":
+            # secondary configuration: the network outputs are stored as bf16 (pd_warp_desc.dtype), gradients come back as bf16
+            for k in ("logits", "sigma"):
+                if k in leaves_map:
+                    leaves_map[k] = leaves_map[k].detach().to(torch.bfloat16).requires_grad_(True)
+                    outputs[k] = leaves_map[k]
+            outputs["probability"] = outputs["logits"].detach()
         leaves = list(leaves_map.values())
         # the integration patch promises x-constant disparities whenever the decoder has no yz planes
         hp = HotPath(opt, batch.target_sides, pc_net=None, photometric=photometric, disp_rowwise=(getattr(opt, "yz_levels", 0) == 0) and not args.no_rowwise)
@@ -497,7 +505,7 @@ def run_ours(args):
         functional.KERNEL_TIMELINE = None
         avg_ms = {k: sum(v) / len(v) for k, v in per.items()}
         dom = max(avg_ms, key=avg_ms.get)
-        alg = algorithmic_bytes(B, N, H, W, opt.use_mixture_loss)  # per launch (= per target side)
+        alg = algorithmic_bytes(B, N, H, W, opt.use_mixture_loss, 2 if args.storage == "bf16" else 4)  # per launch (= per target side)
         n_calls = {k: len(v) / n_roof for k, v in per.items()}  # launches per step
         peak, peak_src = peaks()
         achieved = alg[dom] / (avg_ms[dom] * 1e-3) / 1e9
@@ -533,7 +541,7 @@ def run_ours(args):
         return {
             "metric": METRIC, "value": D.aggregate_throughput(B, ws, ms_step), "unit": UNIT, "n_gpus": ws, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * ws, "planes": N, "height": H, "width": W,
+            "config": {"workload": desc, "storage": "bf16 logits / sigma / gradients, fp32 arithmetic" if args.storage == "bf16" else "fp32", "batch_per_gpu": B, "global_batch": B * ws, "planes": N, "height": H, "width": W,
                        "photometric": photometric or ("mixture" if opt.use_mixture_loss else "l1"), "layout": args.layout,
                        "rowwise_promise": bool((getattr(opt, "yz_levels", 0) == 0) and not args.no_rowwise),
                        "parallelism": "dp%d (independent shards; the path itself has no collective - see the ddp leg)" % ws,
@@ -789,6 +797,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-fuse-bwd", action="store_true", help="keep pd_photometric_bwd as its own launch (diagnostic)")
+    ap.add_argument("--storage", default="fp32", choices=["fp32", "bf16"],
+                    help="bf16: logits / sigma and their gradients are stored as bf16 (secondary configuration; arithmetic stays fp32)")
     ap.add_argument("--e2e-fp32", action="store_true", help="headline e2e ships fp32 colour tensors (the reference's transport) instead of raw uint8 frames")
     ap.add_argument("--no-numa-pin", action="store_true", help="do not move the process to the GPU's NUMA node for the e2e leg")
     ap.add_argument("--no-ddp-leg", action="store_true", help="skip the producer + DistributedDataParallel training-step leg")

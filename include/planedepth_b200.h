@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PD_ABI_VERSION 8
+#define PD_ABI_VERSION 9
 
 typedef void* pd_stream_t; /* a cudaStream_t */
 
@@ -41,7 +41,8 @@ typedef enum pd_status {
     PD_ERR_ALIGN = 3,     /* pointer / stride alignment */
     PD_ERR_ARCH = 4,      /* device is not sm_100 */
     PD_ERR_CUDA = 5,      /* a CUDA runtime call failed (message in pd_last_error) */
-    PD_ERR_WORKSPACE = 6  /* workspace NULL while pd_*_workspace_bytes() > 0 */
+    PD_ERR_WORKSPACE = 6, /* workspace NULL while pd_*_workspace_bytes() > 0 */
+    PD_ERR_UNSUPPORTED = 7 /* valid request no kernel is built for (bf16 storage outside the streamed stereo path) */
 } pd_status;
 
 #define PD_MAX_PLANES 256
@@ -65,6 +66,13 @@ typedef enum pd_mask_dtype { PD_MASK_NONE = 0, PD_MASK_F32 = 1, PD_MASK_U8 = 2 }
  * statistics then say "read every mask row" and the backward streams the mask again); a measurement knob. */
 typedef enum pd_warp_flags { PD_FLAG_EXACT_COORDS = 1, PD_FLAG_NO_MASK_SUMMARY = 2 } pd_warp_flags;
 
+/* Storage type of the [B,N,H,W] network outputs and of their gradients (pd_warp_desc.dtype): logits, sigma, g_logits,
+ * g_sigma.  Everything else (colours, rgb_rec, statistics, nll, plane geometry, masks) is fp32 whatever this says, and all
+ * arithmetic is fp32.  PD_DTYPE_BF16 is implemented by the streamed stereo kernels (disp_warp, x-constant disparity, no
+ * mask or a row mask, W % 8 == 0, no debug outputs, no PD_FLAG_EXACT_COORDS): pd_warp_composite_supports() says whether a
+ * descriptor is served; other requests return PD_ERR_UNSUPPORTED (the Python boundary then upcasts with torch). */
+typedef enum pd_dtype { PD_DTYPE_F32 = 0, PD_DTYPE_BF16 = 1 } pd_dtype;
+
 typedef struct pd_strides4 {
     int64_t b, n, y, x;
 } pd_strides4;
@@ -82,6 +90,8 @@ typedef struct pd_warp_desc {
     int32_t mask_dtype;     /* pd_mask_dtype of pd_warp_in.mask */
     float disp_sign;        /* PD_WARP_DISP: +1 target 'r', -1 target 'l', 0 otherwise (trainer.py:545-548) */
     int32_t flags;          /* bit set of pd_warp_flags */
+    int32_t dtype;          /* pd_dtype of logits / sigma / g_logits / g_sigma (the pointers below are then bf16 arrays) */
+    int32_t reserved0;
     pd_strides4 disp_stride; /* PD_WARP_DISP / PD_WARP_DEPTH: strides of disp_layered (0 allowed:
                                 depth_decoder.py:156 hands out a stride-0 expand) */
     pd_strides4 mask_stride; /* strides of padding_mask */
@@ -183,6 +193,10 @@ int pd_x_constant_check(const void* data, int32_t dtype /* pd_mask_dtype: PD_MAS
  * for the homography fast path only: the source colour re-packed to one rgbx float4 per pixel. */
 size_t pd_warp_composite_workspace_bytes(const pd_warp_desc* desc);
 size_t pd_warp_composite_stats_bytes(const pd_warp_desc* desc);
+
+/* 1 if pd_warp_composite_fwd / _bwd serve this descriptor + pointer set (strides, alignment, dtype), else 0.  Only the
+ * dtype question can come back 0 for otherwise valid arguments. */
+int pd_warp_composite_supports(const pd_warp_desc* desc, const pd_warp_in* in);
 
 int pd_warp_composite_fwd(const pd_warp_desc* desc, const pd_warp_in* in, pd_warp_out* out,
                           void* workspace, pd_stream_t stream);

@@ -22,8 +22,9 @@ PD_LOSS_L1, PD_LOSS_MIXTURE, PD_LOSS_SSIM_L1 = 0, 1, 2
 PD_MASK_NONE, PD_MASK_F32, PD_MASK_U8 = 0, 1, 2
 PD_FLAG_EXACT_COORDS = 1
 PD_FLAG_NO_MASK_SUMMARY = 2
-ABI_VERSION = 8  # PD_ABI_VERSION in include/planedepth_b200.h
+ABI_VERSION = 9  # PD_ABI_VERSION in include/planedepth_b200.h
 PD_STATS_PLAIN, PD_STATS_MIXTURE = 2, 4
+PD_DTYPE_F32, PD_DTYPE_BF16 = 0, 1
 
 EXPORTS = [
     "pd_version", "pd_last_error", "pd_launch_count", "pd_reset_launch_count",
@@ -32,7 +33,7 @@ EXPORTS = [
     "pd_occlusion_masks_workspace_bytes", "pd_occlusion_masks_fwd",
     "pd_smooth_loss_workspace_bytes", "pd_smooth_loss_fwd", "pd_smooth_loss_bwd",
     "pd_plane_tail_fwd", "pd_plane_tail_bwd",
-    "pd_get_tuning", "pd_set_tuning", "pd_x_constant_check", "pd_resize_bicubic_u8",
+    "pd_get_tuning", "pd_set_tuning", "pd_x_constant_check", "pd_resize_bicubic_u8", "pd_warp_composite_supports",
 ]
 
 
@@ -44,7 +45,7 @@ class WarpDesc(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("warp_type", C.c_int32), ("mixture", C.c_int32), ("automask", C.c_int32), ("mask_dtype", C.c_int32),
-        ("disp_sign", C.c_float), ("flags", C.c_int32),
+        ("disp_sign", C.c_float), ("flags", C.c_int32), ("dtype", C.c_int32), ("reserved0", C.c_int32),
         ("disp_stride", Strides4), ("mask_stride", Strides4),
     ]
 
@@ -284,6 +285,8 @@ def lib() -> C.CDLL:
     L.pd_warp_composite_workspace_bytes.argtypes = [C.POINTER(WarpDesc)]
     L.pd_warp_composite_stats_bytes.restype = C.c_size_t
     L.pd_warp_composite_stats_bytes.argtypes = [C.POINTER(WarpDesc)]
+    L.pd_warp_composite_supports.restype = C.c_int
+    L.pd_warp_composite_supports.argtypes = [C.POINTER(WarpDesc), C.POINTER(WarpIn)]
     L.pd_warp_composite_fwd.restype = C.c_int
     L.pd_warp_composite_fwd.argtypes = [C.POINTER(WarpDesc), C.POINTER(WarpIn), C.POINTER(WarpOut), C.c_void_p, C.c_void_p]
     L.pd_warp_composite_bwd.restype = C.c_int

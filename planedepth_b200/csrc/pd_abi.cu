@@ -158,6 +158,7 @@ int validate_warp(const pd_warp_desc* d, const pd_warp_in* in) {
     if (d->N > PD_MAX_PLANES) return fail(PD_ERR_SHAPE, "N=%d exceeds PD_MAX_PLANES", d->N);
     if ((int64_t)d->H * d->W >= (1ll << 31)) return fail(PD_ERR_SHAPE, "H*W too large");
     if (d->warp_type < PD_WARP_DISP || d->warp_type > PD_WARP_DEPTH) return fail(PD_ERR_ARG, "bad warp_type %d", d->warp_type);
+    if (d->dtype != PD_DTYPE_F32 && d->dtype != PD_DTYPE_BF16) return fail(PD_ERR_ARG, "bad dtype %d", d->dtype);
     if (!in->src || !in->logits) return fail(PD_ERR_ARG, "src / logits must not be NULL");
     if (d->mixture && (!in->sigma || !in->tgt)) return fail(PD_ERR_ARG, "mixture needs sigma and tgt");
     if (d->warp_type == PD_WARP_HOMOGRAPHY) {
@@ -255,6 +256,15 @@ size_t pd_warp_composite_stats_bytes(const pd_warp_desc* d) {
     return stats_floats(d) * sizeof(float) + mask_summary_bytes(d);
 }
 
+int pd_warp_composite_supports(const pd_warp_desc* d, const pd_warp_in* in) {
+    if (validate_warp(d, in)) return 0;
+    if (d->dtype == PD_DTYPE_F32) return 1;
+    // bf16: the streamed forward AND backward must find a configuration (dry runs; mask / stride / alignment rules included)
+    pd::WarpParams p = make_params(d, in);
+    if (exact_coords(d) || !api::stream_supported(p)) return 0;
+    return (api::stream_fwd_fits(p) && api::stream_bwd_fits(p)) ? 1 : 0;
+}
+
 int pd_warp_composite_fwd(const pd_warp_desc* d, const pd_warp_in* in, pd_warp_out* out, void* workspace, pd_stream_t stream) {
     int rc = validate_warp(d, in);
     if (rc) return rc;
@@ -267,6 +277,11 @@ int pd_warp_composite_fwd(const pd_warp_desc* d, const pd_warp_in* in, pd_warp_o
     unsigned long long* slot = mask_summary_slot(p, out->stats);
     const bool debug = out->rgb_rec_layered || out->logit_rec || out->probability_rec || out->sigma_rec || out->pi_rec;
     const bool streamed = !debug && !exact_coords(d) && api::stream_supported(p);
+    if (d->dtype == PD_DTYPE_BF16) {
+        // bf16 storage exists in the streamed stereo kernels only; nothing else may reinterpret the bf16 arrays as fp32
+        if (streamed && api::stream_fwd(p, st)) return check_launch("rows_fwd_stream_bf16");
+        return fail(PD_ERR_UNSUPPORTED, "bf16 storage is served by the streamed stereo kernels only (see pd_warp_composite_supports)");
+    }
     // bit n of a row = "plane n's mask row is not all ones".  Only the streamed forward produces the summary (it ORs bits
     // into a cleared slot); in every other case the slot says "read every mask row"
     const bool summarise = streamed && slot && !(d->flags & PD_FLAG_NO_MASK_SUMMARY);
@@ -314,6 +329,7 @@ int pd_warp_composite_bwd(const pd_warp_desc* d, const pd_warp_in* in, const pd_
     const size_t plane_bytes = (size_t)d->B * d->N * p.hw * sizeof(float);
     cudaError_t e = cudaSuccess;
     const bool streamed = !exact_coords(d) && api::stream_supported(p) && api::stream_bwd_fits(p);
+    if (d->dtype == PD_DTYPE_BF16 && !streamed) return fail(PD_ERR_UNSUPPORTED, "bf16 storage is served by the streamed stereo kernels only (see pd_warp_composite_supports)");
     const bool rows = !streamed && api::rows_supported(p);
     // scatter targets are accumulated with atomics in the general / homography paths: zero them first
     if (!streamed && !rows) {

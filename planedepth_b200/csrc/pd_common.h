@@ -29,6 +29,7 @@ int resident_ctas(const void* kernel, int threads, size_t smem);
 namespace api {
 // streamed row kernels (pd_tu_stream_fwd.cu / pd_tu_stream_bwd.cu)
 bool stream_supported(const WarpParams& p);
+bool stream_fwd_fits(const WarpParams& p);
 bool stream_bwd_fits(const WarpParams& p);
 bool stream_fwd(const WarpParams& p, cudaStream_t st);  // false = no launch configuration
 bool stream_bwd(const WarpParams& p, cudaStream_t st);

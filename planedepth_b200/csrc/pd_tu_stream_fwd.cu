@@ -5,6 +5,7 @@
 namespace pd {
 namespace api {
 bool stream_supported(const WarpParams& p) { return ts::stream_path_supported(p); }
+bool stream_fwd_fits(const WarpParams& p) { return ts::launch_fwd_stream(p, nullptr, true); }  // dry run of the launcher
 bool stream_fwd(const WarpParams& p, cudaStream_t st) { return ts::launch_fwd_stream(p, st); }
 }  // namespace api
 }  // namespace pd

@@ -50,6 +50,7 @@ struct StreamCfg {
     int ngroups;  // ceil(B * H / rpc)
     int nc;       // consumer threads (multiple of 32); the CTA has nc + 32 threads, the last warp produces
     int l2_hint;  // streamed rows carry the L2 evict-first policy
+    int bf16;     // logits / sigma / their gradients are stored as bf16 (pd_warp_desc.dtype)
 };
 
 constexpr int MAX_STAGES = 8;
@@ -214,20 +215,29 @@ struct Smem {
     float* sring;     // mixture: [nst*hs][rpc][pitch]
     float* mring;     // dense mask: [nst*hs][rpc][pitch]
     float* dbuf;      // backward: [2][hs][NE][rpc][pitch] exchange rows (NE = 1, mixture 2)
+    float* cbuf;      // bf16 storage: [2][hs][1 + mix][rpc][pitch] rows converted to fp32 by the consumers, double-buffered over blocks
     float* gacc;      // backward with d/d disp: [rpc][N]
     float* fend;      // one past the last float
+    unsigned char* bring;  // bf16 storage: TMA ring of raw bf16 rows [nst*hs][1 + mix][rpc][W * 2 bytes] (behind the float region)
 };
 
 __host__ __device__ inline size_t stream_smem_floats(const StreamCfg& c, int N, bool mix, bool dense, int ne_bwd, bool want_disp) {
     size_t rowf = (size_t)c.rpc * c.pitch;
-    size_t f = 2 * 3 * rowf + (size_t)c.nst * c.hs * rowf * (1 + (mix ? 1 : 0) + (dense ? 1 : 0));
+    const size_t streams = c.bf16 ? (dense ? 1 : 0) : (1 + (mix ? 1 : 0) + (dense ? 1 : 0));  // fp32 ring rows
+    size_t f = 2 * 3 * rowf + (size_t)c.nst * c.hs * rowf * streams;
     f += (size_t)2 * c.hs * ne_bwd * rowf;
+    if (c.bf16) f += (size_t)2 * c.hs * (1 + (mix ? 1 : 0)) * rowf;  // cbuf
     if (want_disp) f += (size_t)c.rpc * N;
     return f;
 }
 
+// bytes of one raw bf16 row in the TMA ring (W % 8 == 0: a multiple of 16)
+__host__ __device__ inline size_t stream_bf16_row_bytes(const StreamCfg& c) { return (size_t)(c.pitch - 2 * PAD) * 2; }
+
 __host__ __device__ inline size_t stream_smem_bytes(const StreamCfg& c, int N, bool mix, bool dense, int ne_bwd, bool want_disp) {
-    return BAR_BYTES + (size_t)2 * c.rpc * N * sizeof(PlaneCoef) + stream_smem_floats(c, N, mix, dense, ne_bwd, want_disp) * sizeof(float) + 16;
+    size_t b = BAR_BYTES + (size_t)2 * c.rpc * N * sizeof(PlaneCoef) + stream_smem_floats(c, N, mix, dense, ne_bwd, want_disp) * sizeof(float) + 16;
+    if (c.bf16) b += (size_t)c.nst * c.hs * (1 + (mix ? 1 : 0)) * c.rpc * stream_bf16_row_bytes(c) + 16;
+    return b;
 }
 
 __device__ __forceinline__ Smem carve(unsigned char* raw, const StreamCfg& c, int N, bool mix, bool dense, int ne_bwd, bool want_disp) {
@@ -237,16 +247,20 @@ __device__ __forceinline__ Smem carve(unsigned char* raw, const StreamCfg& c, in
     s.coef = reinterpret_cast<PlaneCoef*>(raw + BAR_BYTES);
     s.src = reinterpret_cast<float*>(s.coef + (size_t)2 * c.rpc * N);
     s.lring = s.src + 2 * 3 * rowf;
-    float* q = s.lring + (size_t)c.nst * c.hs * rowf;
+    float* q = s.lring;
+    if (!c.bf16) q += (size_t)c.nst * c.hs * rowf;
     s.sring = q;
-    if (mix) q += (size_t)c.nst * c.hs * rowf;
+    if (mix && !c.bf16) q += (size_t)c.nst * c.hs * rowf;
     s.mring = q;
     if (dense) q += (size_t)c.nst * c.hs * rowf;
     s.dbuf = q;
     q += (size_t)2 * c.hs * ne_bwd * rowf;
+    s.cbuf = q;
+    if (c.bf16) q += (size_t)2 * c.hs * (1 + (mix ? 1 : 0)) * rowf;
     s.gacc = q;
     if (want_disp) q += (size_t)c.rpc * N;
     s.fend = q;
+    s.bring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(q) + 15) & ~(uintptr_t)15);
     return s;
 }
 
@@ -299,9 +313,10 @@ __device__ __forceinline__ void stage_coef(const WarpParams& p, const StreamCfg&
 // arms the stage's full barrier with the byte count and issues one bulk copy per (plane, row, stream).
 // Releases that make reuse safe: the stage's empty barrier is armed by the consumers after their last read
 // of block jb - nst; with nst <= nblk that also covers the coefficient / source-row buffers of group it - 2.
-template <bool MIX, int MASKMODE>
+template <bool MIX, int MASKMODE, bool BF16 = false>
 __device__ __forceinline__ void producer_loop(const WarpParams& p, const StreamCfg& c, const Smem& s, int nit) {
     constexpr bool DENSE = (MASKMODE == SMASK_DENSE);
+    static_assert(!(BF16 && DENSE), "bf16 storage is built for row masks only");
     const int lane = threadIdx.x & 31;
     const int W = p.d.W, H = p.d.H, N = p.d.N, rows_total = p.d.B * H;
     const uint32_t rowbytes = (uint32_t)(W * sizeof(float));
@@ -330,7 +345,32 @@ __device__ __forceinline__ void producer_loop(const WarpParams& p, const StreamC
                 }
             }
             const int n0 = j * c.hs, n1 = min(N, n0 + c.hs);
-            if (lane == 0) {
+            if (BF16) {
+                // raw bf16 rows: [stage][plane][logit | sigma][row][W * 2 bytes]; the consumers convert them (see bf16_convert_block)
+                if (lane == 0) {
+                    uint64_t* bar = s.bars + BAR_FULL + stage;
+                    const uint32_t rb = rowbytes / 2;
+                    constexpr int NEc = MIX ? 2 : 1;
+                    mbar_expect_tx(bar, (uint32_t)((n1 - n0) * nrows * NEc) * rb);
+                    const unsigned char* lg = reinterpret_cast<const unsigned char*>(p.in.logits);
+                    const unsigned char* sg = reinterpret_cast<const unsigned char*>(p.in.sigma);
+                    for (int r = 0; r < nrows; ++r) {
+                        const int row = row0 + r, b = row / H, y = row - b * H;
+                        int64_t off = ((((int64_t)b * N + n0) * H + y) * W) * 2;
+                        unsigned char* dst = s.bring + ((size_t)(stage * c.hs) * NEc * c.rpc + r) * rb;
+                        for (int n = n0; n < n1; ++n) {
+                            if (hint) tma_row_hint(reinterpret_cast<float*>(dst), reinterpret_cast<const float*>(lg + off), rb, bar, pol);
+                            else tma_row(reinterpret_cast<float*>(dst), reinterpret_cast<const float*>(lg + off), rb, bar);
+                            if (MIX) {
+                                if (hint) tma_row_hint(reinterpret_cast<float*>(dst + (size_t)c.rpc * rb), reinterpret_cast<const float*>(sg + off), rb, bar, pol);
+                                else tma_row(reinterpret_cast<float*>(dst + (size_t)c.rpc * rb), reinterpret_cast<const float*>(sg + off), rb, bar);
+                            }
+                            off += p.hw * 2;
+                            dst += (size_t)NEc * c.rpc * rb;
+                        }
+                    }
+                }
+            } else if (lane == 0) {
                 uint64_t* bar = s.bars + BAR_FULL + stage;
                 mbar_expect_tx(bar, (uint32_t)((n1 - n0) * nrows * streams) * rowbytes);
                 for (int r = 0; r < nrows; ++r) {
@@ -380,6 +420,40 @@ __device__ __forceinline__ bool all_ones(const float (&m)[PX]) {
 #pragma unroll
     for (int i = 0; i < PX; ++i) acc &= __float_as_uint(m[i]), orr |= __float_as_uint(m[i]);
     return acc == 0x3f800000u && orr == 0x3f800000u;
+}
+
+// bf16 storage: every consumer thread converts the PX values it owns of each plane row of the block that just landed (raw bf16,
+// TMA ring) into the double-buffered fp32 rows the tap windows read; the ring stage is free again right after this
+template <bool MIX, int PX>
+__device__ __forceinline__ void bf16_convert_block(uint32_t braw, uint32_t crow, uint32_t rb_rpc, uint32_t rowpitch4, int np) {
+    // braw: shared address of this thread's PX bf16 values in the first plane's logit row; crow: of its PX floats in cbuf
+    constexpr int NEc = MIX ? 2 : 1;
+    for (int q = 0; q < np; ++q, braw += NEc * rb_rpc, crow += NEc * rowpitch4) {
+#pragma unroll
+        for (int e = 0; e < NEc; ++e) {
+#pragma unroll
+            for (int i = 0; i < PX / 4; ++i) {
+                uint32_t lo, hi;
+                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(braw + e * rb_rpc + 8 * i));
+                sts128(crow + e * rowpitch4 + 16 * i, __uint_as_float(lo << 16), __uint_as_float(lo & 0xffff0000u), __uint_as_float(hi << 16),
+                       __uint_as_float(hi & 0xffff0000u));
+            }
+        }
+    }
+}
+
+// round-to-nearest-even bf16 pair (x -> low half, y -> high half)
+__device__ __forceinline__ uint32_t pack_bf16x2(float x, float y) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
+    return r;
+}
+
+template <int PX>
+__device__ __forceinline__ void store_px_stream_bf16(void* base, int64_t o, const float (&v)[PX]) {
+    uint2* q = reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(base) + o);
+#pragma unroll
+    for (int i = 0; i < PX / 4; ++i) __stcs(q + i, make_uint2(pack_bf16x2(v[4 * i], v[4 * i + 1]), pack_bf16x2(v[4 * i + 2], v[4 * i + 3])));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -506,10 +580,11 @@ __device__ __forceinline__ void fwd_plane_any(uint32_t srow, uint32_t lrow, uint
     }
 }
 
-template <bool MIX, int MASKMODE, int PX, int THREADS, int MINB>
+template <bool MIX, int MASKMODE, int PX, int THREADS, int MINB, bool BF16 = false>
 __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParams p, const StreamCfg cfg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr bool DENSE = (MASKMODE == SMASK_DENSE);
+    constexpr int NEc = MIX ? 2 : 1;
     const int W = p.d.W, H = p.d.H, N = p.d.N, pitch = cfg.pitch, rpc = cfg.rpc, hs = cfg.hs, NB = cfg.nblk;
     const int rows_total = p.d.B * H;
     const Smem s = carve(smem_raw, cfg, N, MIX, DENSE, 0, false);
@@ -527,7 +602,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
     __syncthreads();
     const int nit = (cfg.ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if ((int)threadIdx.x >= cfg.nc) {
-        producer_loop<MIX, MASKMODE>(p, cfg, s, nit);
+        producer_loop<MIX, MASKMODE, BF16>(p, cfg, s, nit);
         return;
     }
     const int lane = threadIdx.x & 31;
@@ -536,9 +611,15 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
     // 32-bit shared-window addresses of the row interiors (byte units from here on)
     const uint32_t bars = smem_u32(s.bars), coef0 = smem_u32(s.coef), src0 = smem_u32(s.src + PAD), lring0 = smem_u32(s.lring + PAD);
     const uint32_t pitch4 = (uint32_t)pitch * 4u, rowpitch4 = (uint32_t)rpc * pitch4;
-    const uint32_t sdelta = (uint32_t)((s.sring - s.lring) * sizeof(float)), mdelta = (uint32_t)((s.mring - s.lring) * sizeof(float));
+    // fp32 storage: logit rows of a stage are rpc rows apart, the sigma ring sits sdelta behind the logit ring.  bf16 storage:
+    // the tap windows read the converted rows [plane][logit | sigma][row], double-buffered over blocks
+    const uint32_t sdelta = BF16 ? rowpitch4 : (uint32_t)((s.sring - s.lring) * sizeof(float));
+    const uint32_t mdelta = (uint32_t)((s.mring - s.lring) * sizeof(float));
+    const uint32_t plane4 = BF16 ? NEc * rowpitch4 : rowpitch4;
+    const uint32_t cbuf0 = smem_u32(s.cbuf + PAD), bring0 = smem_u32(s.bring);
+    const uint32_t rb = (uint32_t)(W * 2), rb_rpc = rb * (uint32_t)rpc;
     const int x04 = x0 * 4, W4 = W * 4;
-    int stage = 0;
+    int stage = 0, jb = 0;
     uint32_t fphase = 0;
 
     for (int it = 0; it < nit; ++it) {
@@ -574,14 +655,24 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
         mbar_wait(bars + 8 * (BAR_SRC + (it & 1)), (it >> 1) & 1);
         unsigned long long not_ones = 0ull;  // dense mask: planes whose mask this thread saw differ from 1.0
 
-        for (int j = 0; j < NB; ++j) {
+        for (int j = 0; j < NB; ++j, ++jb) {
             // every consumer thread waits (also idle ones: a warp must not run ahead of the ring and arrive twice
             // in one phase of an empty barrier); the acquire also publishes the group's coefficients
             mbar_wait(bars + 8 * (BAR_FULL + stage), fphase);
+            const int np = min(hs, N - j * hs);
+            if constexpr (BF16) {
+                // convert this thread's pixels of the block, release the raw stage, meet the other consumers: the windows
+                // below read what every thread converted.  Buffer (jb & 1) was last read in block jb - 2, which every thread
+                // finished before it passed the barrier of block jb - 1.
+                const uint32_t cb = cbuf0 + (uint32_t)((jb & 1) * hs * NEc * rpc + r) * pitch4;
+                if (active) bf16_convert_block<MIX, PX>(bring0 + (uint32_t)(stage * hs * NEc * rpc + r) * rb + (uint32_t)x0 * 2u, cb + x04, rb_rpc, rowpitch4, np);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars + 8 * (BAR_EMPTY + stage));
+                consumer_sync(cfg.nc);
+            }
             if (active) {
-                const int np = min(hs, N - j * hs);
-                uint32_t lrow = lring0 + (uint32_t)(stage * hs * rpc + r) * pitch4;
-                for (int q = 0; q < np; ++q, lrow += rowpitch4, coef_a += (uint32_t)sizeof(PlaneCoef)) {
+                uint32_t lrow = BF16 ? cbuf0 + (uint32_t)((jb & 1) * hs * NEc * rpc + r) * pitch4 : lring0 + (uint32_t)(stage * hs * rpc + r) * pitch4;
+                for (int q = 0; q < np; ++q, lrow += plane4, coef_a += (uint32_t)sizeof(PlaneCoef)) {
                     const PlaneCoef k = load_coef(coef_a);
                     float mm[PX] = {};
                     bool perpix = false;
@@ -594,8 +685,10 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
                     else fwd_plane_any<MIX, PX, false>(srow, lrow, lrow + sdelta, pitch4, x04 + k.k4, W4, k, mm, acc);
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bars + 8 * (BAR_EMPTY + stage));
+            if constexpr (!BF16) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars + 8 * (BAR_EMPTY + stage));
+            }
             if (++stage == cfg.nst) stage = 0, fphase ^= 1;
         }
         if (DENSE && p.mask_rows) {
@@ -786,7 +879,7 @@ __device__ __forceinline__ void gather_any(uint32_t drow, int at4, int W4, float
     }
 }
 
-template <bool MIX, int MASKMODE, bool WANT_DISP, int PX, int THREADS, int MINB>
+template <bool MIX, int MASKMODE, bool WANT_DISP, int PX, int THREADS, int MINB, bool BF16 = false>
 __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParams p, const StreamCfg cfg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr bool DENSE = (MASKMODE == SMASK_DENSE), SUMM = (MASKMODE == SMASK_SUMMARY);
@@ -807,7 +900,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
     __syncthreads();
     const int nit = (cfg.ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if ((int)threadIdx.x >= cfg.nc) {
-        producer_loop<MIX, MASKMODE>(p, cfg, s, nit);
+        producer_loop<MIX, MASKMODE, BF16>(p, cfg, s, nit);
         return;
     }
     const int lane = threadIdx.x & 31;
@@ -816,7 +909,11 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
     const uint32_t bars = smem_u32(s.bars), coef0 = smem_u32(s.coef), src0 = smem_u32(s.src + PAD), lring0 = smem_u32(s.lring + PAD);
     const uint32_t dbuf0 = smem_u32(s.dbuf + PAD);
     const uint32_t pitch4 = (uint32_t)pitch * 4u, rowpitch4 = (uint32_t)rpc * pitch4;
-    const uint32_t sdelta = (uint32_t)((s.sring - s.lring) * sizeof(float)), mdelta = (uint32_t)((s.mring - s.lring) * sizeof(float));
+    const uint32_t sdelta = BF16 ? rowpitch4 : (uint32_t)((s.sring - s.lring) * sizeof(float));  // see rows_fwd_stream
+    const uint32_t mdelta = (uint32_t)((s.mring - s.lring) * sizeof(float));
+    const uint32_t plane4 = BF16 ? NE * rowpitch4 : rowpitch4;
+    const uint32_t cbuf0 = smem_u32(s.cbuf + PAD), bring0 = smem_u32(s.bring);
+    const uint32_t rb = (uint32_t)(W * 2), rb_rpc = rb * (uint32_t)rpc;
     const int x04 = x0 * 4, W4 = W * 4;
     int stage = 0, jb = 0;
     uint32_t fphase = 0;
@@ -883,12 +980,20 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
             // exchange rows of this block: [plane][NE][rpc][pitch], double-buffered over blocks
             const uint32_t dblk = dbuf0 + (uint32_t)((jb & 1) * hs * NE * rpc + r) * pitch4;
             mbar_wait(bars + 8 * (BAR_FULL + stage), fphase);
+            if constexpr (BF16) {
+                // raw bf16 rows -> fp32 rows (cbuf, double-buffered like the exchange rows), then the raw stage is free
+                const uint32_t cb = cbuf0 + (uint32_t)((jb & 1) * hs * NE * rpc + r) * pitch4;
+                if (active) bf16_convert_block<MIX, PX>(bring0 + (uint32_t)(stage * hs * NE * rpc + r) * rb + (uint32_t)x0 * 2u, cb + x04, rb_rpc, rowpitch4, np);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars + 8 * (BAR_EMPTY + stage));
+                consumer_sync(cfg.nc);
+            }
             // ---------------- phase A: per-target gradients into the exchange rows ----------------
             {
-                uint32_t lrow = lring0 + (uint32_t)(stage * hs * rpc + r) * pitch4;
+                uint32_t lrow = BF16 ? cbuf0 + (uint32_t)((jb & 1) * hs * NE * rpc + r) * pitch4 : lring0 + (uint32_t)(stage * hs * rpc + r) * pitch4;
                 uint32_t coef_a = coef_g + (uint32_t)n0 * (uint32_t)sizeof(PlaneCoef);
                 uint32_t drow = dblk;
-                for (int q = 0; q < np; ++q, lrow += rowpitch4, coef_a += (uint32_t)sizeof(PlaneCoef), drow += NE * rowpitch4) {
+                for (int q = 0; q < np; ++q, lrow += plane4, coef_a += (uint32_t)sizeof(PlaneCoef), drow += NE * rowpitch4) {
                     float gsum = 0.0f;
                     if (active) {
                         const PlaneCoef k = load_coef(coef_a);
@@ -919,8 +1024,10 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
                     }
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bars + 8 * (BAR_EMPTY + stage));  // the ring stage is no longer needed
+            if constexpr (!BF16) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars + 8 * (BAR_EMPTY + stage));  // the ring stage is no longer needed
+            }
             if (++stage == cfg.nst) stage = 0, fphase ^= 1;
             // exchange rows of block jb complete.  They are double-buffered: block jb+1 writes the other buffer, and
             // block jb+2 is only written after the next barrier, which every thread reaches after this gather.
@@ -939,11 +1046,13 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
                     float gg[PX];
                     if (p.gin.g_logits) {
                         gather_any<PX>(drow, at4, W4, wc0, wc1, gg);
-                        store_px_stream<PX>(p.gin.g_logits + o, gg);
+                        if constexpr (BF16) store_px_stream_bf16<PX>(p.gin.g_logits, o, gg);
+                        else store_px_stream<PX>(p.gin.g_logits + o, gg);
                     }
                     if constexpr (MIX) if (p.gin.g_sigma) {
                         gather_any<PX>(drow + rowpitch4, at4, W4, wc0, wc1, gg);
-                        store_px_stream<PX>(p.gin.g_sigma + o, gg);
+                        if constexpr (BF16) store_px_stream_bf16<PX>(p.gin.g_sigma, o, gg);
+                        else store_px_stream<PX>(p.gin.g_sigma + o, gg);
                     }
                 }
             }
@@ -995,6 +1104,7 @@ inline bool stream_path_supported(const WarpParams& p) {
 template <int PX, int THREADS>
 inline StreamCfg stream_cfg(const WarpParams& p, bool mix, bool dense, int ne_bwd, bool want_disp, int budget_kb = 0) {
     StreamCfg c;
+    c.bf16 = p.d.dtype == PD_DTYPE_BF16 ? 1 : 0;
     c.tpr = p.d.W / PX;
     c.rpc = THREADS / c.tpr;
     if (c.rpc < 1) c.rpc = 1;
@@ -1042,7 +1152,7 @@ inline int stream_grid(int ngroups, int threads, size_t smem, const void* kernel
 // kernel family only (non-template inline launchers would instantiate every kernel they mention in both).
 #ifndef PD_TS_BWD_ONLY
 // THREADS = consumer threads the row groups are packed into + the producer warp
-template <bool MIX, int MASKMODE, int PX, int THREADS, int MINB>
+template <bool MIX, int MASKMODE, int PX, int THREADS, int MINB, bool BF16 = false>
 inline bool launch_fwd_stream_t(const WarpParams& p, cudaStream_t st, bool dry) {
     // more than four resident CTAs only fit with a shallower ring: 220 KB / MINB each
     const StreamCfg c = stream_cfg<PX, THREADS - 32>(p, MIX, MASKMODE == SMASK_DENSE, 0, false, MINB > 4 ? 220 / MINB : 0);
@@ -1051,7 +1161,7 @@ inline bool launch_fwd_stream_t(const WarpParams& p, cudaStream_t st, bool dry) 
     const size_t smem = stream_smem_bytes(c, p.d.N, MIX, MASKMODE == SMASK_DENSE, 0, false);
     if (smem > 220 * 1024) return false;
     if (dry) return true;
-    auto kern = rows_fwd_stream<MIX, MASKMODE, PX, THREADS, MINB>;
+    auto kern = rows_fwd_stream<MIX, MASKMODE, PX, THREADS, MINB, BF16>;
     stream_smem_optin(kern, smem);
     kern<<<stream_grid(c.ngroups, threads, smem, (const void*)kern), threads, smem, st>>>(p, c);
     return true;
@@ -1060,7 +1170,7 @@ inline bool launch_fwd_stream_t(const WarpParams& p, cudaStream_t st, bool dry) 
 #endif  // PD_TS_BWD_ONLY
 
 #ifndef PD_TS_FWD_ONLY
-template <bool MIX, int MASKMODE, bool WANT_DISP, int PX, int THREADS, int MINB>
+template <bool MIX, int MASKMODE, bool WANT_DISP, int PX, int THREADS, int MINB, bool BF16 = false>
 inline bool launch_bwd_stream_t(const WarpParams& p, cudaStream_t st, bool dry) {
     const StreamCfg c = stream_cfg<PX, THREADS - 32>(p, MIX, MASKMODE == SMASK_DENSE, MIX ? 2 : 1, WANT_DISP);
     const int threads = c.nc + 32;
@@ -1068,7 +1178,7 @@ inline bool launch_bwd_stream_t(const WarpParams& p, cudaStream_t st, bool dry) 
     const size_t smem = stream_smem_bytes(c, p.d.N, MIX, MASKMODE == SMASK_DENSE, MIX ? 2 : 1, WANT_DISP);
     if (smem > 220 * 1024) return false;
     if (dry) return true;
-    auto kern = rows_bwd_stream<MIX, MASKMODE, WANT_DISP, PX, THREADS, MINB>;
+    auto kern = rows_bwd_stream<MIX, MASKMODE, WANT_DISP, PX, THREADS, MINB, BF16>;
     stream_smem_optin(kern, smem);
     kern<<<stream_grid(c.ngroups, threads, smem, (const void*)kern), threads, smem, st>>>(p, c);
     return true;
@@ -1080,6 +1190,14 @@ inline bool launch_bwd_stream_t(const WarpParams& p, cudaStream_t st, bool dry) 
 template <bool MIX, int MASKMODE>
 inline bool launch_fwd_stream_m(const WarpParams& p, cudaStream_t st, bool dry) {
     const int W = p.d.W;
+    if (p.d.dtype == PD_DTYPE_BF16) {  // bf16 storage: row masks, 4 pixels per thread, rows of whole 16-byte units
+        if constexpr (MASKMODE == SMASK_ROW) {
+            if (W % 8 != 0) return false;
+            if (W / 4 <= 160) return launch_fwd_stream_t<MIX, MASKMODE, 4, 192, MIX ? 2 : 3, true>(p, st, dry);
+            if (W / 4 <= 320) return launch_fwd_stream_t<MIX, MASKMODE, 4, 352, MIX ? 1 : 2, true>(p, st, dry);
+        }
+        return false;
+    }
     if (W % 8 == 0 && W / 8 <= 160 && tuning().stream_px8) return launch_fwd_stream_t<MIX, MASKMODE, 8, 192, 2>(p, st, dry);
     if constexpr (!MIX && MASKMODE == SMASK_ROW) {  // occupancy experiments (pd_tuning.stream_fwd_minb): fewer registers, shallower ring
         if (W / 4 <= 160 && tuning().stream_fwd_minb == 5) return launch_fwd_stream_t<MIX, MASKMODE, 4, 192, 5>(p, st, dry);
@@ -1102,6 +1220,14 @@ inline bool launch_fwd_stream(const WarpParams& p, cudaStream_t st, bool dry = f
 template <bool MIX, int MASKMODE, bool WANT_DISP>
 inline bool launch_bwd_stream_w(const WarpParams& p, cudaStream_t st, bool dry) {
     const int W = p.d.W;
+    if (p.d.dtype == PD_DTYPE_BF16) {
+        if constexpr (MASKMODE == SMASK_ROW) {
+            if (W % 8 != 0) return false;
+            if (W / 4 <= 160) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 4, 192, MIX ? 2 : 3, true>(p, st, dry);
+            if (W / 4 <= 320) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 4, 352, 1, true>(p, st, dry);
+        }
+        return false;
+    }
     if (W % 8 == 0 && W / 8 <= 160 && tuning().stream_px8) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 8, 192, 1>(p, st, dry);
     if (W / 4 <= 160) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 4, 192, MIX ? 2 : 3>(p, st, dry);
     if (W / 4 <= 320) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 4, 352, 1>(p, st, dry);

@@ -5,7 +5,7 @@ the library is a raw device pointer.  There is no eager fallback."""
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass
+from dataclasses import dataclass, replace
 from typing import Optional, Tuple
 
 import torch
@@ -21,6 +21,11 @@ KERNEL_TIMELINE = None
 #: gradient) to the warp node that produced its input instead of launching a kernel and writing g_rgb_rec to HBM.
 #: True: for the stereo (disp_warp) kernels; "all": every warp type (the ABI supports it everywhere; tests); False: never.
 FUSE_PHOTOMETRIC_BWD = True
+
+
+#: hand bf16 ``logits`` / ``sigma`` to the kernels as bf16 (pd_warp_desc.dtype) where the library serves it — the streamed stereo
+#: kernels; gradients come back as bf16 — instead of upcasting them with torch first
+BF16_STORAGE = True
 
 
 class _Link:
@@ -115,6 +120,7 @@ class WarpConfig:
     shape: Tuple[int, int, int, int] = (0, 0, 0, 0)  # B,N,H,W
     layered: bool = False  # also materialise the per-plane tensors of trainer.py:582-602 (detached)
     exact_coords: bool = False  # PD_FLAG_EXACT_COORDS: bit-faithful coordinate round trip (slower stereo path)
+    bf16: bool = False  # pd_warp_desc.dtype = PD_DTYPE_BF16: logits / sigma (and their gradients) are stored as bf16
 
 
 class _WarpComposite(torch.autograd.Function):
@@ -127,13 +133,7 @@ class _WarpComposite(torch.autograd.Function):
         ctx.set_materialize_grads(False)  # an unused output's gradient arrives as None, not as a zero-filled tensor
         B, N, H, W = cfg.shape
         dev = logits.device
-        desc = L.WarpDesc(B=B, N=N, H=H, W=W, warp_type=cfg.warp_type, mixture=int(cfg.mixture), automask=int(cfg.automask),
-                          mask_dtype=L.PD_MASK_NONE, disp_sign=float(cfg.disp_sign), flags=(L.PD_FLAG_EXACT_COORDS if cfg.exact_coords else 0))
-        if disp is not None:
-            desc.disp_stride = _strides4(disp)
-        if mask is not None:
-            desc.mask_stride = _strides4(mask)
-            desc.mask_dtype = L.PD_MASK_F32 if mask.dtype == torch.float32 else L.PD_MASK_U8
+        desc = _warp_desc(cfg, disp, mask)
         tin = L.WarpIn(src=_ptr(src), tgt=_ptr(tgt), logits=_ptr(logits), sigma=_ptr(sigma), disp=_ptr(disp), mask=_ptr(mask),
                        hmat=_ptr(hmat), cam=_ptr(cam))
         rgb_rec = torch.empty(B, 3, H, W, device=dev, dtype=torch.float32)
@@ -231,12 +231,37 @@ class _WarpComposite(torch.autograd.Function):
         return (None, None, None, None, g_logits, g_sigma, g_disp, None, g_hmat, None)
 
 
+def _warp_desc(cfg: WarpConfig, disp, mask):
+    B, N, H, W = cfg.shape
+    desc = L.WarpDesc(B=B, N=N, H=H, W=W, warp_type=cfg.warp_type, mixture=int(cfg.mixture), automask=int(cfg.automask),
+                      mask_dtype=L.PD_MASK_NONE, disp_sign=float(cfg.disp_sign), flags=(L.PD_FLAG_EXACT_COORDS if cfg.exact_coords else 0),
+                      dtype=(L.PD_DTYPE_BF16 if cfg.bf16 else L.PD_DTYPE_F32))
+    if disp is not None:
+        desc.disp_stride = _strides4(disp)
+    if mask is not None:
+        desc.mask_stride = _strides4(mask)
+        desc.mask_dtype = L.PD_MASK_F32 if mask.dtype == torch.float32 else L.PD_MASK_U8
+    return desc
+
+
+def _supports(cfg: WarpConfig, src, tgt, logits, sigma, disp, mask, hmat, cam) -> bool:
+    desc = _warp_desc(cfg, disp, mask)
+    tin = L.WarpIn(src=_ptr(src), tgt=_ptr(tgt), logits=_ptr(logits), sigma=_ptr(sigma), disp=_ptr(disp), mask=_ptr(mask), hmat=_ptr(hmat), cam=_ptr(cam))
+    return bool(L.lib().pd_warp_composite_supports(C.byref(desc), C.byref(tin)))
+
+
 def warp_composite(cfg: WarpConfig, src, tgt, logits, sigma=None, disp=None, mask=None, hmat=None, cam=None):
     """Returns (rgb_rec, nll | None, nll_auto | None, layered dict | None)."""
     src = _f32c(src, "src")
-    logits = _f32c(logits, "logits")
+    want_bf16 = (BF16_STORAGE and logits.dtype == torch.bfloat16 and logits.is_cuda and not cfg.layered and not cfg.exact_coords
+                 and (not cfg.mixture or (sigma is not None and sigma.dtype == torch.bfloat16)))
+    if want_bf16:
+        logits = logits.contiguous()
+        sigma = sigma.contiguous() if cfg.mixture else None
+    else:
+        logits = _f32c(logits, "logits")
+        sigma = _f32c(sigma, "sigma") if cfg.mixture else None
     tgt = _f32c(tgt, "tgt") if (cfg.mixture and tgt is not None) else None
-    sigma = _f32c(sigma, "sigma") if cfg.mixture else None
     if disp is not None:
         if disp.dtype != torch.float32:
             disp = disp.float()
@@ -253,6 +278,13 @@ def warp_composite(cfg: WarpConfig, src, tgt, logits, sigma=None, disp=None, mas
         hmat = _f32c(hmat, "hmat")
     if cam is not None:
         cam = _f32c(cam, "cam").detach()
+    if want_bf16:
+        # bf16 storage is served by the streamed stereo kernels only: ask the library, otherwise upcast like any other dtype
+        cfg = replace(cfg, bf16=True)
+        if not _supports(cfg, src, tgt, logits, sigma, disp, mask, hmat, cam):
+            cfg = replace(cfg, bf16=False)
+            logits = _f32c(logits, "logits")
+            sigma = _f32c(sigma, "sigma") if cfg.mixture else None
     # the side channel to the photometric node exists for the stereo kernels only: their row prologue absorbs the fused form
     # for free, while the thread-per-pixel homography / general backward kernels lose 10 % to it (measured, cfg 4)
     link = _Link() if (cfg.warp_type == L.PD_WARP_DISP or FUSE_PHOTOMETRIC_BWD == "all") else None

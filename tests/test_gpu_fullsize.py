@@ -105,11 +105,16 @@ def oracle_run(name, B, seed, smooth=False):
     return res
 
 
-def cuda_run(name, B, seed, exact=False, rowwise=True, graph=False, smooth=False):
+def cuda_run(name, B, seed, exact=False, rowwise=True, graph=False, smooth=False, bf16=False):
     from planedepth_b200.boundary import HotPath
     from planedepth_b200.graph import GraphedStep, make_step
 
     opt, b, photometric = build(name, B, seed, "cuda", smooth)
+    if bf16:  # network outputs stored as bf16 (leaves included: the gradients come back as bf16)
+        for k in ("logits", "sigma"):
+            if k in b.leaves:
+                b.leaves[k] = b.leaves[k].detach().to(torch.bfloat16).requires_grad_(True)
+                b.outputs[k] = b.leaves[k]
     hp = HotPath(opt, b.target_sides, pc_net=None, photometric=photometric, exact_coords=exact, disp_rowwise=rowwise)
     keys = list(b.leaves.keys())
     leaves = [b.leaves[k] for k in keys]
@@ -228,3 +233,45 @@ def test_smooth_fields_meet_the_exact_gates_in_default_mode(name, B):
     indistinguishable from the reference's round trip at the 1e-4 gate, plane-parameter gradients included."""
     want = oracle_run(name, B, 4321, smooth=True)
     compare(name + " smooth default", want, cuda_run(name, B, 4321, smooth=True), exact=False, noise=False)
+
+
+@pytest.mark.parametrize("name,B,one_cta", [("cfg2", 4, False), ("cfg2", 2, True), ("cfg3", 1, False), ("cfg3_small", 2, True)])
+def test_bf16_storage_at_full_size(name, B, one_cta):
+    """pd_warp_desc.dtype = PD_DTYPE_BF16 at the BASELINE widths, with the persistent loops iterating: the bf16-storage kernels
+    against the SAME kernels fed through the upcast path (identical fp32 arithmetic on identical values: forward equal to
+    rounding noise, gradients equal up to their final bf16 rounding)."""
+    from planedepth_b200 import _lib, functional
+
+    def run():
+        if one_cta:
+            with _lib.tuned(stream_ctas_per_sm=1):
+                return cuda_run(name, B, 55, bf16=True)
+        return cuda_run(name, B, 55, bf16=True)
+
+    seen = []
+    orig = functional._supports
+    functional._supports = lambda *a, **k: (seen.append(orig(*a, **k)) or seen[-1])
+    try:
+        got = run()
+    finally:
+        functional._supports = orig
+    assert seen and all(seen), "the library did not take the bf16 storage path"
+    functional.BF16_STORAGE = False
+    try:
+        want = run()
+    finally:
+        functional.BF16_STORAGE = True
+    for s_ in want["sides"]:
+        bounded_check(got[("rgb_rec", s_)], want[("rgb_rec", s_)], 1e-6, "%s bf16 rgb_rec@%s" % (name, s_), allow_frac=1e-5, cap=100)
+        if ("nll", s_) in want:
+            bounded_check(got[("nll", s_)], want[("nll", s_)], 1e-5, "%s bf16 nll@%s" % (name, s_), allow_frac=1e-5, cap=100)
+    for k, v in want["losses"].items():
+        bounded_check(torch.tensor(got["losses"][k]), torch.tensor(v), 1e-6, "%s bf16 %s" % (name, k))
+    for k, gw in want["grads"].items():
+        if gw is None:
+            continue
+        gg = got["grads"][k]
+        assert gg.dtype == gw.dtype
+        scale = float(gw.float().abs().max()) + 1e-12
+        # one bf16 ulp (2^-8 relative to the tensor's maximum at most) where the two fp32 values straddle a rounding boundary
+        bounded_check(gg.float(), gw.float(), 2.0 ** -8 * scale, "%s bf16 grad_%s" % (name, k), allow_frac=1e-5, cap=4)

@@ -551,6 +551,111 @@ def test_bf16_inputs_are_upcast_within_2e_2(idx):
         check(leaf.grad.float(), want, 2e-2 * float(want.abs().max()), "grad_%s (bf16 inputs)" % k, allow_frac=2e-3)
 
 
+@pytest.mark.parametrize("idx,rowwise", [(0, True), (9, True), (2, True), (10, True), (12, True), (16, True)])
+def test_bf16_storage_kernels(idx, rowwise):
+    """pd_warp_desc.dtype = PD_DTYPE_BF16: the streamed stereo kernels read bf16 logits / sigma rows (TMA, converted by the
+    consumers) and store bf16 gradients.  Against the oracle on the SAME bf16-rounded inputs the forward must meet the fp32
+    gate (all arithmetic is fp32), gradients BASELINE's 2e-2 bf16 gate; against the upcast path the forward must be identical
+    and the gradients equal up to one bf16 rounding."""
+    from planedepth_b200 import functional
+
+    cfg = CONFIGS[idx]
+    mix = cfg[5]
+
+    def to_bf16(c):
+        leaves = {}
+        for k in ("logits", "sigma"):
+            if k in c.outputs:
+                leaves[k] = c.outputs[k].detach().to(torch.bfloat16).requires_grad_(True)
+                c.outputs[k] = leaves[k]
+        return leaves
+
+    # oracle on the bf16-rounded values, in fp32
+    cc = build_on("cpu", cfg, seed=600 + idx)
+    for k in ("logits", "sigma"):
+        if k in cc.outputs:
+            cc.outputs[k] = cc.outputs[k].detach().to(torch.bfloat16).float().requires_grad_(True)
+            cc.leaves[k] = cc.outputs[k]
+    lo = O.hot_path(cc.opt, cc.target_sides, cc.inputs, cc.outputs, pyramid_features)
+    lo["loss/total_loss"].backward()
+
+    seen = []
+    orig = functional._supports
+
+    def spy(*a, **k):
+        seen.append(orig(*a, **k))
+        return seen[-1]
+
+    functional._supports = spy
+    try:
+        cg = build_on("cuda", cfg, seed=600 + idx)
+        l16 = to_bf16(cg)
+        lg = run_cuda(cg, None, "fused", rowwise=rowwise)
+    finally:
+        functional._supports = orig
+    assert seen and all(seen), "the library did not take the bf16 storage path"
+    functional.BF16_STORAGE = False
+    try:
+        cu = build_on("cuda", cfg, seed=600 + idx)
+        u16 = to_bf16(cu)
+        lu = run_cuda(cu, None, "fused", rowwise=rowwise)
+    finally:
+        functional.BF16_STORAGE = True
+    for s_ in cc.target_sides:
+        # (the default kernels' exact sample positions, DESIGN.md section 7.2: up to 1.2e-4 px x slope at W = 1280, on iid noise)
+        check(cg.outputs[("rgb_rec", s_)], cc.outputs[("rgb_rec", s_)], TOL, "rgb_rec (bf16 storage vs oracle on bf16 inputs)", allow_frac=1e-3)
+        check(cg.outputs[("rgb_rec", s_)], cu.outputs[("rgb_rec", s_)], 1e-6, "rgb_rec (bf16 storage vs upcast path)", allow_frac=1e-5)
+    for k in lo:
+        check(lg[k], lo[k], TOL, k)
+        check(lg[k], lu[k], 1e-6, k + " (vs upcast)")
+    for k, leaf in l16.items():
+        assert leaf.grad is not None and leaf.grad.dtype == torch.bfloat16
+        want = cc.leaves[k].grad
+        scale = float(want.abs().max()) + 1e-12
+        check(leaf.grad.float(), want, 2e-2 * scale, "grad_%s (bf16 storage)" % k, allow_frac=2e-3)
+        # one bf16 rounding (2^-8 relative) of the same fp32 value, except where fp32 summation order differs in the last bit
+        d = (leaf.grad.float() - u16[k].grad.float()).abs()
+        assert float((d > 2.0 ** -7 * u16[k].grad.float().abs() + 1e-12).float().mean()) <= 1e-3, "grad_%s: bf16 kernel stores differ from the upcast path" % k
+    for k in cc.leaves:
+        if k in ("logits", "sigma") or cc.leaves[k].grad is None:
+            continue
+        scale = float(cc.leaves[k].grad.abs().max()) + 1e-12
+        check(cg.leaves[k].grad, cc.leaves[k].grad, grad_tol(k) * scale, "grad_" + k, allow_frac=2e-3)
+
+
+def test_bf16_storage_falls_back_to_upcast_where_unserved():
+    """A dense un-promised mask, a homography warp or exact_coords are not served in bf16: pd_warp_composite_supports says
+    so and the boundary upcasts (same results as before); the raw ABI answers PD_ERR_UNSUPPORTED, never reads bf16 as fp32."""
+    import ctypes as C
+
+    from planedepth_b200 import _lib as L
+    from planedepth_b200 import functional
+
+    for idx in (2, 4):  # dense cat mask without the promise; homography
+        cfg = CONFIGS[idx]
+        cg = build_on("cuda", cfg, seed=650 + idx)
+        cc = build_on("cpu", cfg, seed=650 + idx)
+        for c in (cg, cc):
+            for k in ("logits", "sigma"):
+                if k in c.outputs:
+                    v = c.outputs[k].detach().to(torch.bfloat16)
+                    c.outputs[k] = (v if c is cg else v.float()).requires_grad_(True)
+                    c.leaves[k] = c.outputs[k]
+        lo = O.hot_path(cc.opt, cc.target_sides, cc.inputs, cc.outputs, pyramid_features)
+        lg = run_cuda(cg, None, "fused")
+        for k in lo:
+            check(lg[k], lo[k], TOL, k)
+        assert cg.leaves["logits"].grad.dtype == torch.bfloat16
+    B, N, H, W = 1, 4, 8, 64
+    d = L.WarpDesc(B=B, N=N, H=H, W=W, warp_type=L.PD_WARP_HOMOGRAPHY, dtype=L.PD_DTYPE_BF16)
+    t = lambda *s: torch.zeros(*s, device="cuda")
+    tin = L.WarpIn(src=t(B, 3, H, W).data_ptr(), logits=t(B, N, H, W).data_ptr(), hmat=t(B * N, 12).data_ptr(), cam=t(B, 9).data_ptr())
+    assert L.lib().pd_warp_composite_supports(C.byref(d), C.byref(tin)) == 0
+    out = L.WarpOut(rgb_rec=t(B, 3, H, W).data_ptr(), stats=t(B, 4, H, W).data_ptr())
+    rc = L.lib().pd_warp_composite_fwd(C.byref(d), C.byref(tin), C.byref(out), t(B * H * W * 4).data_ptr(), None)
+    assert rc == 7 and b"bf16" in L.lib().pd_last_error()
+
+
 # ------------------------------------------------------------------------------------------------
 # decoder tail (networks/depth_decoder.py:258-291) through pd_plane_tail_fwd / _bwd
 # ------------------------------------------------------------------------------------------------
