@@ -20,12 +20,38 @@ def available() -> bool:
 
 
 _loaded = None
+_saved_cuda = None
+
+
+def enter_cpu_mode() -> None:
+    """The reference calls ``.cuda()`` on helper tensors (layers.py:140,196; depth_decoder.py:148): for a CPU run those calls
+    become identities.  Process-wide monkeypatch: leave_cpu_mode() undoes it (bench.py runs its GPU legs before / after)."""
+    global _saved_cuda
+    import torch
+    import torch.nn as nn
+
+    if _saved_cuda is None:
+        _saved_cuda = (torch.Tensor.cuda, nn.Module.cuda)
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        nn.Module.cuda = lambda self, *a, **k: self
+
+
+def leave_cpu_mode() -> None:
+    global _saved_cuda
+    import torch
+    import torch.nn as nn
+
+    if _saved_cuda is not None:
+        torch.Tensor.cuda, nn.Module.cuda = _saved_cuda
+        _saved_cuda = None
 
 
 def load(cpu_only: bool = False):
     """Returns (trainer module, layers module, networks package, options module) of the reference, or None."""
     global _loaded
     if _loaded is not None:
+        if cpu_only:
+            enter_cpu_mode()
         return _loaded
     if not available():
         return None
@@ -42,10 +68,10 @@ def load(cpu_only: bool = False):
     six.string_classes = (str, bytes)
     sys.modules["torch._six"] = six
     torch._six = six
-    if cpu_only or not torch.cuda.is_available():
-        # the reference calls .cuda() on helper tensors
-        torch.Tensor.cuda = lambda self, *a, **k: self
-        nn.Module.cuda = lambda self, *a, **k: self
+    if not torch.cuda.is_available():
+        cpu_only = True
+    if cpu_only:
+        enter_cpu_mode()
     import PIL.Image
 
     if not hasattr(PIL.Image, "ANTIALIAS"):

@@ -273,12 +273,21 @@ def time_cpu(cfg_name, B_sample, steps, warmup):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     step, kind = cpu_step_fn(cfg_name, B_sample)
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = (time.perf_counter() - t0) / steps
+    try:
+        for _ in range(warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt = (time.perf_counter() - t0) / steps
+    finally:
+        # the CPU arm runs the reference with `.cuda()` patched to the identity (baseline/shim.py): undo it for the GPU legs
+        try:
+            import shim
+
+            shim.leave_cpu_mode()
+        except Exception:
+            pass
     return {"value": B_sample / dt, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": "%d step(s) of B=%d images of %s (fwd+bwd), %d torch threads" % (steps, B_sample, cfg_name, cores)}, dt
 
@@ -534,10 +543,7 @@ def run_ours(args):
                          ", ".join(str(k) for k in read_keys), fmt[not args.e2e_fp32]))
         if rank != 0:
             return None
-        cpu = None
-        if ws == 1 and main and not args.no_cpu_baseline:
-            # bounded sample of the same workload on the host cores: ~10-20 s of CPU work (26 steps of B=4 images at ~0.35 s)
-            cpu, _ = time_cpu(cfg_name, min(B, 4), 24, 2)
+        cpu = None  # filled in after the GPU legs (run_ours)
         return {
             "metric": METRIC, "value": D.aggregate_throughput(B, ws, ms_step), "unit": UNIT, "n_gpus": ws, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -570,6 +576,10 @@ def run_ours(args):
         extras["ddp"] = ddp_leg(args, rank, local_rank, ws, dev)
     if ws == 1 and not args.no_reference_gpu:
         extras["reference_gpu"] = reference_gpu_leg(args.config)
+    if rank == 0 and ws == 1 and not args.no_cpu_baseline:
+        # bounded sample of the same workload on the host cores: ~10-20 s of CPU work (26 steps of B=4 images at ~0.35 s).  Last:
+        # the CPU arm patches `.cuda()` to the identity while it runs the reference
+        line["cpu_baseline"], _ = time_cpu(args.config, min(CONFIGS[args.config][0], 4), 24, 2)
     if rank == 0:
         line.update(extras)
         emit(line)
