@@ -750,7 +750,7 @@ def reference_gpu_leg(cfg_name):
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 10
-        res = {"value": B / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "steps": 10, "warmup": 3, "loss": float(loss),
+        res = {"value": B / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "steps": 10, "warmup": 3, "loss": float(loss.detach()),
                "what": "unmodified reference Trainer.pred_novel_images + photometric term (F.grid_sample, autograd), fwd+bwd, same batch, this GPU",
                "warped_images_per_s": B * batch.shape[1] * len(batch.target_sides) / ms * 1e3}
         del batch, leaves, t
