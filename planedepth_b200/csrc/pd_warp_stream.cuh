@@ -1172,7 +1172,7 @@ inline bool launch_fwd_stream_t(const WarpParams& p, cudaStream_t st, bool dry) 
 #ifndef PD_TS_FWD_ONLY
 template <bool MIX, int MASKMODE, bool WANT_DISP, int PX, int THREADS, int MINB, bool BF16 = false>
 inline bool launch_bwd_stream_t(const WarpParams& p, cudaStream_t st, bool dry) {
-    const StreamCfg c = stream_cfg<PX, THREADS - 32>(p, MIX, MASKMODE == SMASK_DENSE, MIX ? 2 : 1, WANT_DISP);
+    const StreamCfg c = stream_cfg<PX, THREADS - 32>(p, MIX, MASKMODE == SMASK_DENSE, MIX ? 2 : 1, WANT_DISP, MINB > 3 ? 220 / MINB : 0);
     const int threads = c.nc + 32;
     if (threads > THREADS) return false;
     const size_t smem = stream_smem_bytes(c, p.d.N, MIX, MASKMODE == SMASK_DENSE, MIX ? 2 : 1, WANT_DISP);
@@ -1229,6 +1229,11 @@ inline bool launch_bwd_stream_w(const WarpParams& p, cudaStream_t st, bool dry) 
         return false;
     }
     if (W % 8 == 0 && W / 8 <= 160 && tuning().stream_px8) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 8, 192, 1>(p, st, dry);
+    if constexpr (!MIX && MASKMODE == SMASK_ROW) {
+        // plain narrow backward: four resident CTAs at 80 registers with a 2 x 3 ring beat three at 96 registers with 2 x 5
+        // (0.1619 vs 0.1640 ms at cfg 2, profiles/r2t_*); pd_tuning.stream_bwd_minb = 3 keeps the three-CTA build for A/B runs
+        if (W / 4 <= 160 && tuning().stream_bwd_minb != 3) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 4, 192, 4>(p, st, dry);
+    }
     if (W / 4 <= 160) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 4, 192, MIX ? 2 : 3>(p, st, dry);
     if (W / 4 <= 320) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 4, 352, 1>(p, st, dry);
     return false;
