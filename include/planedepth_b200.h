@@ -163,7 +163,7 @@ const char* pd_last_error(void);
 
 /* Launch tuning of the streamed row kernels: a process-wide block for tests (forcing the persistent loop to iterate),
  * benchmarks and kernel experiments.  Initialised ONCE at library load from the environment (PD_STREAM_CTAS,
- * PD_STREAM_HS, PD_STREAM_NST, PD_STREAM_SMEM_KB, PD_STREAM_PX8, PD_STREAM_FWD_MINB, PD_STREAM_BWD_MINB, PD_STREAM_NO_L2_HINT, PD_SSIM_TILES), values clamped to legal ranges;
+ * PD_STREAM_HS, PD_STREAM_NST, PD_STREAM_SMEM_KB, PD_STREAM_PX8, PD_STREAM_FWD_MINB, PD_STREAM_BWD_MINB, PD_STREAM_NO_L2_HINT, PD_SSIM_TILES, PD_TAIL_DIRECT), values clamped to legal ranges;
  * 0 = the library's default.  Numerics never depend on it (PD_FLAG_EXACT_COORDS is a per-call descriptor flag). */
 typedef struct pd_tuning {
     int32_t stream_ctas_per_sm; /* cap on resident CTAs per SM of the persistent grids (0 = occupancy limit) */
@@ -176,7 +176,8 @@ typedef struct pd_tuning {
     int32_t stream_fwd_minb;    /* resident CTAs per SM the plain narrow forward is compiled for: 0 / 4 = default, 5, 6 (experiments) */
     int32_t stream_no_l2_hint;  /* 1: the logit / sigma / mask rows travel without the L2 evict-first policy (A/B measurements) */
     int32_t stream_bwd_minb;    /* resident CTAs per SM of the plain narrow backward: 0 / 4 = default, 3 = the three-CTA build (A/B runs) */
-    int32_t reserved[6];
+    int32_t tail_direct;        /* 1: pd_plane_tail_* use the thread-per-pixel kernels instead of the TMA-tile kernels (A/B runs, tests) */
+    int32_t reserved[5];
 } pd_tuning;
 void pd_get_tuning(pd_tuning* out);
 void pd_set_tuning(const pd_tuning* in); /* NULL restores the values read from the environment at load */

@@ -67,7 +67,7 @@ class WarpGradOut(C.Structure):
 class Tuning(C.Structure):
     _fields_ = [("stream_ctas_per_sm", C.c_int32), ("stream_hs", C.c_int32), ("stream_nst", C.c_int32), ("stream_smem_kb", C.c_int32),
                 ("stream_px8", C.c_int32), ("ssim_tiles", C.c_int32), ("homo_tiles", C.c_int32), ("stream_fwd_minb", C.c_int32),
-                ("stream_no_l2_hint", C.c_int32), ("stream_bwd_minb", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("stream_no_l2_hint", C.c_int32), ("stream_bwd_minb", C.c_int32), ("tail_direct", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class WarpGradIn(C.Structure):

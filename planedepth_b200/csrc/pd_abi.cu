@@ -41,6 +41,7 @@ pd_tuning sanitize(pd_tuning t) {
     t.homo_tiles = clampi(t.homo_tiles, -1, 1);
     t.stream_fwd_minb = (t.stream_fwd_minb == 5 || t.stream_fwd_minb == 6) ? t.stream_fwd_minb : 0;
     t.stream_no_l2_hint = t.stream_no_l2_hint != 0;
+    t.tail_direct = t.tail_direct != 0;
     t.stream_bwd_minb = (t.stream_bwd_minb == 3 || t.stream_bwd_minb == 4) ? t.stream_bwd_minb : 0;
     return t;
 }
@@ -63,6 +64,7 @@ pd_tuning tuning_from_env() {
     t.homo_tiles = env_int("PD_HOMO_TILES");
     t.stream_fwd_minb = env_int("PD_STREAM_FWD_MINB");
     t.stream_no_l2_hint = env_int("PD_STREAM_NO_L2_HINT");
+    t.tail_direct = env_int("PD_TAIL_DIRECT");
     t.stream_bwd_minb = env_int("PD_STREAM_BWD_MINB");
     return sanitize(t);
 }

@@ -2,7 +2,7 @@
 #include <string.h>
 
 #include "pd_occlusion.cuh"
-#include "pd_tail.cuh"
+#include "pd_tail_tile.cuh"
 
 using pd::check_device;
 using pd::check_launch;
@@ -54,6 +54,19 @@ int pd_plane_tail_fwd(const pd_tail_desc* d, const pd_tail_in* in, pd_tail_out* 
         return fail(PD_ERR_ARG, "logits / probability / disp / stats (and sigma with mixture) outputs must not be NULL");
     if ((rc = check_device())) return rc;
     p.logits = out->logits, p.sigma = out->sigma, p.prob = out->probability, p.pi = out->pi, p.disp = out->disp, p.depth = out->depth, p.stats = out->stats;
+    pd::tl::TileCfg tc;
+    if (!pd::tuning().tail_direct && pd::tl::tile_cfg(p, d->mixture != 0, 2, tc) && pd::tl::tile_ptrs_ok(p)) {
+        // TMA-tile kernel: one CTA per (row, column tile), every plane row of the tile in flight at once
+        const unsigned tgrid = (unsigned)((int64_t)d->B * d->H * tc.tiles);
+        if (d->mixture) {
+            loss_smem_optin(pd::tl::tail_fwd_tile_kernel<true>, tc.smem);
+            pd::tl::tail_fwd_tile_kernel<true><<<tgrid, tc.threads, tc.smem, (cudaStream_t)stream>>>(p, tc.tw, tc.tiles);
+        } else {
+            loss_smem_optin(pd::tl::tail_fwd_tile_kernel<false>, tc.smem);
+            pd::tl::tail_fwd_tile_kernel<false><<<tgrid, tc.threads, tc.smem, (cudaStream_t)stream>>>(p, tc.tw, tc.tiles);
+        }
+        return check_launch("tail_fwd_tile");
+    }
     const int T = tail_threads(d->N);
     const size_t smem = (size_t)d->N * T * sizeof(float);
     const unsigned grid = (unsigned)(((int64_t)d->B * p.hw + T - 1) / T);
@@ -85,6 +98,18 @@ int pd_plane_tail_bwd(const pd_tail_desc* d, const pd_tail_in* in, const pd_tail
     if (p.g_dl && !p.g_dl_dense) {
         cudaError_t e = cudaMemsetAsync(p.g_dl, 0, (size_t)strided_extent(gs, d->B, d->N, d->H, d->W) * sizeof(float), st);
         if (e != cudaSuccess) return fail(PD_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    }
+    pd::tl::TileCfg tc;
+    if (!pd::tuning().tail_direct && pd::tl::tile_cfg(p, false, 3, tc) && pd::tl::tile_ptrs_ok(p)) {
+        const unsigned tgrid = (unsigned)((int64_t)d->B * d->H * tc.tiles);
+        if (d->mixture) {
+            loss_smem_optin(pd::tl::tail_bwd_tile_kernel<true>, tc.smem);
+            pd::tl::tail_bwd_tile_kernel<true><<<tgrid, tc.threads, tc.smem, st>>>(p, tc.tw, tc.tiles);
+        } else {
+            loss_smem_optin(pd::tl::tail_bwd_tile_kernel<false>, tc.smem);
+            pd::tl::tail_bwd_tile_kernel<false><<<tgrid, tc.threads, tc.smem, st>>>(p, tc.tw, tc.tiles);
+        }
+        return check_launch("tail_bwd_tile");
     }
     const int T = tail_threads(d->N);
     const size_t smem = ((size_t)d->N * T + d->N) * sizeof(float);

@@ -659,12 +659,20 @@ def test_bf16_storage_falls_back_to_upcast_where_unserved():
 # ------------------------------------------------------------------------------------------------
 # decoder tail (networks/depth_decoder.py:258-291) through pd_plane_tail_fwd / _bwd
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("direct", [False, True])
 @pytest.mark.parametrize("name", ["tail_plain", "tail_mix"])
-def test_decoder_tail_matches_reference_golden(name):
+def test_decoder_tail_matches_reference_golden(name, direct):
+    """Both kernel families: the TMA-tile kernels (default) and the thread-per-pixel kernels (pd_tuning.tail_direct; shapes
+    the tiles do not cover)."""
     import os
 
     from helpers import GOLDEN
-    from planedepth_b200.boundary import decoder_tail
+    from planedepth_b200 import _lib
+    from planedepth_b200.boundary import decoder_tail as _tail
+
+    def decoder_tail(*a):
+        with _lib.tuned(tail_direct=int(direct)):
+            return _tail(*a)
 
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     mix = bool(z["mixture"])
@@ -676,7 +684,8 @@ def test_decoder_tail_matches_reference_golden(name):
     L = (out["logits"] * T("A")).sum() + (out["disp"] * T("Cd")).sum()
     if mix:
         L = L + (out["sigma"] * T("Bm")).sum()
-    L.backward()
+    with _lib.tuned(tail_direct=int(direct)):
+        L.backward()
     for k in ["logits", "probability"] + (["sigma"] if mix else []):
         check(out[k], z["out_" + k], TOL, k)
     for k in ("disp", "depth"):  # O(10..100): relative
@@ -685,14 +694,22 @@ def test_decoder_tail_matches_reference_golden(name):
         check(leaf.grad, z[k], TOL * (float(np.abs(z[k]).max()) + 1e-12), k, allow_frac=2e-4)
 
 
+@pytest.mark.parametrize("direct", [False, True])
+@pytest.mark.parametrize("shape", [(2, 9, 12, 64), (1, 49, 3, 640), (1, 20, 3, 640), (1, 63, 2, 1280), (1, 5, 4, 20)])
 @pytest.mark.parametrize("mix", [False, True])
-@pytest.mark.parametrize("layout", ["expand", "dense_u8"])
-def test_decoder_tail_matches_oracle(mix, layout):
-    """Saturating sigmas (clamp gate), masked planes, the decoder's stride-0 disparity (compact gradient), upstream
-    gradients on every output incl. probability and depth."""
-    from planedepth_b200.boundary import decoder_tail
+@pytest.mark.parametrize("layout", ["expand", "dense_u8", "rowmask"])
+def test_decoder_tail_matches_oracle(mix, layout, shape, direct):
+    """Saturating sigmas (clamp gate), masked planes, the decoder's stride-0 disparity (compact gradient), a row-constant
+    mask and per-row disparities (xz planes), upstream gradients on every output incl. probability and depth; BASELINE widths
+    and plane counts (several column tiles per row, the mixture's narrower tiles), a width no tile covers."""
+    from planedepth_b200 import _lib
+    from planedepth_b200.boundary import decoder_tail as _tail
 
-    B, N, H, W = 2, 9, 12, 64
+    def decoder_tail(*a):
+        with _lib.tuned(tail_direct=int(direct)):
+            return _tail(*a)
+
+    B, N, H, W = shape
     g = torch.Generator().manual_seed(31)
     lr = 2.0 * torch.randn(B, N, H, W, generator=g)
     sr = 4.0 * torch.randn(B, N, H, W, generator=g)  # sigmoid reaches below 0.01
@@ -702,6 +719,9 @@ def test_decoder_tail_matches_oracle(mix, layout):
     if layout == "dense_u8":
         bump = 0.3 * torch.randn(B, N, H, W, generator=g)
         mask = mask.bool()
+    if layout == "rowmask":  # x-constant geometry handed over with zero x strides (the compact decoder patch of INTEGRATION.md)
+        mask = mask[..., :1].contiguous().expand(-1, -1, -1, W)
+        rowd = 1.0 + 0.05 * torch.arange(H, dtype=torch.float32).reshape(1, 1, H, 1)
     ws = [torch.randn(B, N, H, W, generator=g) for _ in range(3)] + [torch.randn(B, 1, H, W, generator=g) for _ in range(2)]
 
     def run(dev, fn):
@@ -711,12 +731,15 @@ def test_decoder_tail_matches_oracle(mix, layout):
         dl = b_.expand(B, N, H, W)
         if layout == "dense_u8":
             dl = dl + bump.to(dev)
-        out = fn(l_, s_, mask.to(dev), dl, mix)
+        if layout == "rowmask":
+            dl = (b_.expand(B, N, H, 1) * rowd.to(dev)).expand(B, N, H, W)
+        out = fn(l_, s_, (mask[..., :1].contiguous().to(dev).expand(-1, -1, -1, W) if layout == "rowmask" else mask.to(dev)), dl, mix)
         w = [t.to(dev) for t in ws]
         L = (out["logits"] * w[0]).sum() + (out["probability"] * w[2]).sum() + (out["disp"] * w[3]).sum() + 50.0 * (out["depth"] * w[4]).sum()
         if mix:
             L = L + (out["sigma"] * w[1]).sum()
-        L.backward()
+        with _lib.tuned(tail_direct=int(direct)):
+            L.backward()
         return out, (l_, s_, b_)
 
     want, lw = run("cpu", O.decoder_tail)
