@@ -72,6 +72,16 @@ __device__ __forceinline__ float ssim_val(const WinStats& w, float& n, float& d)
     return (1.0f - n / d) * 0.5f;  // layers.py:303-306 before the clamp
 }
 
+// n / d for d in [C1*C2, ~10] (no denormals, no overflow): reciprocal estimate + one Newton step, quotient with a residual
+// correction (Markstein) -- the correctly rounded quotient of layers.py:306 without the IEEE-division sequence and its
+// slow-path branch (cf. homo_coords() of pd_warp_homo.cuh).  id returns the refined 1 / d.
+__device__ __forceinline__ float quotient_rn(float n, float d, float& id) {
+    const float r0 = fast_rcp(d);
+    id = fmaf(r0, fmaf(-d, r0, 1.0f), r0);
+    const float q0 = n * id;
+    return fmaf(fmaf(-q0, d, n), id, q0);
+}
+
 __device__ __forceinline__ float block_sum(float v, float* red) {
     v = warp_sum(v);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -416,8 +426,8 @@ __global__ void __launch_bounds__(SW_THREADS, 2) ssim_l1_stream_kernel(const Los
                 const float n = a1c * a2c, d = b1c * b2c;
                 // the value feeds comparisons (clamp, automask min): IEEE division as in layers.py:306, so that knife-edge
                 // decisions fall the way the reference's do; the smooth derivative terms use the fast reciprocal
-                const float v = (1.0f - __fdiv_rn(n, d)) * 0.5f;
-                const float id = __fdividef(1.0f, d);
+                float id;
+                const float v = (1.0f - quotient_rn(n, d, id)) * 0.5f;
                 ss += fminf(fmaxf(v, 0.0f), 1.0f);
                 l1 += fabsf(av[P][c] - bv[P][c]);
                 ca[c] = cb[c] = cc[c] = 0.0f;
@@ -437,8 +447,10 @@ __global__ void __launch_bounds__(SW_THREADS, 2) ssim_l1_stream_kernel(const Los
                     u.sx = (Sh[O][c][1] + Sh[P][c][1] + hs[1]) * k9 - u.mx * u.mx;
                     u.sy = w.sy;
                     u.sxy = (Sh[O][c][2] + Sh[P][c][2] + hs[2]) * k9 - u.mx * u.my;
-                    float na, da;
-                    ssa += fminf(fmaxf(ssim_val(u, na, da), 0.0f), 1.0f);
+                    const float na = (2.0f * u.mx * u.my + kC1) * (2.0f * u.sxy + kC2);
+                    const float da = (u.mx * u.mx + u.my * u.my + kC1) * (u.sx + u.sy + kC2);
+                    float ida;
+                    ssa += fminf(fmaxf((1.0f - quotient_rn(na, da, ida)) * 0.5f, 0.0f), 1.0f);
                     l1a += fabsf(sv[P][c] - bv[P][c]);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) Sh[O][c][k] = hs[k];
