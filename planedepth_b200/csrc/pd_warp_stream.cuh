@@ -48,6 +48,7 @@ struct StreamCfg {
     int nst;      // ring stages
     int nblk;     // blocks per row group = ceil(N / hs)
     int ngroups;  // ceil(B * H / rpc)
+    int early;    // 1: the producer stages the NEXT group's coefficients / source rows while this one streams (producer_loop)
     int nc;       // consumer threads (multiple of 32); the CTA has nc + 32 threads, the last warp produces
     int l2_hint;  // streamed rows carry the L2 evict-first policy
     int bf16;     // logits / sigma / their gradients are stored as bf16 (pd_warp_desc.dtype)
@@ -324,26 +325,35 @@ __device__ __forceinline__ void producer_loop(const WarpParams& p, const StreamC
     const uint64_t pol = l2_evict_first_policy();
     const bool hint = c.l2_hint != 0;
     int stage = 0, use = 0;  // use = how many times the ring wrapped
+    // coefficients and source rows of one row group into its (group & 1) buffers
+    auto stage_group = [&](int it2) {
+        const int g2 = blockIdx.x + it2 * gridDim.x;
+        const int r0 = g2 * c.rpc;
+        const int nr = min(c.rpc, rows_total - r0);
+        stage_coef<MASKMODE>(p, c, s.coef + (size_t)(it2 & 1) * c.rpc * N, g2, rows_total);
+        __syncwarp();
+        if (lane == 0) {
+            uint64_t* bar = s.bars + BAR_SRC + (it2 & 1);
+            mbar_expect_tx(bar, (uint32_t)(nr * 3) * rowbytes);
+            for (int r = 0; r < nr; ++r) {
+                const int row = r0 + r, b = row / H, y = row - b * H;
+                const float* gp = p.in.src + ((int64_t)b * 3 * H + y) * W;
+                float* sp = s.src + ((size_t)((it2 & 1) * c.rpc + r) * 3) * c.pitch + PAD;
+                for (int ch = 0; ch < 3; ++ch) tma_row(sp + (size_t)ch * c.pitch, gp + (int64_t)ch * p.hw, rowbytes, bar);
+            }
+        }
+    };
+    // With more blocks than ring stages the NEXT group is staged while this one streams: at block nst the awaited release
+    // is of block 0 of this group by every consumer warp, so the previous group (the other user of those buffers and of
+    // that barrier) is finished.  Otherwise a group is staged at its own first block.
+    const bool early = c.nblk > c.nst && c.early;
     for (int it = 0; it < nit; ++it) {
         const int g = blockIdx.x + it * gridDim.x;
         const int row0 = g * c.rpc;
         const int nrows = min(c.rpc, rows_total - row0);
         for (int j = 0; j < c.nblk; ++j) {
             if (use > 0) mbar_wait(s.bars + BAR_EMPTY + stage, (use - 1) & 1);
-            if (j == 0) {
-                stage_coef<MASKMODE>(p, c, s.coef + (size_t)(it & 1) * c.rpc * N, g, rows_total);
-                __syncwarp();
-                if (lane == 0) {
-                    uint64_t* bar = s.bars + BAR_SRC + (it & 1);
-                    mbar_expect_tx(bar, (uint32_t)(nrows * 3) * rowbytes);
-                    for (int r = 0; r < nrows; ++r) {
-                        const int row = row0 + r, b = row / H, y = row - b * H;
-                        const float* gp = p.in.src + ((int64_t)b * 3 * H + y) * W;
-                        float* sp = s.src + ((size_t)((it & 1) * c.rpc + r) * 3) * c.pitch + PAD;
-                        for (int ch = 0; ch < 3; ++ch) tma_row(sp + (size_t)ch * c.pitch, gp + (int64_t)ch * p.hw, rowbytes, bar);
-                    }
-                }
-            }
+            if (j == 0 && (it == 0 || !early)) stage_group(it);
             const int n0 = j * c.hs, n1 = min(N, n0 + c.hs);
             if (BF16) {
                 // raw bf16 rows: [stage][plane][logit | sigma][row][W * 2 bytes]; the consumers convert them (see bf16_convert_block)
@@ -392,6 +402,8 @@ __device__ __forceinline__ void producer_loop(const WarpParams& p, const StreamC
                     }
                 }
             }
+            // after this block's copies are in flight: the staging costs a dependent global load of the disparities
+            if (early && j == c.nst && it + 1 < nit) stage_group(it + 1);
             if (++stage == c.nst) stage = 0, ++use;
         }
     }
@@ -1132,6 +1144,9 @@ inline StreamCfg stream_cfg(const WarpParams& p, bool mix, bool dense, int ne_bw
     if (c.nst > c.nblk) c.nst = c.nblk;  // reuse of the per-group buffers relies on nst <= nblk (see producer_loop)
     c.ngroups = (p.d.B * p.d.H + c.rpc - 1) / c.rpc;
     c.l2_hint = tn.stream_no_l2_hint ? 0 : 1;
+    // measured (profiles/r2e2_*): staging the next row group early gains 0.6 - 1 % except in the narrow plain backward,
+    // whose two-stage ring loses 1 % to the producer's detour
+    c.early = narrow_plain_bwd ? 0 : 1;
     return c;
 }
 
