@@ -28,6 +28,7 @@ namespace pd {
 namespace ts {
 
 constexpr int PAD = 12;  // zero floats on both sides of every shared-memory row (>= window size)
+constexpr int PADB = 16;  // zero bf16 values on both sides of a raw bf16 row (32 bytes: the TMA destination stays 16-byte aligned)
 
 struct __align__(16) PlaneCoef {
     // first 16 bytes: everything the backward's gather phase needs (one 128-bit broadcast load)
@@ -216,10 +217,9 @@ struct Smem {
     float* sring;     // mixture: [nst*hs][rpc][pitch]
     float* mring;     // dense mask: [nst*hs][rpc][pitch]
     float* dbuf;      // backward: [2][hs][NE][rpc][pitch] exchange rows (NE = 1, mixture 2)
-    float* cbuf;      // bf16 storage: [2][hs][1 + mix][rpc][pitch] rows converted to fp32 by the consumers, double-buffered over blocks
     float* gacc;      // backward with d/d disp: [rpc][N]
     float* fend;      // one past the last float
-    unsigned char* bring;  // bf16 storage: TMA ring of raw bf16 rows [nst*hs][1 + mix][rpc][W * 2 bytes] (behind the float region)
+    unsigned char* bring;  // bf16 storage: TMA ring of raw bf16 rows [nst*hs][1 + mix][rpc][(W + 2 * PADB) * 2 bytes] (behind the float region)
 };
 
 __host__ __device__ inline size_t stream_smem_floats(const StreamCfg& c, int N, bool mix, bool dense, int ne_bwd, bool want_disp) {
@@ -227,13 +227,12 @@ __host__ __device__ inline size_t stream_smem_floats(const StreamCfg& c, int N, 
     const size_t streams = c.bf16 ? (dense ? 1 : 0) : (1 + (mix ? 1 : 0) + (dense ? 1 : 0));  // fp32 ring rows
     size_t f = 2 * 3 * rowf + (size_t)c.nst * c.hs * rowf * streams;
     f += (size_t)2 * c.hs * ne_bwd * rowf;
-    if (c.bf16) f += (size_t)2 * c.hs * (1 + (mix ? 1 : 0)) * rowf;  // cbuf
     if (want_disp) f += (size_t)c.rpc * N;
     return f;
 }
 
-// bytes of one raw bf16 row in the TMA ring (W % 8 == 0: a multiple of 16)
-__host__ __device__ inline size_t stream_bf16_row_bytes(const StreamCfg& c) { return (size_t)(c.pitch - 2 * PAD) * 2; }
+// bytes of one raw bf16 row in the TMA ring, zero pads included (W % 8 == 0: a multiple of 16)
+__host__ __device__ inline size_t stream_bf16_row_bytes(const StreamCfg& c) { return (size_t)(c.pitch - 2 * PAD + 2 * PADB) * 2; }
 
 __host__ __device__ inline size_t stream_smem_bytes(const StreamCfg& c, int N, bool mix, bool dense, int ne_bwd, bool want_disp) {
     size_t b = BAR_BYTES + (size_t)2 * c.rpc * N * sizeof(PlaneCoef) + stream_smem_floats(c, N, mix, dense, ne_bwd, want_disp) * sizeof(float) + 16;
@@ -256,8 +255,6 @@ __device__ __forceinline__ Smem carve(unsigned char* raw, const StreamCfg& c, in
     if (dense) q += (size_t)c.nst * c.hs * rowf;
     s.dbuf = q;
     q += (size_t)2 * c.hs * ne_bwd * rowf;
-    s.cbuf = q;
-    if (c.bf16) q += (size_t)2 * c.hs * (1 + (mix ? 1 : 0)) * rowf;
     s.gacc = q;
     if (want_disp) q += (size_t)c.rpc * N;
     s.fend = q;
@@ -272,6 +269,17 @@ __device__ __forceinline__ void zero_pads(const Smem& s, const StreamCfg& c, int
     for (int i = threadIdx.x; i < nrows * 2 * PAD; i += blockDim.x) {
         const int rw = i / (2 * PAD), q = i - rw * 2 * PAD;
         s.src[(size_t)rw * c.pitch + (q < PAD ? q : W + q)] = 0.0f;
+    }
+}
+
+// same for the raw bf16 ring rows (PADB values on both sides, written as 32-bit words)
+__device__ __forceinline__ void zero_pads_bf16(const Smem& s, const StreamCfg& c, int W, int nrows) {
+    const size_t rbp = stream_bf16_row_bytes(c);
+    constexpr int WORDS = PADB / 2;  // 32-bit words per pad
+    for (int i = threadIdx.x; i < nrows * 2 * WORDS; i += blockDim.x) {
+        const int rw = i / (2 * WORDS), q = i - rw * 2 * WORDS;
+        uint32_t* row = reinterpret_cast<uint32_t*>(s.bring + (size_t)rw * rbp);
+        row[q < WORDS ? q : W / 2 + q] = 0u;
     }
 }
 
@@ -356,7 +364,7 @@ __device__ __forceinline__ void producer_loop(const WarpParams& p, const StreamC
             if (j == 0 && (it == 0 || !early)) stage_group(it);
             const int n0 = j * c.hs, n1 = min(N, n0 + c.hs);
             if (BF16) {
-                // raw bf16 rows: [stage][plane][logit | sigma][row][W * 2 bytes]; the consumers convert them (see bf16_convert_block)
+                // raw bf16 rows: [stage][plane][logit | sigma][row][PADB | W | PADB]; the consumers' tap windows convert on load
                 if (lane == 0) {
                     uint64_t* bar = s.bars + BAR_FULL + stage;
                     const uint32_t rb = rowbytes / 2;
@@ -367,16 +375,17 @@ __device__ __forceinline__ void producer_loop(const WarpParams& p, const StreamC
                     for (int r = 0; r < nrows; ++r) {
                         const int row = row0 + r, b = row / H, y = row - b * H;
                         int64_t off = ((((int64_t)b * N + n0) * H + y) * W) * 2;
-                        unsigned char* dst = s.bring + ((size_t)(stage * c.hs) * NEc * c.rpc + r) * rb;
+                        const size_t rbp = stream_bf16_row_bytes(c);
+                        unsigned char* dst = s.bring + ((size_t)(stage * c.hs) * NEc * c.rpc + r) * rbp + PADB * 2;
                         for (int n = n0; n < n1; ++n) {
                             if (hint) tma_row_hint(reinterpret_cast<float*>(dst), reinterpret_cast<const float*>(lg + off), rb, bar, pol);
                             else tma_row(reinterpret_cast<float*>(dst), reinterpret_cast<const float*>(lg + off), rb, bar);
                             if (MIX) {
-                                if (hint) tma_row_hint(reinterpret_cast<float*>(dst + (size_t)c.rpc * rb), reinterpret_cast<const float*>(sg + off), rb, bar, pol);
-                                else tma_row(reinterpret_cast<float*>(dst + (size_t)c.rpc * rb), reinterpret_cast<const float*>(sg + off), rb, bar);
+                                if (hint) tma_row_hint(reinterpret_cast<float*>(dst + (size_t)c.rpc * rbp), reinterpret_cast<const float*>(sg + off), rb, bar, pol);
+                                else tma_row(reinterpret_cast<float*>(dst + (size_t)c.rpc * rbp), reinterpret_cast<const float*>(sg + off), rb, bar);
                             }
                             off += p.hw * 2;
-                            dst += (size_t)NEc * c.rpc * rb;
+                            dst += (size_t)NEc * c.rpc * rbp;
                         }
                     }
                 }
@@ -434,23 +443,26 @@ __device__ __forceinline__ bool all_ones(const float (&m)[PX]) {
     return acc == 0x3f800000u && orr == 0x3f800000u;
 }
 
-// bf16 storage: every consumer thread converts the PX values it owns of each plane row of the block that just landed (raw bf16,
-// TMA ring) into the double-buffered fp32 rows the tap windows read; the ring stage is free again right after this
-template <bool MIX, int PX>
-__device__ __forceinline__ void bf16_convert_block(uint32_t braw, uint32_t crow, uint32_t rb_rpc, uint32_t rowpitch4, int np) {
-    // braw: shared address of this thread's PX bf16 values in the first plane's logit row; crow: of its PX floats in cbuf
-    constexpr int NEc = MIX ? 2 : 1;
-    for (int q = 0; q < np; ++q, braw += NEc * rb_rpc, crow += NEc * rowpitch4) {
-#pragma unroll
-        for (int e = 0; e < NEc; ++e) {
-#pragma unroll
-            for (int i = 0; i < PX / 4; ++i) {
-                uint32_t lo, hi;
-                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(braw + e * rb_rpc + 8 * i));
-                sts128(crow + e * rowpitch4 + 16 * i, __uint_as_float(lo << 16), __uint_as_float(lo & 0xffff0000u), __uint_as_float(hi << 16),
-                       __uint_as_float(hi & 0xffff0000u));
-            }
-        }
+// bf16 storage: a tap window of 8 consecutive bf16 values from the 8-byte aligned shared address a, widened to fp32 in
+// registers (bf16 -> fp32 is a 16-bit shift / mask: one ALU instruction per value the window body actually uses)
+__device__ __forceinline__ void load_window_bf16(uint32_t a, float (&v)[8]) {
+    uint32_t w0, w1, w2, w3;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(a));
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w2), "=r"(w3) : "r"(a + 8));
+    v[0] = __uint_as_float(w0 << 16), v[1] = __uint_as_float(w0 & 0xffff0000u);
+    v[2] = __uint_as_float(w1 << 16), v[3] = __uint_as_float(w1 & 0xffff0000u);
+    v[4] = __uint_as_float(w2 << 16), v[5] = __uint_as_float(w2 & 0xffff0000u);
+    v[6] = __uint_as_float(w3 << 16), v[7] = __uint_as_float(w3 & 0xffff0000u);
+}
+
+// logit / sigma window of the plane body: fp32 rows or raw bf16 rows
+template <int WF, bool BF16>
+__device__ __forceinline__ void load_plane_window(uint32_t a, float (&v)[WF]) {
+    if constexpr (BF16) {
+        static_assert(WF == 8, "bf16 storage: 4 pixels per thread");
+        load_window_bf16(a, v);
+    } else {
+        load_window<WF>(a, v);
     }
 }
 
@@ -478,13 +490,13 @@ struct FwdAcc {
     float tr[MIX ? PX : 1], tg[MIX ? PX : 1], tb[MIX ? PX : 1], ea[MIX ? PX : 1];
 };
 
-template <bool MIX, int PX, int R, bool PERPIX>
+template <bool MIX, int PX, int R, bool PERPIX, bool BF16 = false>
 __device__ __forceinline__ void fwd_plane(uint32_t srow, uint32_t lrow, uint32_t sgrow, uint32_t pitch4, const PlaneCoef& k,
                                           const float (&mm)[PX], FwdAcc<MIX, PX>& a) {
-    // srow / lrow / sgrow: shared addresses of the (already window-aligned) first float of the tap windows
+    // srow / lrow / sgrow: shared addresses of the (already window-aligned) first value of the tap windows
     constexpr int WF = PX + 4;
     float v[WF], t[PX];
-    load_window<WF>(lrow, v);
+    load_plane_window<WF, BF16>(lrow, v);
 #pragma unroll
     for (int i = 0; i < PX; ++i) {
         if (PERPIX) t[i] = fmaf(fmaf(k.wl0, v[R + i], k.wl1 * v[R + i + 1]), mm[i], -a.Ml2[i]);
@@ -533,7 +545,7 @@ __device__ __forceinline__ void fwd_plane(uint32_t srow, uint32_t lrow, uint32_t
         for (int i = 0; i < PX; ++i) a.R2[i] = fmaf(a0[i], v[R + i], fmaf(a1[i], v[R + i + 1], a.R2[i]));
     } else {
         float es[PX], inv[PX], err[PX];
-        load_window<WF>(sgrow, v);
+        load_plane_window<WF, BF16>(sgrow, v);
 #pragma unroll
         for (int i = 0; i < PX; ++i) {
             float s = fmaf(k.wc0, v[R + i], k.wc1 * v[R + i + 1]);
@@ -578,17 +590,18 @@ __device__ __forceinline__ void fwd_plane(uint32_t srow, uint32_t lrow, uint32_t
 }
 
 // at4 = byte offset of the first tap inside the row; the windows start at the aligned offset below it
-template <bool MIX, int PX, bool PERPIX>
+template <bool MIX, int PX, bool PERPIX, bool BF16 = false>
 __device__ __forceinline__ void fwd_plane_any(uint32_t srow, uint32_t lrow, uint32_t sgrow, uint32_t pitch4, int at4, int W4, const PlaneCoef& k,
                                               const float (&mm)[PX], FwdAcc<MIX, PX>& a) {
     const int wo = window_off(at4, W4);
-    srow += wo, lrow += wo, sgrow += wo;
+    const int wl = BF16 ? wo / 2 : wo;  // the logit / sigma rows hold 2-byte values with bf16 storage
+    srow += wo, lrow += wl, sgrow += wl;
     if (at4 & 8) {
-        if (at4 & 4) fwd_plane<MIX, PX, 3, PERPIX>(srow, lrow, sgrow, pitch4, k, mm, a);
-        else fwd_plane<MIX, PX, 2, PERPIX>(srow, lrow, sgrow, pitch4, k, mm, a);
+        if (at4 & 4) fwd_plane<MIX, PX, 3, PERPIX, BF16>(srow, lrow, sgrow, pitch4, k, mm, a);
+        else fwd_plane<MIX, PX, 2, PERPIX, BF16>(srow, lrow, sgrow, pitch4, k, mm, a);
     } else {
-        if (at4 & 4) fwd_plane<MIX, PX, 1, PERPIX>(srow, lrow, sgrow, pitch4, k, mm, a);
-        else fwd_plane<MIX, PX, 0, PERPIX>(srow, lrow, sgrow, pitch4, k, mm, a);
+        if (at4 & 4) fwd_plane<MIX, PX, 1, PERPIX, BF16>(srow, lrow, sgrow, pitch4, k, mm, a);
+        else fwd_plane<MIX, PX, 0, PERPIX, BF16>(srow, lrow, sgrow, pitch4, k, mm, a);
     }
 }
 
@@ -601,6 +614,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
     const int rows_total = p.d.B * H;
     const Smem s = carve(smem_raw, cfg, N, MIX, DENSE, 0, false);
     zero_pads(s, cfg, W);
+    if constexpr (BF16) zero_pads_bf16(s, cfg, W, cfg.nst * cfg.hs * NEc * cfg.rpc);
     if (threadIdx.x == 0) {
         const uint32_t readers = (uint32_t)(cfg.nc / 32);
         for (int i = 0; i < cfg.nst; ++i) {
@@ -624,12 +638,12 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
     const uint32_t bars = smem_u32(s.bars), coef0 = smem_u32(s.coef), src0 = smem_u32(s.src + PAD), lring0 = smem_u32(s.lring + PAD);
     const uint32_t pitch4 = (uint32_t)pitch * 4u, rowpitch4 = (uint32_t)rpc * pitch4;
     // fp32 storage: logit rows of a stage are rpc rows apart, the sigma ring sits sdelta behind the logit ring.  bf16 storage:
-    // the tap windows read the converted rows [plane][logit | sigma][row], double-buffered over blocks
-    const uint32_t sdelta = BF16 ? rowpitch4 : (uint32_t)((s.sring - s.lring) * sizeof(float));
+    // the tap windows read the raw rows [stage][plane][logit | sigma][row] (byte pitch rbp, interiors PADB values in)
+    const uint32_t rbp = (uint32_t)stream_bf16_row_bytes(cfg);
+    const uint32_t sdelta = BF16 ? (uint32_t)rpc * rbp : (uint32_t)((s.sring - s.lring) * sizeof(float));
     const uint32_t mdelta = (uint32_t)((s.mring - s.lring) * sizeof(float));
-    const uint32_t plane4 = BF16 ? NEc * rowpitch4 : rowpitch4;
-    const uint32_t cbuf0 = smem_u32(s.cbuf + PAD), bring0 = smem_u32(s.bring);
-    const uint32_t rb = (uint32_t)(W * 2), rb_rpc = rb * (uint32_t)rpc;
+    const uint32_t plane4 = BF16 ? NEc * (uint32_t)rpc * rbp : rowpitch4;
+    const uint32_t bring0 = smem_u32(s.bring) + PADB * 2;
     const int x04 = x0 * 4, W4 = W * 4;
     int stage = 0, jb = 0;
     uint32_t fphase = 0;
@@ -672,18 +686,8 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
             // in one phase of an empty barrier); the acquire also publishes the group's coefficients
             mbar_wait(bars + 8 * (BAR_FULL + stage), fphase);
             const int np = min(hs, N - j * hs);
-            if constexpr (BF16) {
-                // convert this thread's pixels of the block, release the raw stage, meet the other consumers: the windows
-                // below read what every thread converted.  Buffer (jb & 1) was last read in block jb - 2, which every thread
-                // finished before it passed the barrier of block jb - 1.
-                const uint32_t cb = cbuf0 + (uint32_t)((jb & 1) * hs * NEc * rpc + r) * pitch4;
-                if (active) bf16_convert_block<MIX, PX>(bring0 + (uint32_t)(stage * hs * NEc * rpc + r) * rb + (uint32_t)x0 * 2u, cb + x04, rb_rpc, rowpitch4, np);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bars + 8 * (BAR_EMPTY + stage));
-                consumer_sync(cfg.nc);
-            }
             if (active) {
-                uint32_t lrow = BF16 ? cbuf0 + (uint32_t)((jb & 1) * hs * NEc * rpc + r) * pitch4 : lring0 + (uint32_t)(stage * hs * rpc + r) * pitch4;
+                uint32_t lrow = BF16 ? bring0 + (uint32_t)(stage * hs * NEc * rpc + r) * rbp : lring0 + (uint32_t)(stage * hs * rpc + r) * pitch4;
                 for (int q = 0; q < np; ++q, lrow += plane4, coef_a += (uint32_t)sizeof(PlaneCoef)) {
                     const PlaneCoef k = load_coef(coef_a);
                     float mm[PX] = {};
@@ -694,13 +698,11 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_fwd_stream(const WarpParam
                         if (perpix) not_ones |= 1ull << (j * hs + q);
                     }
                     if (DENSE && perpix) fwd_plane_any<MIX, PX, true>(srow, lrow, lrow + sdelta, pitch4, x04 + k.k4, W4, k, mm, acc);
-                    else fwd_plane_any<MIX, PX, false>(srow, lrow, lrow + sdelta, pitch4, x04 + k.k4, W4, k, mm, acc);
+                    else fwd_plane_any<MIX, PX, false, BF16>(srow, lrow, lrow + sdelta, pitch4, x04 + k.k4, W4, k, mm, acc);
                 }
             }
-            if constexpr (!BF16) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bars + 8 * (BAR_EMPTY + stage));
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + 8 * (BAR_EMPTY + stage));
             if (++stage == cfg.nst) stage = 0, fphase ^= 1;
         }
         if (DENSE && p.mask_rows) {
@@ -760,14 +762,14 @@ __device__ __forceinline__ float sgn(float a, float b) { return (a > b) ? 1.0f :
 
 // phase A of one plane: dL/d(masked logit) [and dL/d(clamped-through sigma)] per target pixel into the exchange
 // rows; returns this thread's contribution to dL/d(sign*disparity) of the plane row
-template <bool MIX, bool WANT_DISP, int PX, int R, bool PERPIX>
+template <bool MIX, bool WANT_DISP, int PX, int R, bool PERPIX, bool BF16 = false>
 __device__ __forceinline__ float bwd_plane(uint32_t srow, uint32_t lrow, uint32_t sgrow, uint32_t pitch4, const PlaneCoef& k,
                                            const float (&mm)[PX], const BwdCtx<MIX, PX>& c, uint32_t dst, uint32_t fdelta) {
     // srow / lrow / sgrow: window-aligned shared addresses; dst: this thread's slot in the exchange row of dL/dlogit,
     // dst + fdelta the one of dL/dsigma
     constexpr int WF = PX + 4;
     float v[WF], pi[PX], Gn[PX], dlu[PX], gx[PX];
-    load_window<WF>(lrow, v);
+    load_plane_window<WF, BF16>(lrow, v);
 #pragma unroll
     for (int i = 0; i < PX; ++i) {
         float t;
@@ -807,7 +809,7 @@ __device__ __forceinline__ float bwd_plane(uint32_t srow, uint32_t lrow, uint32_
             if (WANT_DISP) gx[i] = fmaf(dl[i], dlu[i], pi[i] * (c.g0[i] * dr[i] + c.g1[i] * dg[i] + c.g2[i] * db[i]));
         }
     } else {
-        load_window<WF>(sgrow, v);
+        load_plane_window<WF, BF16>(sgrow, v);
 #pragma unroll
         for (int i = 0; i < PX; ++i) {
             float sraw = fmaf(k.wc0, v[R + i], k.wc1 * v[R + i + 1]);
@@ -855,17 +857,18 @@ __device__ __forceinline__ float bwd_plane(uint32_t srow, uint32_t lrow, uint32_
     return gsum;
 }
 
-template <bool MIX, bool WANT_DISP, int PX, bool PERPIX>
+template <bool MIX, bool WANT_DISP, int PX, bool PERPIX, bool BF16 = false>
 __device__ __forceinline__ float bwd_plane_any(uint32_t srow, uint32_t lrow, uint32_t sgrow, uint32_t pitch4, int at4, int W4, const PlaneCoef& k,
                                                const float (&mm)[PX], const BwdCtx<MIX, PX>& c, uint32_t dst, uint32_t fdelta) {
     const int wo = window_off(at4, W4);
-    srow += wo, lrow += wo, sgrow += wo;
+    const int wl = BF16 ? wo / 2 : wo;  // see fwd_plane_any
+    srow += wo, lrow += wl, sgrow += wl;
     if (at4 & 8) {
-        if (at4 & 4) return bwd_plane<MIX, WANT_DISP, PX, 3, PERPIX>(srow, lrow, sgrow, pitch4, k, mm, c, dst, fdelta);
-        return bwd_plane<MIX, WANT_DISP, PX, 2, PERPIX>(srow, lrow, sgrow, pitch4, k, mm, c, dst, fdelta);
+        if (at4 & 4) return bwd_plane<MIX, WANT_DISP, PX, 3, PERPIX, BF16>(srow, lrow, sgrow, pitch4, k, mm, c, dst, fdelta);
+        return bwd_plane<MIX, WANT_DISP, PX, 2, PERPIX, BF16>(srow, lrow, sgrow, pitch4, k, mm, c, dst, fdelta);
     }
-    if (at4 & 4) return bwd_plane<MIX, WANT_DISP, PX, 1, PERPIX>(srow, lrow, sgrow, pitch4, k, mm, c, dst, fdelta);
-    return bwd_plane<MIX, WANT_DISP, PX, 0, PERPIX>(srow, lrow, sgrow, pitch4, k, mm, c, dst, fdelta);
+    if (at4 & 4) return bwd_plane<MIX, WANT_DISP, PX, 1, PERPIX, BF16>(srow, lrow, sgrow, pitch4, k, mm, c, dst, fdelta);
+    return bwd_plane<MIX, WANT_DISP, PX, 0, PERPIX, BF16>(srow, lrow, sgrow, pitch4, k, mm, c, dst, fdelta);
 }
 
 // phase B of one plane: gradient of source column j = wc0 * D[j - k0] + wc1 * D[j - k0 - 1]
@@ -900,6 +903,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
     const int rows_total = p.d.B * H;
     const Smem s = carve(smem_raw, cfg, N, MIX, DENSE, NE, WANT_DISP);
     zero_pads(s, cfg, W);
+    if constexpr (BF16) zero_pads_bf16(s, cfg, W, cfg.nst * cfg.hs * NE * cfg.rpc);
     if (threadIdx.x == 0) {
         for (int i = 0; i < cfg.nst; ++i) {
             mbar_init(s.bars + BAR_FULL + i, 1);
@@ -921,11 +925,11 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
     const uint32_t bars = smem_u32(s.bars), coef0 = smem_u32(s.coef), src0 = smem_u32(s.src + PAD), lring0 = smem_u32(s.lring + PAD);
     const uint32_t dbuf0 = smem_u32(s.dbuf + PAD);
     const uint32_t pitch4 = (uint32_t)pitch * 4u, rowpitch4 = (uint32_t)rpc * pitch4;
-    const uint32_t sdelta = BF16 ? rowpitch4 : (uint32_t)((s.sring - s.lring) * sizeof(float));  // see rows_fwd_stream
+    const uint32_t rbp = (uint32_t)stream_bf16_row_bytes(cfg);  // see rows_fwd_stream
+    const uint32_t sdelta = BF16 ? (uint32_t)rpc * rbp : (uint32_t)((s.sring - s.lring) * sizeof(float));
     const uint32_t mdelta = (uint32_t)((s.mring - s.lring) * sizeof(float));
-    const uint32_t plane4 = BF16 ? NE * rowpitch4 : rowpitch4;
-    const uint32_t cbuf0 = smem_u32(s.cbuf + PAD), bring0 = smem_u32(s.bring);
-    const uint32_t rb = (uint32_t)(W * 2), rb_rpc = rb * (uint32_t)rpc;
+    const uint32_t plane4 = BF16 ? NE * (uint32_t)rpc * rbp : rowpitch4;
+    const uint32_t bring0 = smem_u32(s.bring) + PADB * 2;
     const int x04 = x0 * 4, W4 = W * 4;
     int stage = 0, jb = 0;
     uint32_t fphase = 0;
@@ -992,17 +996,9 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
             // exchange rows of this block: [plane][NE][rpc][pitch], double-buffered over blocks
             const uint32_t dblk = dbuf0 + (uint32_t)((jb & 1) * hs * NE * rpc + r) * pitch4;
             mbar_wait(bars + 8 * (BAR_FULL + stage), fphase);
-            if constexpr (BF16) {
-                // raw bf16 rows -> fp32 rows (cbuf, double-buffered like the exchange rows), then the raw stage is free
-                const uint32_t cb = cbuf0 + (uint32_t)((jb & 1) * hs * NE * rpc + r) * pitch4;
-                if (active) bf16_convert_block<MIX, PX>(bring0 + (uint32_t)(stage * hs * NE * rpc + r) * rb + (uint32_t)x0 * 2u, cb + x04, rb_rpc, rowpitch4, np);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bars + 8 * (BAR_EMPTY + stage));
-                consumer_sync(cfg.nc);
-            }
             // ---------------- phase A: per-target gradients into the exchange rows ----------------
             {
-                uint32_t lrow = BF16 ? cbuf0 + (uint32_t)((jb & 1) * hs * NE * rpc + r) * pitch4 : lring0 + (uint32_t)(stage * hs * rpc + r) * pitch4;
+                uint32_t lrow = BF16 ? bring0 + (uint32_t)(stage * hs * NE * rpc + r) * rbp : lring0 + (uint32_t)(stage * hs * rpc + r) * pitch4;
                 uint32_t coef_a = coef_g + (uint32_t)n0 * (uint32_t)sizeof(PlaneCoef);
                 uint32_t drow = dblk;
                 for (int q = 0; q < np; ++q, lrow += plane4, coef_a += (uint32_t)sizeof(PlaneCoef), drow += NE * rowpitch4) {
@@ -1021,7 +1017,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
                         if ((DENSE || SUMM) && perpix)
                             gsum = bwd_plane_any<MIX, WANT_DISP, PX, true>(srow, lrow, lrow + sdelta, pitch4, x04 + k.k4, W4, k, mm, c, drow + x04, rowpitch4);
                         else
-                            gsum = bwd_plane_any<MIX, WANT_DISP, PX, false>(srow, lrow, lrow + sdelta, pitch4, x04 + k.k4, W4, k, mm, c, drow + x04, rowpitch4);
+                            gsum = bwd_plane_any<MIX, WANT_DISP, PX, false, BF16>(srow, lrow, lrow + sdelta, pitch4, x04 + k.k4, W4, k, mm, c, drow + x04, rowpitch4);
                     }
                     if (WANT_DISP) {
                         // warp sum when the whole warp works on one row, per-thread shared atomics otherwise
@@ -1036,10 +1032,8 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
                     }
                 }
             }
-            if constexpr (!BF16) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bars + 8 * (BAR_EMPTY + stage));  // the ring stage is no longer needed
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + 8 * (BAR_EMPTY + stage));  // the ring stage is no longer needed
             if (++stage == cfg.nst) stage = 0, fphase ^= 1;
             // exchange rows of block jb complete.  They are double-buffered: block jb+1 writes the other buffer, and
             // block jb+2 is only written after the next barrier, which every thread reaches after this gather.
@@ -1126,7 +1120,8 @@ inline StreamCfg stream_cfg(const WarpParams& p, bool mix, bool dense, int ne_bw
     const pd_tuning& tn = tuning();  // clamped when it was set: hs >= 1, 1 <= nst <= MAX_STAGES
     // measured (profiles/r2c_*): the narrow plain backward prefers fewer, longer blocks (a consumer barrier per block)
     const bool narrow_plain_bwd = ne_bwd > 0 && !mix && c.nc <= 160;
-    c.hs = tn.stream_hs > 0 ? tn.stream_hs : (narrow_plain_bwd ? 5 : 4);
+    // bf16 forward: rows are half as long, so a stage of 8 planes costs what 4 cost in fp32 (measured, profiles/r2b2_*: 0.1026 -> 0.0989 ms)
+    c.hs = tn.stream_hs > 0 ? tn.stream_hs : (narrow_plain_bwd ? 5 : ((c.bf16 && ne_bwd == 0) ? 8 : 4));
     if (c.hs > p.d.N) c.hs = p.d.N;
     c.nst = tn.stream_nst > 0 ? tn.stream_nst : (narrow_plain_bwd ? 2 : 3);
     if (c.nst > MAX_STAGES) c.nst = MAX_STAGES;
@@ -1208,7 +1203,7 @@ inline bool launch_fwd_stream_m(const WarpParams& p, cudaStream_t st, bool dry) 
     if (p.d.dtype == PD_DTYPE_BF16) {  // bf16 storage: row masks, 4 pixels per thread, rows of whole 16-byte units
         if constexpr (MASKMODE == SMASK_ROW) {
             if (W % 8 != 0) return false;
-            if (W / 4 <= 160) return launch_fwd_stream_t<MIX, MASKMODE, 4, 192, MIX ? 2 : 3, true>(p, st, dry);
+            if (W / 4 <= 160) return launch_fwd_stream_t<MIX, MASKMODE, 4, 192, MIX ? 2 : 4, true>(p, st, dry);
             if (W / 4 <= 320) return launch_fwd_stream_t<MIX, MASKMODE, 4, 352, MIX ? 1 : 2, true>(p, st, dry);
         }
         return false;
@@ -1238,7 +1233,7 @@ inline bool launch_bwd_stream_w(const WarpParams& p, cudaStream_t st, bool dry) 
     if (p.d.dtype == PD_DTYPE_BF16) {
         if constexpr (MASKMODE == SMASK_ROW) {
             if (W % 8 != 0) return false;
-            if (W / 4 <= 160) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 4, 192, MIX ? 2 : 3, true>(p, st, dry);
+            if (W / 4 <= 160) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 4, 192, MIX ? 2 : 4, true>(p, st, dry);
             if (W / 4 <= 320) return launch_bwd_stream_t<MIX, MASKMODE, WANT_DISP, 4, 352, 1, true>(p, st, dry);
         }
         return false;
