@@ -275,14 +275,15 @@ __device__ __forceinline__ void prefetch_plane(const WarpParams& p, const RowCtx
 template <int MASKMODE>
 __device__ __forceinline__ bool plane_mask(const WarpParams& p, const RowCtx& c, int n, float mrow, float m[RP]) {
     // returns false when the mask is identically 1 for this thread's pixels (no multiplies needed)
-    if (MASKMODE == MASK_DENSE_F32) {
+    if constexpr (MASKMODE == MASK_DENSE_F32) {
         float4 v = ldg4(reinterpret_cast<const float*>(p.in.mask) + soff(p.d.mask_stride, c.b, n, c.y, c.x0));
         m[0] = v.x, m[1] = v.y, m[2] = v.z, m[3] = v.w;
         return true;
-    }
+    } else {
 #pragma unroll
-    for (int i = 0; i < RP; ++i) m[i] = mrow;
-    return mrow != 1.0f;
+        for (int i = 0; i < RP; ++i) m[i] = mrow;
+        return mrow != 1.0f;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
