@@ -35,16 +35,20 @@ struct HTaps {
     bool ix0, ix1, iy0, iy1;     // column x0 / x0+1, row y0 / y0+1 inside the image
 };
 
+// FAST: both image sizes admit the division-free round trip (rows_rcp() != 0), decided once per launch
+template <bool FAST>
 __device__ __forceinline__ float rt(float p, float size_m1, float rcp) {
-    return (rcp != 0.0f) ? roundtrip_fast(p, size_m1, rcp) : roundtrip(p, size_m1);
+    if constexpr (FAST) return roundtrip_fast(p, size_m1, rcp);
+    else return (rcp != 0.0f) ? roundtrip_fast(p, size_m1, rcp) : roundtrip(p, size_m1);
 }
 
 // ATen grid_sampler_2d (bilinear, zeros padding) taps of the sample position (x, y), cf. make_taps()
-__device__ __forceinline__ HTaps make_htaps(float x, float y, int W, int H) {
-    x = fminf(fmaxf(x, -2.0f), (float)(W + 1));
-    y = fminf(fmaxf(y, -2.0f), (float)(H + 1));
-    const float fx0 = floorf(x), fy0 = floorf(y);
-    const int x0 = (int)fx0, y0 = (int)fy0;
+__device__ __forceinline__ HTaps make_htaps(float x, float y, int W, int H, float Wp1, float Hp1) {
+    x = fminf(fmaxf(x, -2.0f), Wp1);  // Wp1 = W + 1, Hp1 = H + 1 as floats (hoisted by the caller)
+    y = fminf(fmaxf(y, -2.0f), Hp1);
+    // one float -> int conversion per axis; the integer goes back to float on the ALU pipe (exact: |x0| <= W + 1)
+    const int x0 = __float2int_rd(x), y0 = __float2int_rd(y);
+    const float fx0 = (float)x0, fy0 = (float)y0;
     HTaps t;
     t.rx1 = x - fx0, t.rx0 = (fx0 + 1.0f) - x;
     t.ry1 = y - fy0, t.ry0 = (fy0 + 1.0f) - y;
@@ -107,14 +111,17 @@ __device__ __forceinline__ void load_plane_params(const float* sh, int n, float4
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <bool MIX>
+template <bool MIX, bool FASTRT>
 __global__ void __launch_bounds__(HT) homo_fwd_kernel(const WarpParams p, const float4* __restrict__ rgbx, float rcp_w, float rcp_h) {
     extern __shared__ __align__(16) float sh[];  // [N][12]
     const int N = p.d.N, W = p.d.W, H = p.d.H;
-    const int64_t pix = (int64_t)blockIdx.x * HT + threadIdx.x;  // hw % HT == 0: a CTA stays inside one image
-    const int b = (int)(pix / p.hw);
-    const int rem = (int)(pix - (int64_t)b * p.hw);
+    // hw % HT == 0: a CTA stays inside one image, so the image index (and every per-image base pointer) is CTA-uniform
+    const int b = (int)(((int64_t)blockIdx.x * HT) / p.hw);
+    const int rem = (int)((int64_t)blockIdx.x * HT - (int64_t)b * p.hw) + (int)threadIdx.x;
+    const int64_t pix = (int64_t)b * p.hw + rem;
     const int y = rem / W, x = rem - y * W;
+    const float Wp1 = (float)(W + 1), Hp1 = (float)(H + 1);
+    const unsigned Wm1 = (unsigned)(W - 1), Hm1 = (unsigned)(H - 1);
     for (int i = threadIdx.x; i < N * 12; i += HT) sh[i] = __ldg(p.in.hmat + (int64_t)b * N * 12 + i);
     __syncthreads();
     const float fx = (float)x, fy = (float)y;
@@ -144,12 +151,13 @@ __global__ void __launch_bounds__(HT) homo_fwd_kernel(const WarpParams p, const 
         const HCoord c = homo_coords(h0, h1, h2, fx, fy, rx, ry, rz);
         float cr = 0.0f, cg = 0.0f, cb = 0.0f, l2 = 0.0f, sraw = 0.0f;  // a masked plane enters with logit 0, colour 0 (:580-583)
         if (c.m != 0.0f) {
-            float su = rt(c.u, p.wm1, rcp_w), sv = rt(c.v, p.hm1, rcp_h);
-            su = fminf(fmaxf(su, -2.0f), (float)(W + 1));
-            sv = fminf(fmaxf(sv, -2.0f), (float)(H + 1));
-            const float fx0 = floorf(su), fy0 = floorf(sv);
-            const int x0 = (int)fx0, y0 = (int)fy0;
-            if ((unsigned)x0 < (unsigned)(W - 1) && (unsigned)y0 < (unsigned)(H - 1)) {
+            float su = rt<FASTRT>(c.u, p.wm1, rcp_w), sv = rt<FASTRT>(c.v, p.hm1, rcp_h);
+            su = fminf(fmaxf(su, -2.0f), Wp1);
+            sv = fminf(fmaxf(sv, -2.0f), Hp1);
+            // one float -> int conversion per axis; the integer goes back to float on the ALU pipe (exact: |x0| <= W + 1)
+            const int x0 = __float2int_rd(su), y0 = __float2int_rd(sv);
+            const float fx0 = (float)x0, fy0 = (float)y0;
+            if ((unsigned)x0 < Wm1 && (unsigned)y0 < Hm1) {
                 // all four taps inside the image (the common case): one base offset, immediate / row offsets, raw weights
                 const float wx1 = su - fx0, wx0 = (fx0 + 1.0f) - su, wy1 = sv - fy0, wy0 = (fy0 + 1.0f) - sv;
                 const float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
@@ -167,7 +175,7 @@ __global__ void __launch_bounds__(HT) homo_fwd_kernel(const WarpParams p, const 
                     sraw = fmaf(__ldg(q0 + W + 1), w11, fmaf(__ldg(q0 + W), w10, fmaf(__ldg(q0 + 1), w01, __ldg(q0) * w00)));
                 }
             } else {
-                const HTaps t = make_htaps(su, sv, W, H);
+                const HTaps t = make_htaps(su, sv, W, H, Wp1, Hp1);
                 const float4 a = __ldg(src + t.o00), bq = __ldg(src + t.o01), cq = __ldg(src + t.o10), d = __ldg(src + t.o11);
                 const float l00 = __ldg(lg + t.o00), l01 = __ldg(lg + t.o01), l10 = __ldg(lg + t.o10), l11 = __ldg(lg + t.o11);
                 cr = hblend(a.x, bq.x, cq.x, d.x, t);
@@ -269,15 +277,16 @@ __device__ __forceinline__ float warp_reduce_scatter8(const float (&v)[8]) {
 // FUSED: the upstream gradients arrive in pd_warp_grad_out's fused form (formed here from the photometric forward's unit
 // gradient); otherwise the prologue is the plain load of g_rgb_rec / g_nll.  Two instantiations: the generic prologue
 // (pointer tests, 64-bit offsets kept live) changed the register allocation of the plane loop and cost 10 % at cfg 4.
-template <bool MIX, bool FUSED>
+template <bool MIX, bool FUSED, bool FASTRT>
 __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const float4* __restrict__ rgbx, float rcp_w, float rcp_h) {
     extern __shared__ __align__(16) float sh[];  // [N][12] parameters, then [N][9] dL/dH accumulators of the CTA
     const int N = p.d.N, W = p.d.W, H = p.d.H;
     float* gacc = sh + N * 12;
-    const int64_t pix = (int64_t)blockIdx.x * HT + threadIdx.x;
-    const int b = (int)(pix / p.hw);
-    const int rem = (int)(pix - (int64_t)b * p.hw);
+    const int b = (int)(((int64_t)blockIdx.x * HT) / p.hw);  // CTA-uniform, see homo_fwd_kernel
+    const int rem = (int)((int64_t)blockIdx.x * HT - (int64_t)b * p.hw) + (int)threadIdx.x;
+    const int64_t pix = (int64_t)b * p.hw + rem;
     const int y = rem / W, x = rem - y * W;  // W % 32 == 0: a warp stays inside one row
+    const float Wp1 = (float)(W + 1), Hp1 = (float)(H + 1);
     const int lane = threadIdx.x & 31;
     const bool want_h = p.gin.g_hmat != nullptr;
     for (int i = threadIdx.x; i < N * 12; i += HT) sh[i] = __ldg(p.in.hmat + (int64_t)b * N * 12 + i);
@@ -346,7 +355,7 @@ __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const 
         HTaps t;
         const bool act = c.m != 0.0f;  // every gradient of a masked plane carries the factor m = 0 (:580)
         if (act) {
-            t = make_htaps(rt(c.u, p.wm1, rcp_w), rt(c.v, p.hm1, rcp_h), W, H);
+            t = make_htaps(rt<FASTRT>(c.u, p.wm1, rcp_w), rt<FASTRT>(c.v, p.hm1, rcp_h), W, H, Wp1, Hp1);
             const float4 a = __ldg(src + t.o00), bq = __ldg(src + t.o01), cq = __ldg(src + t.o10), d = __ldg(src + t.o11);
             const float l00 = __ldg(lg + t.o00), l01 = __ldg(lg + t.o01), l10 = __ldg(lg + t.o10), l11 = __ldg(lg + t.o11);
             const float cr = hblend(a.x, bq.x, cq.x, d.x, t);
@@ -443,21 +452,28 @@ inline void launch_homo_fwd(const WarpParams& p, const float4* rgbx, cudaStream_
     const unsigned grid = (unsigned)((int64_t)p.d.B * p.hw / HT);
     const size_t smem = (size_t)p.d.N * 12 * sizeof(float);
     const float rw = rows_rcp(p.d.W), rh = rows_rcp(p.d.H);
-    if (p.d.mixture) homo_fwd_kernel<true><<<grid, HT, smem, st>>>(p, rgbx, rw, rh);
-    else homo_fwd_kernel<false><<<grid, HT, smem, st>>>(p, rgbx, rw, rh);
+    const bool fast = rw != 0.0f && rh != 0.0f;
+    if (p.d.mixture) {
+        if (fast) homo_fwd_kernel<true, true><<<grid, HT, smem, st>>>(p, rgbx, rw, rh);
+        else homo_fwd_kernel<true, false><<<grid, HT, smem, st>>>(p, rgbx, rw, rh);
+    } else {
+        if (fast) homo_fwd_kernel<false, true><<<grid, HT, smem, st>>>(p, rgbx, rw, rh);
+        else homo_fwd_kernel<false, false><<<grid, HT, smem, st>>>(p, rgbx, rw, rh);
+    }
 }
 
 inline void launch_homo_bwd(const WarpParams& p, const float4* rgbx, cudaStream_t st) {
     const unsigned grid = (unsigned)((int64_t)p.d.B * p.hw / HT);
     const size_t smem = (size_t)p.d.N * 21 * sizeof(float);
     const float rw = rows_rcp(p.d.W), rh = rows_rcp(p.d.H);
-    const bool fused = p.gout.g_ph_sum != nullptr;
+    const bool fused = p.gout.g_ph_sum != nullptr, fast = rw != 0.0f && rh != 0.0f;
+    auto launch = [&](auto kern) { kern<<<grid, HT, smem, st>>>(p, rgbx, rw, rh); };
     if (p.d.mixture) {
-        if (fused) homo_bwd_kernel<true, true><<<grid, HT, smem, st>>>(p, rgbx, rw, rh);
-        else homo_bwd_kernel<true, false><<<grid, HT, smem, st>>>(p, rgbx, rw, rh);
+        if (fused) fast ? launch(homo_bwd_kernel<true, true, true>) : launch(homo_bwd_kernel<true, true, false>);
+        else fast ? launch(homo_bwd_kernel<true, false, true>) : launch(homo_bwd_kernel<true, false, false>);
     } else {
-        if (fused) homo_bwd_kernel<false, true><<<grid, HT, smem, st>>>(p, rgbx, rw, rh);
-        else homo_bwd_kernel<false, false><<<grid, HT, smem, st>>>(p, rgbx, rw, rh);
+        if (fused) fast ? launch(homo_bwd_kernel<false, true, true>) : launch(homo_bwd_kernel<false, true, false>);
+        else fast ? launch(homo_bwd_kernel<false, false, true>) : launch(homo_bwd_kernel<false, false, false>);
     }
 }
 
