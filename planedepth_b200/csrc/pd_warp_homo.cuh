@@ -279,9 +279,10 @@ __device__ __forceinline__ float warp_reduce_scatter8(const float (&v)[8]) {
 // (pointer tests, 64-bit offsets kept live) changed the register allocation of the plane loop and cost 10 % at cfg 4.
 template <bool MIX, bool FUSED, bool FASTRT>
 __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const float4* __restrict__ rgbx, float rcp_w, float rcp_h) {
-    extern __shared__ __align__(16) float sh[];  // [N][12] parameters, then [N][9] dL/dH accumulators of the CTA
+    extern __shared__ __align__(16) float sh[];  // [N][12] parameters, then [HT / 32][N][9] dL/dH accumulators, one set per warp
     const int N = p.d.N, W = p.d.W, H = p.d.H;
-    float* gacc = sh + N * 12;
+    float* gacc0 = sh + N * 12;
+    float* gacc = gacc0 + (threadIdx.x >> 5) * N * 9;  // private to the warp: plain read-modify-write, no shared atomics (CAS loops)
     const int b = (int)(((int64_t)blockIdx.x * HT) / p.hw);  // CTA-uniform, see homo_fwd_kernel
     const int rem = (int)((int64_t)blockIdx.x * HT - (int64_t)b * p.hw) + (int)threadIdx.x;
     const int64_t pix = (int64_t)b * p.hw + rem;
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const 
     const int lane = threadIdx.x & 31;
     const bool want_h = p.gin.g_hmat != nullptr;
     for (int i = threadIdx.x; i < N * 12; i += HT) sh[i] = __ldg(p.in.hmat + (int64_t)b * N * 12 + i);
-    for (int i = threadIdx.x; i < N * 9; i += HT) gacc[i] = 0.0f;
+    for (int i = threadIdx.x; i < (HT / 32) * N * 9; i += HT) gacc0[i] = 0.0f;
     __syncthreads();
     const float fx = (float)x, fy = (float)y;
     const float* ik = p.in.cam + (int64_t)b * 9;
@@ -413,12 +414,12 @@ __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const 
             const float tot = warp_reduce_scatter8(v8);
             const int k = lane >> 2;
             if ((lane & 3) == 0 && k < 6 && tot != 0.0f) {
-                float* dst = gacc + n * 9;
+                float* dst = gacc + n * 9;  // the six writing lanes of a warp touch nine distinct elements
                 if (k < 3) {
-                    atomicAdd(dst + 3 * k + 2, tot);
-                    atomicAdd(dst + 3 * k + 1, tot * fy);
+                    dst[3 * k + 2] += tot;
+                    dst[3 * k + 1] += tot * fy;
                 } else {
-                    atomicAdd(dst + 3 * (k - 3), tot);
+                    dst[3 * (k - 3)] += tot;
                 }
             }
         }
@@ -427,7 +428,9 @@ __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const 
         __syncthreads();
         float* dst = p.gin.g_hmat + (int64_t)b * N * 9;
         for (int i = threadIdx.x; i < N * 9; i += HT) {
-            const float v = gacc[i];
+            float v = 0.0f;
+#pragma unroll
+            for (int w = 0; w < HT / 32; ++w) v += gacc0[w * N * 9 + i];
             if (v != 0.0f) atomicAdd(dst + i, v);
         }
     }
@@ -464,10 +467,13 @@ inline void launch_homo_fwd(const WarpParams& p, const float4* rgbx, cudaStream_
 
 inline void launch_homo_bwd(const WarpParams& p, const float4* rgbx, cudaStream_t st) {
     const unsigned grid = (unsigned)((int64_t)p.d.B * p.hw / HT);
-    const size_t smem = (size_t)p.d.N * 21 * sizeof(float);
+    const size_t smem = (size_t)p.d.N * (12 + (HT / 32) * 9) * sizeof(float);
     const float rw = rows_rcp(p.d.W), rh = rows_rcp(p.d.H);
     const bool fused = p.gout.g_ph_sum != nullptr, fast = rw != 0.0f && rh != 0.0f;
-    auto launch = [&](auto kern) { kern<<<grid, HT, smem, st>>>(p, rgbx, rw, rh); };
+    auto launch = [&](auto kern) {
+        smem_optin((const void*)kern, smem);  // N = 256 planes need 86 KB; cached per (kernel, size), no attribute call in steady state
+        kern<<<grid, HT, smem, st>>>(p, rgbx, rw, rh);
+    };
     if (p.d.mixture) {
         if (fused) fast ? launch(homo_bwd_kernel<true, true, true>) : launch(homo_bwd_kernel<true, true, false>);
         else fast ? launch(homo_bwd_kernel<true, false, true>) : launch(homo_bwd_kernel<true, false, false>);

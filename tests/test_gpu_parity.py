@@ -166,6 +166,7 @@ CONFIGS = [
     (2, 8, 8, 256, "disp_warp", False, True, [], True, dict(n_xz=3)),            # xz masks: all-zero rows above the horizon
     (1, 5, 24, 96, "homography_warp", True, True, [-1], True, dict(n_xz=2)),     # homography fast path, division-free round trip
     (2, 7, 24, 96, "homography_warp", False, False, [1], False, dict(n_xz=2)),
+    (1, 150, 8, 32, "homography_warp", False, False, [1], False, dict(n_xz=2)),  # many planes: > 48 KB of per-warp dL/dH sums
 ]
 
 
