@@ -68,9 +68,10 @@ __device__ __forceinline__ Taps make_taps(float x, float y, int W, int H) {
     Taps t;
     x = fminf(fmaxf(x, -2.0f), (float)(W + 1));
     y = fminf(fmaxf(y, -2.0f), (float)(H + 1));
-    float fx0 = floorf(x), fy0 = floorf(y);
-    t.x0 = (int)fx0;
-    t.y0 = (int)fy0;
+    // floor as ONE float -> int conversion per axis; the integer goes back to float on the ALU pipe (exact: |x0| <= size + 1)
+    t.x0 = __float2int_rd(x);
+    t.y0 = __float2int_rd(y);
+    const float fx0 = (float)t.x0, fy0 = (float)t.y0;
     t.wx1 = x - fx0;
     t.wx0 = (fx0 + 1.0f) - x;
     t.wy1 = y - fy0;

@@ -42,8 +42,8 @@ __device__ __forceinline__ float sample_shift(const float* __restrict__ plane, f
         return blend(v, t);
     }
     u = fminf(fmaxf(u, -2.0f), (float)(p.W + 1));
-    const float f0 = floorf(u);
-    const int x0 = (int)f0;
+    const int x0 = __float2int_rd(u);  // one conversion; back to float on the ALU pipe (exact: |x0| <= W + 1)
+    const float f0 = (float)x0;
     const float w1 = u - f0;
     return fmaf(px<FLIP>(plane, y, x0 + 1, p.W, p.H), w1, px<FLIP>(plane, y, x0, p.W, p.H) * (1.0f - w1));
 }
@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(1024) occlusion_row_kernel(const OcclParams p,
     extern __shared__ float erow[];  // [2][W + 2 * OC_PAD]
     const int W = p.W, N = p.N;
     const int pitch = W + 2 * OC_PAD;
+    const float Wp1 = (float)(W + 1);
     const int row = blockIdx.x, b = row / p.H, y = row - b * p.H;
     for (int i = threadIdx.x; i < 2 * pitch; i += blockDim.x) erow[i] = 0.0f;  // pads stay zero; interiors are rewritten per plane
     const float* src = P + ((int64_t)(pb + b) * N * p.H + y) * W;  // row y of plane 0; planes are hw apart
@@ -126,9 +127,9 @@ __global__ void __launch_bounds__(1024) occlusion_row_kernel(const OcclParams p,
     }
     // sample of the row of plane n at u (two taps, zero padding, optional mirror), in log2 units
     auto sample = [&](const float* r, float u) -> float {
-        u = fminf(fmaxf(u, -2.0f), (float)(W + 1));
-        const float f0 = floorf(u);
-        const int x0 = (int)f0;
+        u = fminf(fmaxf(u, -2.0f), Wp1);
+        const int x0 = __float2int_rd(u);
+        const float f0 = (float)x0;
         const float w1 = u - f0;
         const float a = ((unsigned)x0 < (unsigned)W) ? __ldg(r + (FLIP ? W - 1 - x0 : x0)) : 0.0f;
         const float c = ((unsigned)(x0 + 1) < (unsigned)W) ? __ldg(r + (FLIP ? W - 2 - x0 : x0 + 1)) : 0.0f;
@@ -160,9 +161,9 @@ __global__ void __launch_bounds__(1024) occlusion_row_kernel(const OcclParams p,
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
             float u = (float)x[k] + sign2 * __ldg(d2[k] + (int64_t)n * p.ds.n);
-            u = fminf(fmaxf(u, -2.0f), (float)(W + 1));
-            const float f0 = floorf(u);
-            const int x0 = (int)f0;  // in [-2, W+1]: both taps inside the padded row
+            u = fminf(fmaxf(u, -2.0f), Wp1);
+            const int x0 = __float2int_rd(u);  // in [-2, W+1]: both taps inside the padded row
+            const float f0 = (float)x0;
             const float w1 = u - f0;
             acc[k] = fmaf(e[x0 + 1], w1, fmaf(e[x0], 1.0f - w1, acc[k]));
         }

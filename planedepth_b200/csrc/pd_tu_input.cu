@@ -51,8 +51,8 @@ __global__ void __launch_bounds__(256) resize_bicubic_u8_kernel(const ResizePara
         const int rem = (int)(i - (int64_t)b * hw);
         const int y = rem / W, x = rem - y * W;
         const float fy = p.sy * (float)(y + p.d.y0), fx = p.sx * (float)(x + p.d.x0);
-        const float fy0 = floorf(fy), fx0 = floorf(fx);
-        const int iy = (int)fy0, ix = (int)fx0;
+        const int iy = __float2int_rd(fy), ix = __float2int_rd(fx);
+        const float fy0 = (float)iy, fx0 = (float)ix;
         float wy[4], wx[4];
         cubic_weights(fy - fy0, wy);
         cubic_weights(fx - fx0, wx);

@@ -226,8 +226,8 @@ __device__ __forceinline__ void sample_irregular(const WarpParams& p, const RowC
     for (int i = 0; i < RP; ++i) {
         float uh = roundtrip(__fadd_rn(c.xf[i], pr.sd), p.wm1);
         uh = fminf(fmaxf(uh, -2.0f), (float)(W + 1));
-        float f0 = floorf(uh);
-        int x0 = (int)f0;
+        int x0 = __float2int_rd(uh);
+        float f0 = (float)x0;
         o.w1[i] = uh - f0;
         o.w0[i] = (f0 + 1.0f) - uh;
         int xs = min(max(x0, -ROW_PAD), W + ROW_PAD - 2);  // pads are zero
@@ -459,7 +459,7 @@ __device__ __forceinline__ void gather_irregular(float wm1, const PlaneRow& pr, 
             if ((unsigned)x >= (unsigned)W) continue;
             float uh = roundtrip(__fadd_rn((float)x, pr.sd), wm1);
             uh = fminf(fmaxf(uh, -2.0f), (float)(W + 1));
-            const int ix = (int)floorf(uh);
+            const int ix = __float2int_rd(uh);
             if (ix == j) acc += e0[x];
             if (ix + 1 == j) acc += e1[x];
         }
