@@ -200,6 +200,9 @@ __global__ void __launch_bounds__(160) tail_fwd_tile_kernel(const TailParams p, 
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
+constexpr int TT_BWD_WARPS = 5;               // launch bound of the backward tile kernel: 160 threads
+constexpr int TT_BWD_HDR = 2 + TT_BWD_WARPS;  // per-plane header floats: row mask, row disparity, one gradient sum per warp
+
 template <bool MIX>
 __global__ void __launch_bounds__(160) tail_bwd_tile_kernel(const TailParams p, const int tw, const int tiles) {
     extern __shared__ __align__(128) unsigned char tt_raw[];
@@ -207,8 +210,9 @@ __global__ void __launch_bounds__(160) tail_bwd_tile_kernel(const TailParams p, 
     uint64_t* bars = reinterpret_cast<uint64_t*>(tt_raw);
     float* mrow = reinterpret_cast<float*>(tt_raw + TT_MAXG * 8);
     float* drow = mrow + N;
-    float* gacc = drow + N;  // [N] per-CTA sums of the compact disparity gradient
-    float* tile = reinterpret_cast<float*>(tt_raw + TT_MAXG * 8 + (((size_t)3 * N * 4 + 15) & ~(size_t)15));  // [N][tw] logits -> pi
+    float* gacc0 = drow + N;  // [TT_BWD_WARPS][N] sums of the compact disparity gradient, one private row per warp (a shared
+    float* gacc = gacc0 + (threadIdx.x >> 5) * N;  // float atomicAdd compiles to a compare-and-swap loop)
+    float* tile = reinterpret_cast<float*>(tt_raw + TT_MAXG * 8 + (((size_t)TT_BWD_HDR * N * 4 + 15) & ~(size_t)15));  // [N][tw] logits -> pi
     const int t = blockIdx.x % tiles;
     const int row = blockIdx.x / tiles;
     const int b = row / H, y = row - b * H;
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(160) tail_bwd_tile_kernel(const TailParams p, 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tt_stage_row_scalars(p, b, y, mrow, drow);
-    for (int n = threadIdx.x; n < N; n += blockDim.x) gacc[n] = 0.0f;
+    for (int n = threadIdx.x; n < TT_BWD_WARPS * N; n += blockDim.x) gacc0[n] = 0.0f;
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t rb = (uint32_t)tw * 4u;
@@ -342,16 +346,18 @@ __global__ void __launch_bounds__(160) tail_bwd_tile_kernel(const TailParams p, 
                     }
                 }
             }
-            if (xred) {  // reduced over x (and possibly y): warp sum, one shared atomic per warp
+            if (xred) {  // reduced over x (and possibly y): warp sum into the warp's own row
                 const float s_ = warp_sum(gdl);
-                if (lane == 0 && s_ != 0.0f) atomicAdd(gacc + n, s_);
+                if (lane == 0) gacc[n] += s_;
             }
         }
     }
     if (p.g_dl && !p.g_dl_dense && p.gds.x == 0) {
         __syncthreads();
         for (int n = threadIdx.x; n < N; n += blockDim.x) {
-            const float v = gacc[n];
+            float v = 0.0f;
+#pragma unroll
+            for (int w = 0; w < TT_BWD_WARPS; ++w) v += gacc0[w * N + n];
             if (v != 0.0f) atomicAdd(p.g_dl + soff(p.gds, b, n, y, 0), v);  // a zero y stride folds the rows as well
         }
     }

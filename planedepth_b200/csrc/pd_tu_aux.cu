@@ -100,7 +100,7 @@ int pd_plane_tail_bwd(const pd_tail_desc* d, const pd_tail_in* in, const pd_tail
         if (e != cudaSuccess) return fail(PD_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
     }
     pd::tl::TileCfg tc;
-    if (!pd::tuning().tail_direct && pd::tl::tile_cfg(p, false, 3, tc) && pd::tl::tile_ptrs_ok(p)) {
+    if (!pd::tuning().tail_direct && pd::tl::tile_cfg(p, false, pd::tl::TT_BWD_HDR, tc) && pd::tl::tile_ptrs_ok(p)) {
         const unsigned tgrid = (unsigned)((int64_t)d->B * d->H * tc.tiles);
         if (d->mixture) {
             loss_smem_optin(pd::tl::tail_bwd_tile_kernel<true>, tc.smem);
