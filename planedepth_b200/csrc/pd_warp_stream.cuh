@@ -217,7 +217,7 @@ struct Smem {
     float* sring;     // mixture: [nst*hs][rpc][pitch]
     float* mring;     // dense mask: [nst*hs][rpc][pitch]
     float* dbuf;      // backward: [2][hs][NE][rpc][pitch] exchange rows (NE = 1, mixture 2)
-    float* gacc;      // backward with d/d disp: [rpc][N]
+    float* gacc;      // backward with d/d disp: [max(rpc, consumer warps)][N] (one private row per warp when warps do not straddle rows)
     float* fend;      // one past the last float
     unsigned char* bring;  // bf16 storage: TMA ring of raw bf16 rows [nst*hs][1 + mix][rpc][(W + 2 * PADB) * 2 bytes] (behind the float region)
 };
@@ -227,7 +227,7 @@ __host__ __device__ inline size_t stream_smem_floats(const StreamCfg& c, int N, 
     const size_t streams = c.bf16 ? (dense ? 1 : 0) : (1 + (mix ? 1 : 0) + (dense ? 1 : 0));  // fp32 ring rows
     size_t f = 2 * 3 * rowf + (size_t)c.nst * c.hs * rowf * streams;
     f += (size_t)2 * c.hs * ne_bwd * rowf;
-    if (want_disp) f += (size_t)c.rpc * N;
+    if (want_disp) f += (size_t)(c.rpc > c.nc / 32 ? c.rpc : c.nc / 32) * N;
     return f;
 }
 
@@ -256,7 +256,7 @@ __device__ __forceinline__ Smem carve(unsigned char* raw, const StreamCfg& c, in
     s.dbuf = q;
     q += (size_t)2 * c.hs * ne_bwd * rowf;
     s.gacc = q;
-    if (want_disp) q += (size_t)c.rpc * N;
+    if (want_disp) q += (size_t)(c.rpc > c.nc / 32 ? c.rpc : c.nc / 32) * N;
     s.fend = q;
     s.bring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(q) + 15) & ~(uintptr_t)15);
     return s;
@@ -941,8 +941,14 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
         const bool active = (r < rpc) && (row < rows_total);
         const int b = active ? row / H : 0, y = active ? row - b * H : 0;
         const int64_t rem = (int64_t)y * W + x0;
+        // d/d disparity sums of the group.  When every warp works inside one row (tpr % 32 == 0) each warp owns a private row of
+        // sums and adds to it with plain read-modify-writes (a shared float atomicAdd compiles to a compare-and-swap loop that
+        // all warps of a row would contend for); otherwise rows are shared and the adds are atomic.
+        const bool wrows = WANT_DISP && (cfg.tpr & 31) == 0;
+        const int wpr = cfg.tpr >> 5;  // warps per row (wrows)
         if (WANT_DISP) {
-            for (int i = threadIdx.x; i < rpc * N; i += cfg.nc) s.gacc[i] = 0.0f;
+            const int nacc = (wrows ? cfg.nc / 32 : rpc) * N;
+            for (int i = threadIdx.x; i < nacc; i += cfg.nc) s.gacc[i] = 0.0f;
             consumer_sync(cfg.nc);
         }
 
@@ -1023,7 +1029,10 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
                         // warp sum when the whole warp works on one row, per-thread shared atomics otherwise
                         const int n = n0 + q;
                         const int r_first = (int)((threadIdx.x & ~31u) / cfg.tpr), r_last = (int)((threadIdx.x | 31u) / cfg.tpr);
-                        if (r_first == r_last) {
+                        if (wrows) {
+                            const float sum = warp_sum(gsum);
+                            if (lane == 0) s.gacc[(threadIdx.x >> 5) * N + n] += sum * p.d.disp_sign;
+                        } else if (r_first == r_last) {
                             const float sum = warp_sum(gsum);
                             if (lane == 0 && r < rpc && sum != 0.0f) atomicAdd(s.gacc + r * N + n, sum * p.d.disp_sign);
                         } else if (active && gsum != 0.0f) {
@@ -1068,7 +1077,12 @@ __global__ void __launch_bounds__(THREADS, MINB) rows_bwd_stream(const WarpParam
             for (int i = threadIdx.x; i < rpc * N; i += cfg.nc) {
                 const int rr = i / N, n = i - rr * N;
                 const int rw = g * rpc + rr;
-                const float v = s.gacc[i];
+                float v = 0.0f;
+                if (wrows) {
+                    for (int w = rr * wpr; w < (rr + 1) * wpr; ++w) v += s.gacc[w * N + n];
+                } else {
+                    v = s.gacc[i];
+                }
                 if (rw < rows_total && v != 0.0f) {
                     const int bb = rw / H, yy = rw - bb * H;
                     atomicAdd(p.gin.g_disp + soff(p.gin.g_disp_stride, bb, n, yy, 0), v);
