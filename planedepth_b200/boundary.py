@@ -201,7 +201,17 @@ class HotPathMixin:
         wt = _flag(opt, "warp_type", "disp_warp")
         if wt not in _WARP:
             raise ValueError("unknown warp_type %r" % (wt,))
-        for side in self.target_sides:
+        sides = list(self.target_sides)
+        homo = None
+        if wt == "homography_warp" and len(sides) > 1:
+            # the 3x3 algebra of ALL target sides in one batched call: the same per-matrix operations, a third of the tiny
+            # kernels (forward and autograd) in a step with three sides
+            S = len(sides)
+            Ts = torch.stack([outputs[("Rt", s_)] for s_ in sides], 0).reshape(S * B, 4, 4)
+            rep = lambda t: t[None].expand(S, *t.shape).reshape(S * t.shape[0], *t.shape[1:])
+            hm_all, cam_all = homography_params(rep(outputs["distance"]), rep(outputs["norm"]), Ts, rep(inputs["K"]), rep(inputs["inv_K"]))
+            homo = (hm_all.reshape(S, B * N, 12), cam_all[:B])
+        for si, side in enumerate(sides):
             disp = mask = hmat = cam = None
             sign = 0.0
             if wt == "disp_warp":
@@ -215,7 +225,10 @@ class HotPathMixin:
                     self._verify_x_constant(mask, "padding_mask")
                     mask = mask.detach()[..., :1].expand(-1, -1, -1, mask.shape[3])  # zero x stride: one value per row
             elif wt == "homography_warp":
-                hmat, cam = homography_params(outputs["distance"], outputs["norm"], outputs[("Rt", side)], inputs["K"], inputs["inv_K"])
+                if homo is not None:
+                    hmat, cam = homo[0][si], homo[1]
+                else:
+                    hmat, cam = homography_params(outputs["distance"], outputs["norm"], outputs[("Rt", side)], inputs["K"], inputs["inv_K"])
             else:
                 disp = outputs["disp_layered"]
                 mask = outputs["padding_mask"]  # upstream dereferences an unbound local here (defect D1)
