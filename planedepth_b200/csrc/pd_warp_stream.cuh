@@ -1136,8 +1136,12 @@ inline StreamCfg stream_cfg(const WarpParams& p, bool mix, bool dense, int ne_bw
     const bool narrow_plain_bwd = ne_bwd > 0 && !mix && c.nc <= 160;
     // bf16 forward: rows are half as long, so a stage of 8 planes costs what 4 cost in fp32 (measured, profiles/r2b2_*: 0.1026 -> 0.0989 ms)
     c.hs = tn.stream_hs > 0 ? tn.stream_hs : (narrow_plain_bwd ? 5 : ((c.bf16 && ne_bwd == 0) ? 8 : 4));
-    if (c.hs > p.d.N) c.hs = p.d.N;
     c.nst = tn.stream_nst > 0 ? tn.stream_nst : (narrow_plain_bwd ? 2 : 3);
+    // measured (profiles/r2v3_*): the narrow plain forward prefers blocks that divide the plane count evenly -- N = 49 as 7 blocks
+    // of 7 planes in a two-stage ring (three resident CTAs) beats 13 blocks of 4 in three stages (four CTAs) by 3 %; 8, 9 or 10
+    // planes per block (ragged last block) are slower than either
+    if (tn.stream_hs == 0 && tn.stream_nst == 0 && ne_bwd == 0 && !mix && c.nc <= 160 && p.d.N % 7 == 0) c.hs = 7, c.nst = c.bf16 ? 3 : 2;
+    if (c.hs > p.d.N) c.hs = p.d.N;
     if (c.nst > MAX_STAGES) c.nst = MAX_STAGES;
     // shrink the pipeline until the CTA fits the shared-memory budget (default: three CTAs per SM)
     // (three CTAs of <= 192 threads per SM, two of the 352-thread CTAs that wide rows need)

@@ -1,10 +1,11 @@
 #!/bin/bash
 # ring-shape sweep of the streamed kernels (planes per stage x stages) through the load-time tuning variables
-TAG=${1:-r2v}
+# usage: gpu_ring_sweep.sh TAG "hs nst" "hs nst" ...
+TAG=${1:-r2v}; shift
 O=gpurun_out
 mkdir -p $O
 B="--steps 30 --warmup 5 --no-cpu-baseline --no-ddp-leg --no-reference-gpu"
-for shape in "0 0" "2 6" "3 4" "2 4" "3 3" "3 5" "2 8" "1 8" "4 4" "0 0"; do
+for shape in "$@"; do
   set -- $shape
   PD_STREAM_HS=$1 PD_STREAM_NST=$2 python bench.py $B > $O/${TAG}_hs$1_nst$2.json 2>/dev/null
   python - <<PY
