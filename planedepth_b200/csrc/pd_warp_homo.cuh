@@ -13,6 +13,8 @@
 //     instead of 45 butterfly shuffles, accumulated per CTA in shared memory, flushed once.
 // PD_FLAG_EXACT_COORDS keeps the general kernels (IEEE divisions).
 #pragma once
+#include <type_traits>
+
 #include "pd_warp_general.cuh"
 
 namespace pd {
@@ -288,6 +290,7 @@ __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const 
     const int64_t pix = (int64_t)b * p.hw + rem;
     const int y = rem / W, x = rem - y * W;  // W % 32 == 0: a warp stays inside one row
     const float Wp1 = (float)(W + 1), Hp1 = (float)(H + 1);
+    const unsigned Wm1 = (unsigned)(W - 1), Hm1 = (unsigned)(H - 1);
     const int lane = threadIdx.x & 31;
     const bool want_h = p.gin.g_hmat != nullptr;
     for (int i = threadIdx.x; i < N * 12; i += HT) sh[i] = __ldg(p.in.hmat + (int64_t)b * N * 12 + i);
@@ -352,11 +355,13 @@ __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const 
         float4 h0, h1, h2;
         load_plane_params(sh, n, h0, h1, h2);
         const HCoord c = homo_coords(h0, h1, h2, fx, fy, rx, ry, rz);
-        float gqx = 0.0f, gqy = 0.0f, gqz = 0.0f, dl = 0.0f, dsg = 0.0f;
-        HTaps t;
-        const bool act = c.m != 0.0f;  // every gradient of a masked plane carries the factor m = 0 (:580)
-        if (act) {
-            t = make_htaps(rt<FASTRT>(c.u, p.wm1, rcp_w), rt<FASTRT>(c.v, p.hm1, rcp_h), W, H, Wp1, Hp1);
+        float gqx = 0.0f, gqy = 0.0f, gqz = 0.0f;
+        // One sample: loads, blends, the gradients of the logit / sigma / colour taps, the scatter and (want_h) the coordinate
+        // gradient.  Instantiated twice: ALL_IN = every tap inside the image (the common case: raw weights, no per-tap selects,
+        // unconditional reductions) and the general form with clamped addresses and zeroed weights.
+        auto sample = [&](const HTaps& t, auto all_in) {
+            constexpr bool ALL_IN = decltype(all_in)::value;
+            float dl = 0.0f, dsg = 0.0f;
             const float4 a = __ldg(src + t.o00), bq = __ldg(src + t.o01), cq = __ldg(src + t.o10), d = __ldg(src + t.o11);
             const float l00 = __ldg(lg + t.o00), l01 = __ldg(lg + t.o01), l10 = __ldg(lg + t.o10), l11 = __ldg(lg + t.o11);
             const float cr = hblend(a.x, bq.x, cq.x, d.x, t);
@@ -397,17 +402,48 @@ __global__ void __launch_bounds__(HT) homo_bwd_kernel(const WarpParams p, const 
                 float tsw = fmaf(dcr, cq.x, fmaf(dcg, cq.y, fmaf(dcb, cq.z, dl * l10)));
                 float tse = fmaf(dcr, d.x, fmaf(dcg, d.y, fmaf(dcb, d.z, dl * l11)));
                 if (MIX) tnw = fmaf(dsg, s00, tnw), tne = fmaf(dsg, s01, tne), tsw = fmaf(dsg, s10, tsw), tse = fmaf(dsg, s11, tse);
-                tnw = (t.ix0 && t.iy0) ? tnw : 0.0f, tne = (t.ix1 && t.iy0) ? tne : 0.0f;
-                tsw = (t.ix0 && t.iy1) ? tsw : 0.0f, tse = (t.ix1 && t.iy1) ? tse : 0.0f;
+                if constexpr (!ALL_IN) {
+                    tnw = (t.ix0 && t.iy0) ? tnw : 0.0f, tne = (t.ix1 && t.iy0) ? tne : 0.0f;
+                    tsw = (t.ix0 && t.iy1) ? tsw : 0.0f, tse = (t.ix1 && t.iy1) ? tse : 0.0f;
+                }
                 const float gx = (tne - tnw) * t.ry0 + (tse - tsw) * t.ry1;
                 const float gy = (tsw - tnw) * t.rx0 + (tse - tne) * t.rx1;
                 // u = qx / zc, v = qy / zc, zc = max(qz, 1e-7)   (layers.py:227-228)
                 gqx = gx * c.zinv, gqy = gy * c.zinv;
                 gqz = -(gx * c.u + gy * c.v) * c.zinv * c.dz;
             }
+            if constexpr (ALL_IN) {
+                // four in-image taps: reductions without the per-tap zero tests (a zero weight adds an exact zero)
+                if (glg && dl != 0.0f) {
+                    atomicAdd(glg + t.o00, dl * t.w00), atomicAdd(glg + t.o01, dl * t.w01);
+                    atomicAdd(glg + t.o10, dl * t.w10), atomicAdd(glg + t.o11, dl * t.w11);
+                }
+                if (MIX && gsg && dsg != 0.0f) {
+                    atomicAdd(gsg + t.o00, dsg * t.w00), atomicAdd(gsg + t.o01, dsg * t.w01);
+                    atomicAdd(gsg + t.o10, dsg * t.w10), atomicAdd(gsg + t.o11, dsg * t.w11);
+                }
+            } else {
+                if (glg && dl != 0.0f) hscatter(glg, t, dl);
+                if (MIX && gsg && dsg != 0.0f) hscatter(gsg, t, dsg);
+            }
+        };
+        if (c.m != 0.0f) {  // every gradient of a masked plane carries the factor m = 0 (:580)
+            float su = rt<FASTRT>(c.u, p.wm1, rcp_w), sv = rt<FASTRT>(c.v, p.hm1, rcp_h);
+            su = fminf(fmaxf(su, -2.0f), Wp1);
+            sv = fminf(fmaxf(sv, -2.0f), Hp1);
+            const int x0 = __float2int_rd(su), y0 = __float2int_rd(sv);
+            if ((unsigned)x0 < Wm1 && (unsigned)y0 < Hm1) {
+                const float fx0 = (float)x0, fy0 = (float)y0;
+                HTaps t;
+                t.rx1 = su - fx0, t.rx0 = (fx0 + 1.0f) - su, t.ry1 = sv - fy0, t.ry0 = (fy0 + 1.0f) - sv;
+                t.ix0 = t.ix1 = t.iy0 = t.iy1 = true;
+                t.o00 = y0 * W + x0, t.o01 = t.o00 + 1, t.o10 = t.o00 + W, t.o11 = t.o10 + 1;
+                t.w00 = t.rx0 * t.ry0, t.w01 = t.rx1 * t.ry0, t.w10 = t.rx0 * t.ry1, t.w11 = t.rx1 * t.ry1;
+                sample(t, std::true_type{});
+            } else {
+                sample(make_htaps(su, sv, W, H, Wp1, Hp1), std::false_type{});
+            }
         }
-        if (act && glg && dl != 0.0f) hscatter(glg, t, dl);
-        if (MIX && act && gsg && dsg != 0.0f) hscatter(gsg, t, dsg);
         if (want_h) {
             // dL/dH[i][j] = sum_pixels gq_i * (x, y, 1)_j; y is the same for the whole warp
             const float v8[8] = {gqx, gqy, gqz, gqx * fx, gqy * fx, gqz * fx, 0.0f, 0.0f};
