@@ -64,7 +64,12 @@ typedef enum pd_mask_dtype { PD_MASK_NONE = 0, PD_MASK_F32 = 1, PD_MASK_U8 = 2 }
  * homography / depth warps and dense disparities always use the reference's arithmetic. */
 /* PD_FLAG_NO_MASK_SUMMARY: the streamed forward does not summarise a dense padding_mask per row (the saved
  * statistics then say "read every mask row" and the backward streams the mask again); a measurement knob. */
-typedef enum pd_warp_flags { PD_FLAG_EXACT_COORDS = 1, PD_FLAG_NO_MASK_SUMMARY = 2 } pd_warp_flags;
+/* PD_FLAG_ACCUMULATE (pd_warp_composite_bwd only): g_logits / g_sigma are ADDED to instead of being zero-filled first, so that
+ * the target sides of one step (trainer.py:528: for side in self.target_sides) scatter into one caller-zeroed buffer -- what
+ * autograd otherwise does with one [B,N,H,W] add per extra side.  Only the scatter kernels can do that (homography / depth
+ * warps, x-varying disparity); a descriptor served by kernels that WRITE their gradient rows (streamed / bit-faithful stereo
+ * kernels) answers PD_ERR_UNSUPPORTED. */
+typedef enum pd_warp_flags { PD_FLAG_EXACT_COORDS = 1, PD_FLAG_NO_MASK_SUMMARY = 2, PD_FLAG_ACCUMULATE = 4 } pd_warp_flags;
 
 /* Storage type of the [B,N,H,W] network outputs and of their gradients (pd_warp_desc.dtype): logits, sigma, g_logits,
  * g_sigma.  Everything else (colours, rgb_rec, statistics, nll, plane geometry, masks) is fp32 whatever this says, and all

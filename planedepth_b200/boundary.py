@@ -27,7 +27,8 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib as L
-from .functional import WarpConfig, occlusion_masks, photometric_loss, plane_tail, smooth_loss, warp_composite
+from . import functional as _fn
+from .functional import WarpConfig, occlusion_masks, photometric_loss, plane_tail, smooth_loss, warp_composite, warp_composite_sides
 
 _WARP = {"disp_warp": L.PD_WARP_DISP, "homography_warp": L.PD_WARP_HOMOGRAPHY, "depth_warp": L.PD_WARP_DEPTH}
 
@@ -211,6 +212,19 @@ class HotPathMixin:
             rep = lambda t: t[None].expand(S, *t.shape).reshape(S * t.shape[0], *t.shape[1:])
             hm_all, cam_all = homography_params(rep(outputs["distance"]), rep(outputs["norm"]), Ts, rep(inputs["K"]), rep(inputs["inv_K"]))
             homo = (hm_all.reshape(S, B * N, 12), cam_all[:B])
+            if not self.materialize_layered and not self.exact_coords and _fn.FUSE_PHOTOMETRIC_BWD != "all":
+                # ... and all sides through ONE autograd node, whose backward lets every side's scatter kernel add into the same
+                # zero-filled gradient buffers (functional._WarpCompositeSides) instead of leaving the sum to autograd
+                cfg = WarpConfig(warp_type=_WARP[wt], mixture=mixture, automask=automask, disp_sign=0.0, shape=(B, N, H, W))
+                res = warp_composite_sides(cfg, src, [inputs[(color, s_)] if mixture else None for s_ in sides], outputs["logits"],
+                                           outputs.get("sigma") if mixture else None, [homo[0][i] for i in range(S)], homo[1])
+                for side, (rgb_rec, nll, nll_auto) in zip(sides, res):
+                    outputs[("rgb_rec", side)] = rgb_rec
+                    if mixture:
+                        outputs[("nll_rec", side)] = nll
+                        if automask:
+                            outputs[("nll_auto_rec", side)] = nll_auto
+                return
         for si, side in enumerate(sides):
             disp = mask = hmat = cam = None
             sign = 0.0

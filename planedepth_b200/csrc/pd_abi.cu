@@ -335,8 +335,12 @@ int pd_warp_composite_bwd(const pd_warp_desc* d, const pd_warp_in* in, const pd_
     const bool streamed = !exact_coords(d) && api::stream_supported(p) && api::stream_bwd_fits(p);
     if (d->dtype == PD_DTYPE_BF16 && !streamed) return fail(PD_ERR_UNSUPPORTED, "bf16 storage is served by the streamed stereo kernels only (see pd_warp_composite_supports)");
     const bool rows = !streamed && api::rows_supported(p);
-    // scatter targets are accumulated with atomics in the general / homography paths: zero them first
-    if (!streamed && !rows) {
+    const bool accumulate = (d->flags & PD_FLAG_ACCUMULATE) != 0;
+    if (accumulate && (streamed || rows))
+        return fail(PD_ERR_UNSUPPORTED, "PD_FLAG_ACCUMULATE: this descriptor is served by kernels that write their gradient rows");
+    // scatter targets are accumulated with atomics in the general / homography paths: zero them first (unless the caller
+    // accumulates several target sides into buffers it zeroed itself)
+    if (!streamed && !rows && !accumulate) {
         if (p.gin.g_logits) e = cudaMemsetAsync(p.gin.g_logits, 0, plane_bytes, st);
         if (e == cudaSuccess && p.gin.g_sigma) e = cudaMemsetAsync(p.gin.g_sigma, 0, plane_bytes, st);
     }

@@ -231,6 +231,93 @@ class _WarpComposite(torch.autograd.Function):
         return (None, None, None, None, g_logits, g_sigma, g_disp, None, g_hmat, None)
 
 
+class _WarpCompositeSides(torch.autograd.Function):
+    """pd_warp_composite_fwd / _bwd for ALL target sides of a homography warp in one autograd node (trainer.py:528-603: the loop
+    over ``self.target_sides``).  The forward is the per-side call; the backward zero-fills ``g_logits`` / ``g_sigma`` once and
+    lets every side's scatter kernel add into them (``PD_FLAG_ACCUMULATE``) -- per-side nodes leave that sum to autograd, which
+    costs one [B,N,H,W] zero-fill and one [B,N,H,W] add per extra side."""
+
+    @staticmethod
+    def forward(ctx, cfg: WarpConfig, nsides: int, src, logits, sigma, cam, *per_side):
+        lib = L.lib()
+        ctx.set_materialize_grads(False)
+        B, N, H, W = cfg.shape
+        dev = logits.device
+        tgts, hmats = per_side[:nsides], per_side[nsides:]
+        desc = _warp_desc(cfg, None, None)
+        saved, outs = [], []
+        for s_ in range(nsides):
+            tin = L.WarpIn(src=_ptr(src), tgt=_ptr(tgts[s_]), logits=_ptr(logits), sigma=_ptr(sigma), hmat=_ptr(hmats[s_]), cam=_ptr(cam))
+            rgb_rec = torch.empty(B, 3, H, W, device=dev, dtype=torch.float32)
+            stats = torch.empty((lib.pd_warp_composite_stats_bytes(C.byref(desc)) + 3) // 4, device=dev, dtype=torch.float32)
+            nll = torch.empty(B, 1, H, W, device=dev, dtype=torch.float32) if cfg.mixture else torch.empty(0, device=dev)
+            nll_auto = torch.empty(B, 1, H, W, device=dev, dtype=torch.float32) if (cfg.mixture and cfg.automask) else torch.empty(0, device=dev)
+            out = L.WarpOut(rgb_rec=_ptr(rgb_rec), stats=_ptr(stats), nll=_ptr(nll if cfg.mixture else None),
+                            nll_auto=_ptr(nll_auto if (cfg.mixture and cfg.automask) else None))
+            _call("pd_warp_composite_fwd", lib.pd_warp_composite_fwd, C.byref(desc), C.byref(tin), C.byref(out), _ptr(_workspace(lib, desc, dev)), _stream())
+            saved += [rgb_rec, stats]
+            outs += [rgb_rec, nll, nll_auto]
+            ctx.mark_non_differentiable(nll_auto)
+            if not cfg.mixture:
+                ctx.mark_non_differentiable(nll)
+        ctx.cfg, ctx.desc, ctx.nsides = cfg, desc, nsides
+        ctx.save_for_backward(src, logits, sigma, cam, *tgts, *hmats, *saved)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        lib = L.lib()
+        cfg, S = ctx.cfg, ctx.nsides
+        B, N, H, W = cfg.shape
+        t = ctx.saved_tensors
+        src, logits, sigma, cam = t[:4]
+        tgts, hmats, saved = t[4:4 + S], t[4 + S:4 + 2 * S], t[4 + 2 * S:]
+        dev = logits.device
+        need = ctx.needs_input_grad  # (cfg, nsides, src, logits, sigma, cam, tgt x S, hmat x S)
+        g_logits = torch.zeros_like(logits) if need[3] else None
+        g_sigma = torch.zeros_like(sigma) if (cfg.mixture and sigma is not None and need[4]) else None
+        desc = L.WarpDesc.from_buffer_copy(ctx.desc)
+        desc.flags |= L.PD_FLAG_ACCUMULATE
+        g_hmats = [None] * S
+        for s_ in range(S):
+            g_rgb, g_nll = grads[3 * s_], grads[3 * s_ + 1]
+            g_nll = _f32c(g_nll, "grad nll") if (cfg.mixture and g_nll is not None and g_nll.numel()) else None
+            if g_rgb is None and g_nll is None:
+                continue  # this side's outputs did not reach the loss
+            rgb_rec, stats = saved[2 * s_], saved[2 * s_ + 1]
+            g_rgb = torch.zeros_like(rgb_rec) if g_rgb is None else _f32c(g_rgb, "grad rgb_rec")
+            tin = L.WarpIn(src=_ptr(src), tgt=_ptr(tgts[s_]), logits=_ptr(logits), sigma=_ptr(sigma), hmat=_ptr(hmats[s_]), cam=_ptr(cam))
+            sv = L.WarpOut(rgb_rec=_ptr(rgb_rec), stats=_ptr(stats))
+            gout = L.WarpGradOut(g_rgb_rec=_ptr(g_rgb), g_nll=_ptr(g_nll))
+            gin = L.WarpGradIn(g_logits=_ptr(g_logits), g_sigma=_ptr(g_sigma))
+            g9 = None
+            if need[6 + S + s_]:
+                g9 = torch.empty(B * N, 9, device=dev, dtype=torch.float32)
+                gin.g_hmat = g9.data_ptr()
+            _call("pd_warp_composite_bwd", lib.pd_warp_composite_bwd, C.byref(desc), C.byref(tin), C.byref(sv), C.byref(gout), C.byref(gin),
+                  _ptr(_workspace(lib, desc, dev)), _stream())
+            if g9 is not None:
+                g_hmats[s_] = torch.cat([g9, torch.zeros(B * N, 3, device=dev)], 1)
+        return (None, None, None, g_logits, g_sigma, None) + (None,) * S + tuple(g_hmats)
+
+
+def warp_composite_sides(cfg: WarpConfig, src, tgts, logits, sigma, hmats, cam):
+    """Homography warp of several target sides through one autograd node (see _WarpCompositeSides).
+    Returns a list of (rgb_rec, nll | None, nll_auto | None) per side."""
+    S = len(hmats)
+    src = _f32c(src, "src").detach()
+    logits = _f32c(logits, "logits")
+    sigma = _f32c(sigma, "sigma") if cfg.mixture else None
+    tg = [(_f32c(t_, "tgt").detach() if (cfg.mixture and t_ is not None) else None) for t_ in tgts]
+    hm = [_f32c(h_, "hmat") for h_ in hmats]
+    outs = _WarpCompositeSides.apply(cfg, S, src, logits, sigma, _f32c(cam, "cam").detach(), *tg, *hm)
+    res = []
+    for s_ in range(S):
+        rgb_rec, nll, nll_auto = outs[3 * s_:3 * s_ + 3]
+        res.append((rgb_rec, nll if cfg.mixture else None, nll_auto if (cfg.mixture and cfg.automask) else None))
+    return res
+
+
 def _warp_desc(cfg: WarpConfig, disp, mask):
     B, N, H, W = cfg.shape
     desc = L.WarpDesc(B=B, N=N, H=H, W=W, warp_type=cfg.warp_type, mixture=int(cfg.mixture), automask=int(cfg.automask),
