@@ -754,3 +754,29 @@ def test_decoder_tail_matches_oracle(mix, layout, shape, direct):
             continue
         scale = float(b_.grad.abs().max()) + 1e-12
         check(a.grad, b_.grad, (5e-4 if nm == "base" else TOL) * scale, "grad_" + nm, allow_frac=2e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("idx", [4, 5])
+def test_homography_sides_share_one_gradient_buffer(idx):
+    """Several homography target sides run through ONE autograd node whose backward lets every side's scatter kernel add into
+    the same zero-filled g_logits / g_sigma (PD_FLAG_ACCUMULATE); the per-side nodes (autograd sums the sides) must give the
+    same losses and gradients."""
+    from planedepth_b200.boundary import HotPath
+
+    cfg = CONFIGS[idx]
+    res = {}
+    for per_side in (False, True):
+        cg = build_on("cuda", cfg, seed=900 + idx)
+        # the layered outputs are a per-side feature: asking for them forces one autograd node per side
+        hp = HotPath(cg.opt, cg.target_sides, pc_net=pyramid_features, materialize_layered=per_side)
+        losses = hp.process(cg.inputs, cg.outputs)
+        losses["loss/total_loss"].backward()
+        torch.cuda.synchronize()
+        res[per_side] = (float(losses["loss/total_loss"]), {k: v.grad.clone() for k, v in cg.leaves.items() if v.grad is not None})
+    assert len(cfg[7]) + 1 >= 2  # stereo side + at least one frame
+    assert abs(res[False][0] - res[True][0]) <= 1e-6 * max(1.0, abs(res[True][0]))
+    for k, g in res[True][1].items():
+        scale = float(g.abs().max()) + 1e-12
+        # same kernels, same inputs: only the summation order of the sides differs (atomics into one buffer vs autograd's adds)
+        assert float((res[False][1][k] - g).abs().max()) <= 2e-5 * scale, k
