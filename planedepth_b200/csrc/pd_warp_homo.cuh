@@ -10,7 +10,11 @@
 //     keeps the reference's fp32 rounding (division-free form where the size allows it);
 //   * backward: the 9 sums of dL/dH per (plane, warp) shrink to 6 (a warp works inside one row, so the
 //     y-weighted sums are y times the plain ones) and are reduced with a 9-shuffle reduce-scatter
-//     instead of 45 butterfly shuffles, accumulated per CTA in shared memory, flushed once.
+//     instead of 45 butterfly shuffles, accumulated per WARP in shared memory (plain read-modify-writes:
+//     a shared float atomicAdd is a compare-and-swap loop), summed and flushed once per CTA;
+//   * per-sample overhead: the image index is CTA-uniform (blockIdx), the round-trip variant is a launch-time
+//     template parameter, floor() is one float->int conversion, and both passes instantiate the sample body
+//     twice: all four taps inside the image (raw weights, no per-tap tests) and the general clamped form.
 // PD_FLAG_EXACT_COORDS keeps the general kernels (IEEE divisions).
 #pragma once
 #include <type_traits>
