@@ -69,7 +69,10 @@ typedef enum pd_mask_dtype { PD_MASK_NONE = 0, PD_MASK_F32 = 1, PD_MASK_U8 = 2 }
  * autograd otherwise does with one [B,N,H,W] add per extra side.  Only the scatter kernels can do that (homography / depth
  * warps, x-varying disparity); a descriptor served by kernels that WRITE their gradient rows (streamed / bit-faithful stereo
  * kernels) answers PD_ERR_UNSUPPORTED. */
-typedef enum pd_warp_flags { PD_FLAG_EXACT_COORDS = 1, PD_FLAG_NO_MASK_SUMMARY = 2, PD_FLAG_ACCUMULATE = 4 } pd_warp_flags;
+/* PD_FLAG_WORKSPACE_READY: the workspace already holds what an earlier call with the same `src` and shape left there (the
+ * homography fast path's packed rgbx copy of the source image), so the call does not rebuild it: the target sides of a step
+ * share the source frame (trainer.py:567). */
+typedef enum pd_warp_flags { PD_FLAG_EXACT_COORDS = 1, PD_FLAG_NO_MASK_SUMMARY = 2, PD_FLAG_ACCUMULATE = 4, PD_FLAG_WORKSPACE_READY = 8 } pd_warp_flags;
 
 /* Storage type of the [B,N,H,W] network outputs and of their gradients (pd_warp_desc.dtype): logits, sigma, g_logits,
  * g_sigma.  Everything else (colours, rgb_rec, statistics, nll, plane geometry, masks) is fp32 whatever this says, and all

@@ -23,6 +23,7 @@ PD_MASK_NONE, PD_MASK_F32, PD_MASK_U8 = 0, 1, 2
 PD_FLAG_EXACT_COORDS = 1
 PD_FLAG_NO_MASK_SUMMARY = 2
 PD_FLAG_ACCUMULATE = 4
+PD_FLAG_WORKSPACE_READY = 8
 ABI_VERSION = 9  # PD_ABI_VERSION in include/planedepth_b200.h
 PD_STATS_PLAIN, PD_STATS_MIXTURE = 2, 4
 PD_DTYPE_F32, PD_DTYPE_BF16 = 0, 1

@@ -10,17 +10,21 @@ size_t homo_workspace_bytes(const pd_warp_desc* d) {
 }
 int homo_fwd(const WarpParams& p, void* workspace, cudaStream_t st) {
     if (!workspace) return fail(PD_ERR_WORKSPACE, "homography warp needs the workspace of pd_warp_composite_workspace_bytes()");
-    hm::homo_pack(p, (float4*)workspace, st);
-    int rc = check_launch("pack_rgbx");
-    if (rc) return rc;
+    if (!(p.d.flags & PD_FLAG_WORKSPACE_READY)) {
+        hm::homo_pack(p, (float4*)workspace, st);
+        int rc = check_launch("pack_rgbx");
+        if (rc) return rc;
+    }
     hm::launch_homo_fwd(p, (const float4*)workspace, st);
     return check_launch("homo_fwd");
 }
 int homo_bwd(const WarpParams& p, void* workspace, cudaStream_t st) {
     if (!workspace) return fail(PD_ERR_WORKSPACE, "homography warp needs the workspace of pd_warp_composite_workspace_bytes()");
-    hm::homo_pack(p, (float4*)workspace, st);
-    int rc = check_launch("pack_rgbx");
-    if (rc) return rc;
+    if (!(p.d.flags & PD_FLAG_WORKSPACE_READY)) {
+        hm::homo_pack(p, (float4*)workspace, st);
+        int rc = check_launch("pack_rgbx");
+        if (rc) return rc;
+    }
     hm::launch_homo_bwd(p, (const float4*)workspace, st);
     return check_launch("homo_bwd");
 }

@@ -245,6 +245,9 @@ class _WarpCompositeSides(torch.autograd.Function):
         dev = logits.device
         tgts, hmats = per_side[:nsides], per_side[nsides:]
         desc = _warp_desc(cfg, None, None)
+        ws = _workspace(lib, desc, dev)  # the homography fast path's packed copy of `src`: built by the first side, reused by the rest
+        ready = L.WarpDesc.from_buffer_copy(desc)
+        ready.flags |= L.PD_FLAG_WORKSPACE_READY
         saved, outs = [], []
         for s_ in range(nsides):
             tin = L.WarpIn(src=_ptr(src), tgt=_ptr(tgts[s_]), logits=_ptr(logits), sigma=_ptr(sigma), hmat=_ptr(hmats[s_]), cam=_ptr(cam))
@@ -254,13 +257,13 @@ class _WarpCompositeSides(torch.autograd.Function):
             nll_auto = torch.empty(B, 1, H, W, device=dev, dtype=torch.float32) if (cfg.mixture and cfg.automask) else torch.empty(0, device=dev)
             out = L.WarpOut(rgb_rec=_ptr(rgb_rec), stats=_ptr(stats), nll=_ptr(nll if cfg.mixture else None),
                             nll_auto=_ptr(nll_auto if (cfg.mixture and cfg.automask) else None))
-            _call("pd_warp_composite_fwd", lib.pd_warp_composite_fwd, C.byref(desc), C.byref(tin), C.byref(out), _ptr(_workspace(lib, desc, dev)), _stream())
+            _call("pd_warp_composite_fwd", lib.pd_warp_composite_fwd, C.byref(desc if s_ == 0 else ready), C.byref(tin), C.byref(out), _ptr(ws), _stream())
             saved += [rgb_rec, stats]
             outs += [rgb_rec, nll, nll_auto]
             ctx.mark_non_differentiable(nll_auto)
             if not cfg.mixture:
                 ctx.mark_non_differentiable(nll)
-        ctx.cfg, ctx.desc, ctx.nsides = cfg, desc, nsides
+        ctx.cfg, ctx.desc, ctx.nsides, ctx.ws = cfg, desc, nsides, ws  # ws stays private to this node until its backward has run
         ctx.save_for_backward(src, logits, sigma, cam, *tgts, *hmats, *saved)
         return tuple(outs)
 
@@ -277,7 +280,7 @@ class _WarpCompositeSides(torch.autograd.Function):
         g_logits = torch.zeros_like(logits) if need[3] else None
         g_sigma = torch.zeros_like(sigma) if (cfg.mixture and sigma is not None and need[4]) else None
         desc = L.WarpDesc.from_buffer_copy(ctx.desc)
-        desc.flags |= L.PD_FLAG_ACCUMULATE
+        desc.flags |= L.PD_FLAG_ACCUMULATE | (L.PD_FLAG_WORKSPACE_READY if ctx.ws is not None else 0)
         g_hmats = [None] * S
         for s_ in range(S):
             g_rgb, g_nll = grads[3 * s_], grads[3 * s_ + 1]
@@ -295,7 +298,7 @@ class _WarpCompositeSides(torch.autograd.Function):
                 g9 = torch.empty(B * N, 9, device=dev, dtype=torch.float32)
                 gin.g_hmat = g9.data_ptr()
             _call("pd_warp_composite_bwd", lib.pd_warp_composite_bwd, C.byref(desc), C.byref(tin), C.byref(sv), C.byref(gout), C.byref(gin),
-                  _ptr(_workspace(lib, desc, dev)), _stream())
+                  _ptr(ctx.ws), _stream())
             if g9 is not None:
                 g_hmats[s_] = torch.cat([g9, torch.zeros(B * N, 3, device=dev)], 1)
         return (None, None, None, g_logits, g_sigma, None) + (None,) * S + tuple(g_hmats)
