@@ -139,3 +139,14 @@ def test_no_per_call_environment_reads():
                 if "getenv(" in line and not line.lstrip().startswith("//"):
                     hits.append((f, i))
     assert [f for f, _ in hits] == ["pd_abi.cu"], hits
+
+
+def test_python_constants_match_the_header_enums():
+    """The flag / status / dtype values the ctypes binding uses are the header's (a renumbered enum would otherwise pass unnoticed)."""
+    txt = open(HEADER).read()
+    found = dict((k, int(v)) for k, v in re.findall(r"\b(PD_[A-Z0-9_]+)\s*=\s*(\d+)", txt))
+    for name in ("PD_FLAG_EXACT_COORDS", "PD_FLAG_NO_MASK_SUMMARY", "PD_FLAG_ACCUMULATE", "PD_FLAG_WORKSPACE_READY", "PD_WARP_DISP",
+                 "PD_WARP_HOMOGRAPHY", "PD_WARP_DEPTH", "PD_LOSS_L1", "PD_LOSS_MIXTURE", "PD_LOSS_SSIM_L1", "PD_MASK_NONE", "PD_MASK_F32",
+                 "PD_MASK_U8", "PD_DTYPE_F32", "PD_DTYPE_BF16"):
+        assert name in found, name
+        assert getattr(L, name) == found[name], name
